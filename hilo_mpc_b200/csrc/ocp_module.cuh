@@ -1,0 +1,118 @@
+// C entry points of one generated OCP module (one .so per transcribed problem, built by hilo_mpc_b200/codegen.py).
+// The core library (hilo_b200.cu) dlopens the module and forwards hb_ocp_* calls to these hbm_* symbols.
+#pragma once
+#include "ocp_kernels.cuh"
+#include "../../include/hilo_b200.h"
+
+namespace hb {
+
+struct OcpCount {
+  static HB_HD void run(const OcpArgs& a, int b) {
+    if (a.st[(long long)b * ST_COUNT + ST_ACTIVE] != 0.0) {
+#if HB_DEVICE_BUILD && defined(__CUDA_ARCH__)
+      atomicAdd(a.iters + a.B, 1);  // slot B of the iters array is the active counter
+#else
+      a.iters[a.B] += 1;
+#endif
+    }
+  }
+};
+
+template <class P>
+struct OcpModule {
+  using T = OcpT<P>;
+
+  static void dims(hb_ocp_dims* d) {
+    d->nx = T::NX; d->nu = T::NU; d->N = T::N; d->nc = T::NC; d->nsp = T::NSP; d->ntp = T::NTP;
+    d->nuold = T::NUOLD; d->nap = T::NAP; d->stage_doubles = T::SD; d->elim_doubles = T::TD;
+    d->method = P::METHOD; d->fixed_x0 = P::FIXED_X0 ? 1 : 0; d->n_state = ST_COUNT;
+  }
+
+  // doubles of workspace needed for a batch of B instances with n_alpha line-search candidates
+  static size_t work_doubles(int B, int n_alpha) {
+    const size_t b = (size_t)B, n1 = T::N + 1, n = T::N;
+    size_t w = 0;
+    w += 2 * b * n1 * T::NX + 2 * b * n * T::NU + 2 * b * n * T::NC;       // z multipliers
+    w += b * n * T::SD + b * T::SDN + b * n * T::TD + b * n * T::KD;       // qp, qpN, el, fb
+    w += b * n1 * T::NX + b * n * T::NU + b * n * T::NC;                   // dx, du, dxc
+    w += 7 * b * n1;                                                       // per-node scalars
+    w += 2 * b * (size_t)n_alpha * n1;                                     // line-search table
+    w += b * ST_COUNT;                                                     // state
+    return w + 64;
+  }
+
+  static int solve(const hb_ocp_call* c) {
+    if (c == nullptr || c->B <= 0) return -1;
+    if (c->work == nullptr || c->work_doubles < work_doubles(c->B, c->n_alpha)) return -2;
+    if (c->n_alpha < 1 || c->n_alpha > 32) return -3;
+    OcpArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = c->B; a.n_alpha = c->n_alpha; a.max_iter = c->max_iter;
+    a.tol = c->tol; a.acc_tol = c->acc_tol; a.mu_init = c->mu_init; a.mu_min = c->mu_min;
+    a.time0 = c->time0; a.dt = c->dt;
+    a.x0 = c->x0; a.sp = c->sp; a.sp_stride = c->sp_stride; a.tp = c->tp; a.tp_stride = c->tp_stride;
+    a.uold = c->uold; a.uold_stride = c->uold_stride; a.ap = c->ap; a.ap_stride = c->ap_stride;
+    a.xlb = c->xlb; a.xub = c->xub; a.ulb = c->ulb; a.uub = c->uub;
+    a.x = c->x; a.u = c->u; a.xc = c->xc; a.lam = c->lam;
+    a.status = c->status; a.iters = c->iters;
+    const size_t b = (size_t)c->B, n1 = T::N + 1, n = T::N;
+    double* w = c->work;
+    auto take = [&](size_t cnt) { double* p = w; w += cnt; return p; };
+    a.zlx = take(b * n1 * T::NX); a.zux = take(b * n1 * T::NX);
+    a.zlu = take(b * n * T::NU); a.zuu = take(b * n * T::NU);
+    a.zlc = take(b * n * T::NC); a.zuc = take(b * n * T::NC);
+    a.qp = take(b * n * T::SD); a.qpN = take(b * T::SDN); a.el = take(b * n * T::TD); a.fb = take(b * n * T::KD);
+    a.dx = take(b * n1 * T::NX); a.du = take(b * n * T::NU); a.dxc = take(b * n * T::NC);
+    a.s_cinf = take(b * n1); a.s_c1 = take(b * n1); a.s_phi = take(b * n1); a.s_comp = take(b * n1);
+    a.s_ap = take(b * n1); a.s_ad = take(b * n1); a.s_dphi = take(b * n1);
+    a.ls_phi = take(b * (size_t)c->n_alpha * n1); a.ls_c1 = take(b * (size_t)c->n_alpha * n1);
+    a.st = take(b * ST_COUNT);
+    cudaStream_t s = (cudaStream_t)c->stream;
+
+    OcpDriver<P>::init(a, s);
+    const int check_every = c->check_every > 0 ? c->check_every : 4;
+    int launched = 0;
+    for (int it = 0; it <= c->max_iter; ++it) {
+      OcpDriver<P>::iteration(a, s);
+      ++launched;
+      if ((it + 1) % check_every == 0 || it == c->max_iter) {
+        int active = 0;
+#if HB_DEVICE_BUILD
+        cudaMemsetAsync(a.iters + a.B, 0, sizeof(int), s);
+        launch_1d<OcpCount>(a, a.B, s);
+        cudaMemcpyAsync(&active, a.iters + a.B, sizeof(int), cudaMemcpyDeviceToHost, s);
+        cudaError_t e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) return (int)e;
+#else
+        a.iters[a.B] = 0;
+        launch_1d<OcpCount>(a, a.B, s);
+        active = a.iters[a.B];
+#endif
+        if (active == 0) break;
+      }
+    }
+    if (c->stats != nullptr) {
+#if HB_DEVICE_BUILD
+      cudaMemcpyAsync(c->stats, a.st, b * ST_COUNT * sizeof(double), cudaMemcpyDeviceToDevice, s);
+#else
+      memcpy(c->stats, a.st, b * ST_COUNT * sizeof(double));
+#endif
+    }
+    if (c->n_iterations_launched != nullptr) *c->n_iterations_launched = launched;
+#if HB_DEVICE_BUILD
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : (int)e;
+#else
+    return 0;
+#endif
+  }
+};
+
+}  // namespace hb
+
+#define HB_DEFINE_OCP_MODULE(PROB)                                                                        \
+  extern "C" void hbm_ocp_dims(hb_ocp_dims* d) { hb::OcpModule<PROB>::dims(d); }                          \
+  extern "C" size_t hbm_ocp_work_doubles(int B, int n_alpha) {                                            \
+    return hb::OcpModule<PROB>::work_doubles(B, n_alpha);                                                 \
+  }                                                                                                       \
+  extern "C" int hbm_ocp_solve(const hb_ocp_call* c) { return hb::OcpModule<PROB>::solve(c); }

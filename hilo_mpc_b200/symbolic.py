@@ -1,0 +1,794 @@
+"""Tiny symbolic layer: hash-consed scalar expression DAG with forward-mode AD and code generation.
+
+The reference delegates every expression to CasADi ``SX`` (e.g. ``hilo_mpc/modules/dynamic_model/
+dynamic_model.py:2882-2994`` builds the ODE/measurement ``ca.Function`` objects and IPOPT gets its
+Jacobians/Hessians from CasADi AD, ``hilo_mpc/modules/controller/mpc.py:1778-1787``).  CasADi is not
+available here, and the B200 engine needs the residuals/Jacobians as CUDA device functions anyway,
+so this module provides the three things the hot path needs and nothing more:
+
+* scalar expression nodes with operator overloading (vectors/matrices are ``numpy`` object arrays),
+* symbolic differentiation (``jacobian``/``gradient``/``hessian``) with common-subexpression sharing,
+* emitters: CUDA/C source for device functions and NumPy-vectorised Python callables.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Dict, Iterable, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+Number = Union[int, float]
+
+_UNARY = ('neg', 'sin', 'cos', 'tan', 'exp', 'log', 'sqrt', 'tanh', 'atan', 'asin', 'acos', 'sinh', 'cosh', 'abs',
+          'sign', 'sigmoid')
+_BINARY = ('add', 'sub', 'mul', 'div', 'pow', 'atan2', 'fmin', 'fmax')
+
+
+class Expr:
+    """One node of the expression DAG. Nodes are interned, so ``a is b`` iff structurally equal."""
+    __slots__ = ('op', 'args', 'value', 'name', 'id', '__weakref__')
+    __array_priority__ = 1000.  # let numpy defer to our reflected operators elementwise
+
+    _table: Dict[tuple, 'Expr'] = {}
+    _count = 0
+
+    def __new__(cls, op: str, args: tuple = (), value: Optional[float] = None, name: Optional[str] = None):
+        if op == 'sym':
+            key = None  # symbols are unique objects even when names collide
+        elif op == 'const':
+            key = ('const', float(value).hex())
+        else:
+            key = (op,) + tuple(a.id for a in args)
+        if key is not None:
+            hit = cls._table.get(key)
+            if hit is not None:
+                return hit
+        self = object.__new__(cls)
+        self.op = op
+        self.args = args
+        self.value = None if value is None else float(value)
+        self.name = name
+        self.id = Expr._count
+        Expr._count += 1
+        if key is not None:
+            cls._table[key] = self
+        return self
+
+    # ------------------------------------------------------------------ construction helpers
+    @staticmethod
+    def const(v: Number) -> 'Expr':
+        return Expr('const', (), value=float(v))
+
+    @staticmethod
+    def wrap(v) -> 'Expr':
+        if isinstance(v, Expr):
+            return v
+        if isinstance(v, (int, float, np.integer, np.floating)):
+            return Expr.const(float(v))
+        if isinstance(v, np.ndarray) and v.size == 1:
+            return Expr.wrap(v.reshape(-1)[0])
+        raise TypeError(f"Cannot convert {type(v).__name__} to a symbolic expression")
+
+    def is_const(self, v: Optional[float] = None) -> bool:
+        return self.op == 'const' and (v is None or self.value == v)
+
+    def is_symbolic(self) -> bool:
+        return True
+
+    # ------------------------------------------------------------------ arithmetic
+    def __add__(self, o):
+        if isinstance(o, np.ndarray):
+            return NotImplemented
+        return _add(self, Expr.wrap(o))
+
+    def __radd__(self, o):
+        return _add(Expr.wrap(o), self)
+
+    def __sub__(self, o):
+        if isinstance(o, np.ndarray):
+            return NotImplemented
+        return _sub(self, Expr.wrap(o))
+
+    def __rsub__(self, o):
+        return _sub(Expr.wrap(o), self)
+
+    def __mul__(self, o):
+        if isinstance(o, np.ndarray):
+            return NotImplemented
+        return _mul(self, Expr.wrap(o))
+
+    def __rmul__(self, o):
+        return _mul(Expr.wrap(o), self)
+
+    def __truediv__(self, o):
+        if isinstance(o, np.ndarray):
+            return NotImplemented
+        return _div(self, Expr.wrap(o))
+
+    def __rtruediv__(self, o):
+        return _div(Expr.wrap(o), self)
+
+    def __pow__(self, o):
+        if isinstance(o, np.ndarray):
+            return NotImplemented
+        return _pow(self, Expr.wrap(o))
+
+    def __rpow__(self, o):
+        return _pow(Expr.wrap(o), self)
+
+    def __neg__(self):
+        return _neg(self)
+
+    def __pos__(self):
+        return self
+
+    def __abs__(self):
+        return _unary('abs', self)
+
+    def __float__(self):
+        if self.op == 'const':
+            return self.value
+        raise TypeError("Symbolic expression cannot be converted to float")
+
+    def __hash__(self):
+        return self.id
+
+    def __eq__(self, o):  # identity semantics (needed for dict keys); use ``is`` in library code
+        return self is o
+
+    def __repr__(self):
+        return to_string(self)
+
+    # numpy ufunc hooks so np.sin(expr_array) etc. work elementwise on object arrays
+    def sin(self):
+        return sin(self)
+
+    def cos(self):
+        return cos(self)
+
+    def tan(self):
+        return tan(self)
+
+    def exp(self):
+        return exp(self)
+
+    def log(self):
+        return log(self)
+
+    def sqrt(self):
+        return sqrt(self)
+
+    def tanh(self):
+        return tanh(self)
+
+    def arctan(self):
+        return atan(self)
+
+    def arcsin(self):
+        return _unary('asin', self)
+
+    def arccos(self):
+        return _unary('acos', self)
+
+    def sinh(self):
+        return _unary('sinh', self)
+
+    def cosh(self):
+        return _unary('cosh', self)
+
+
+# ---------------------------------------------------------------------- node constructors with simplification
+def _add(a: Expr, b: Expr) -> Expr:
+    if a.op == 'const' and b.op == 'const':
+        return Expr.const(a.value + b.value)
+    if a.is_const(0.):
+        return b
+    if b.is_const(0.):
+        return a
+    if b.op == 'neg':
+        return _sub(a, b.args[0])
+    if a.op == 'neg':
+        return _sub(b, a.args[0])
+    return Expr('add', (a, b))
+
+
+def _sub(a: Expr, b: Expr) -> Expr:
+    if a.op == 'const' and b.op == 'const':
+        return Expr.const(a.value - b.value)
+    if b.is_const(0.):
+        return a
+    if a.is_const(0.):
+        return _neg(b)
+    if a is b:
+        return Expr.const(0.)
+    if b.op == 'neg':
+        return _add(a, b.args[0])
+    return Expr('sub', (a, b))
+
+
+def _mul(a: Expr, b: Expr) -> Expr:
+    if a.op == 'const' and b.op == 'const':
+        return Expr.const(a.value * b.value)
+    if a.is_const(0.) or b.is_const(0.):
+        return Expr.const(0.)
+    if a.is_const(1.):
+        return b
+    if b.is_const(1.):
+        return a
+    if a.is_const(-1.):
+        return _neg(b)
+    if b.is_const(-1.):
+        return _neg(a)
+    if a.op == 'neg' and b.op == 'neg':
+        return _mul(a.args[0], b.args[0])
+    if b.op == 'const' and a.op != 'const':  # canonical order: constant first
+        a, b = b, a
+    return Expr('mul', (a, b))
+
+
+def _div(a: Expr, b: Expr) -> Expr:
+    if b.op == 'const':
+        if b.value == 1.:
+            return a
+        if a.op == 'const':
+            return Expr.const(a.value / b.value)
+    if a.is_const(0.):
+        return Expr.const(0.)
+    if a is b:
+        return Expr.const(1.)
+    return Expr('div', (a, b))
+
+
+def _neg(a: Expr) -> Expr:
+    if a.op == 'const':
+        return Expr.const(-a.value)
+    if a.op == 'neg':
+        return a.args[0]
+    return Expr('neg', (a,))
+
+
+def _pow(a: Expr, b: Expr) -> Expr:
+    if b.op == 'const':
+        if b.value == 0.:
+            return Expr.const(1.)
+        if b.value == 1.:
+            return a
+        if a.op == 'const':
+            return Expr.const(a.value ** b.value)
+        if b.value == 2.:
+            return _mul(a, a) if a.op in ('sym', 'const') else Expr('pow', (a, b))
+        if b.value == .5:
+            return sqrt(a)
+    return Expr('pow', (a, b))
+
+
+_CONST_FOLD = {
+    'sin': math.sin, 'cos': math.cos, 'tan': math.tan, 'exp': math.exp, 'log': math.log, 'sqrt': math.sqrt,
+    'tanh': math.tanh, 'atan': math.atan, 'asin': math.asin, 'acos': math.acos, 'sinh': math.sinh,
+    'cosh': math.cosh, 'abs': abs, 'sign': lambda v: float(np.sign(v)), 'sigmoid': lambda v: 1. / (1. + math.exp(-v)),
+}
+
+
+def _unary(op: str, a) -> Expr:
+    a = Expr.wrap(a)
+    if a.op == 'const':
+        try:
+            return Expr.const(_CONST_FOLD[op](a.value))
+        except (ValueError, OverflowError):
+            pass
+    return Expr(op, (a,))
+
+
+def _elementwise(fun):
+    def wrapper(a, *rest):
+        if isinstance(a, np.ndarray):
+            out = np.empty(a.shape, dtype=object)
+            flat = out.reshape(-1)
+            for k, v in enumerate(a.reshape(-1)):
+                flat[k] = fun(v, *rest)
+            return out
+        return fun(a, *rest)
+    wrapper.__name__ = fun.__name__
+    return wrapper
+
+
+@_elementwise
+def sin(a): return _unary('sin', a)
+@_elementwise
+def cos(a): return _unary('cos', a)
+@_elementwise
+def tan(a): return _unary('tan', a)
+@_elementwise
+def exp(a): return _unary('exp', a)
+@_elementwise
+def log(a): return _unary('log', a)
+@_elementwise
+def sqrt(a): return _unary('sqrt', a)
+@_elementwise
+def tanh(a): return _unary('tanh', a)
+@_elementwise
+def atan(a): return _unary('atan', a)
+@_elementwise
+def asin(a): return _unary('asin', a)
+@_elementwise
+def acos(a): return _unary('acos', a)
+@_elementwise
+def sinh(a): return _unary('sinh', a)
+@_elementwise
+def cosh(a): return _unary('cosh', a)
+@_elementwise
+def fabs(a): return _unary('abs', a)
+@_elementwise
+def sign(a): return _unary('sign', a)
+@_elementwise
+def sigmoid(a): return _unary('sigmoid', a)
+
+
+def atan2(a, b) -> Expr:
+    return Expr('atan2', (Expr.wrap(a), Expr.wrap(b)))
+
+
+def fmin(a, b) -> Expr:
+    return Expr('fmin', (Expr.wrap(a), Expr.wrap(b)))
+
+
+def fmax(a, b) -> Expr:
+    return Expr('fmax', (Expr.wrap(a), Expr.wrap(b)))
+
+
+# ---------------------------------------------------------------------- vectors
+def sym(name: str, n: Optional[int] = None, m: Optional[int] = None):
+    """``sym('x')`` -> scalar symbol; ``sym('x', 3)`` -> (3,) object array ``x_0..x_2``; ``sym('P', 2, 2)`` matrix."""
+    if n is None:
+        return Expr('sym', (), name=name)
+    if m is None:
+        return np.array([Expr('sym', (), name=f'{name}_{k}') for k in range(n)], dtype=object)
+    out = np.empty((n, m), dtype=object)
+    for i in range(n):
+        for j in range(m):
+            out[i, j] = Expr('sym', (), name=f'{name}_{i}_{j}')
+    return out
+
+
+def named_syms(names: Sequence[str]) -> np.ndarray:
+    return np.array([Expr('sym', (), name=str(k)) for k in names], dtype=object)
+
+
+def as_vector(x) -> np.ndarray:
+    """Coerce scalars / lists / arrays of numbers and expressions into a flat object array of ``Expr``."""
+    if isinstance(x, Expr):
+        return np.array([x], dtype=object)
+    if x is None:
+        return np.empty((0,), dtype=object)
+    arr = np.asarray(x, dtype=object).reshape(-1)
+    out = np.empty(arr.shape, dtype=object)
+    for k, v in enumerate(arr):
+        out[k] = Expr.wrap(v)
+    return out
+
+
+def is_symbolic(x) -> bool:
+    if isinstance(x, Expr):
+        return x.op != 'const'
+    if isinstance(x, np.ndarray) and x.dtype == object:
+        return any(isinstance(v, Expr) and v.op != 'const' for v in x.reshape(-1))
+    if isinstance(x, (list, tuple)):
+        return any(is_symbolic(v) for v in x)
+    return False
+
+
+# ---------------------------------------------------------------------- traversal
+def topo_sort(outputs: Iterable[Expr]) -> List[Expr]:
+    order: List[Expr] = []
+    seen = set()
+    for root in outputs:
+        if root.id in seen:
+            continue
+        stack = [(root, 0)]
+        while stack:
+            node, idx = stack.pop()
+            if idx == 0 and node.id in seen:
+                continue
+            if idx < len(node.args):
+                stack.append((node, idx + 1))
+                child = node.args[idx]
+                if child.id not in seen:
+                    stack.append((child, 0))
+            else:
+                if node.id not in seen:
+                    seen.add(node.id)
+                    order.append(node)
+    return order
+
+
+def symbols_of(outputs: Iterable[Expr]) -> List[Expr]:
+    return [n for n in topo_sort(outputs) if n.op == 'sym']
+
+
+def depends_on(expr, variables) -> bool:
+    vs = {v.id for v in as_vector(variables)}
+    return any(n.id in vs for n in topo_sort(as_vector(expr)))
+
+
+def substitute(exprs, old, new):
+    """Replace symbols ``old`` by expressions ``new`` (like ``ca.substitute``). Shape of ``exprs`` is preserved."""
+    scalar = isinstance(exprs, Expr)
+    arr = np.asarray(exprs, dtype=object) if not scalar else np.array([exprs], dtype=object)
+    shape = arr.shape
+    flat = [Expr.wrap(v) for v in arr.reshape(-1)]
+    old_v = as_vector(old)
+    new_v = as_vector(new)
+    if len(old_v) != len(new_v):
+        raise ValueError("substitute: dimension mismatch")
+    memo: Dict[int, Expr] = {o.id: n for o, n in zip(old_v, new_v)}
+    for node in topo_sort(flat):
+        if node.id in memo:
+            continue
+        if not node.args:
+            memo[node.id] = node
+            continue
+        new_args = tuple(memo[a.id] for a in node.args)
+        if all(n is a for n, a in zip(new_args, node.args)):
+            memo[node.id] = node
+        else:
+            memo[node.id] = _rebuild(node.op, new_args)
+    out = np.array([memo[f.id] for f in flat], dtype=object).reshape(shape)
+    return out[0] if scalar else out
+
+
+def _rebuild(op: str, args: tuple) -> Expr:
+    if op == 'add':
+        return _add(*args)
+    if op == 'sub':
+        return _sub(*args)
+    if op == 'mul':
+        return _mul(*args)
+    if op == 'div':
+        return _div(*args)
+    if op == 'pow':
+        return _pow(*args)
+    if op == 'neg':
+        return _neg(*args)
+    if op in ('atan2', 'fmin', 'fmax'):
+        return Expr(op, args)
+    return _unary(op, args[0])
+
+
+# ---------------------------------------------------------------------- differentiation
+def _deriv_node(node: Expr, d: List[Optional[Expr]]) -> Optional[Expr]:
+    """Forward tangent of ``node`` given tangents ``d`` of its args (``None`` means structurally zero)."""
+    op, a = node.op, node.args
+    if op == 'add':
+        if d[0] is None:
+            return d[1]
+        if d[1] is None:
+            return d[0]
+        return _add(d[0], d[1])
+    if op == 'sub':
+        if d[1] is None:
+            return d[0]
+        if d[0] is None:
+            return _neg(d[1])
+        return _sub(d[0], d[1])
+    if op == 'mul':
+        t0 = None if d[0] is None else _mul(d[0], a[1])
+        t1 = None if d[1] is None else _mul(a[0], d[1])
+        if t0 is None:
+            return t1
+        if t1 is None:
+            return t0
+        return _add(t0, t1)
+    if op == 'div':
+        t0 = None if d[0] is None else _div(d[0], a[1])
+        t1 = None if d[1] is None else _mul(_div(node, a[1]), d[1])
+        if t1 is None:
+            return t0
+        if t0 is None:
+            return _neg(t1)
+        return _sub(t0, t1)
+    if op == 'neg':
+        return None if d[0] is None else _neg(d[0])
+    if op == 'pow':
+        base, ex = a
+        t = None
+        if d[0] is not None:
+            if ex.op == 'const':
+                t = _mul(_mul(ex, _pow(base, Expr.const(ex.value - 1.))), d[0])
+            else:
+                t = _mul(_mul(ex, _pow(base, _sub(ex, Expr.const(1.)))), d[0])
+        if d[1] is not None:
+            t1 = _mul(_mul(node, log(base)), d[1])
+            t = t1 if t is None else _add(t, t1)
+        return t
+    if op == 'atan2':
+        y, x = a
+        den = _add(_mul(x, x), _mul(y, y))
+        t = None
+        if d[0] is not None:
+            t = _mul(_div(x, den), d[0])
+        if d[1] is not None:
+            t1 = _mul(_div(y, den), d[1])
+            t = _neg(t1) if t is None else _sub(t, t1)
+        return t
+    if op in ('fmin', 'fmax'):
+        raise NotImplementedError("fmin/fmax are not differentiable in this layer")
+    if d[0] is None:
+        return None
+    x = a[0]
+    if op == 'sin':
+        g = cos(x)
+    elif op == 'cos':
+        g = _neg(sin(x))
+    elif op == 'tan':
+        g = _add(Expr.const(1.), _mul(node, node))
+    elif op == 'exp':
+        g = node
+    elif op == 'log':
+        g = _div(Expr.const(1.), x)
+    elif op == 'sqrt':
+        g = _div(Expr.const(.5), node)
+    elif op == 'tanh':
+        g = _sub(Expr.const(1.), _mul(node, node))
+    elif op == 'atan':
+        g = _div(Expr.const(1.), _add(Expr.const(1.), _mul(x, x)))
+    elif op == 'asin':
+        g = _div(Expr.const(1.), sqrt(_sub(Expr.const(1.), _mul(x, x))))
+    elif op == 'acos':
+        g = _neg(_div(Expr.const(1.), sqrt(_sub(Expr.const(1.), _mul(x, x)))))
+    elif op == 'sinh':
+        g = cosh(x)
+    elif op == 'cosh':
+        g = sinh(x)
+    elif op == 'abs':
+        g = sign(x)
+    elif op == 'sign':
+        return None
+    elif op == 'sigmoid':
+        g = _mul(node, _sub(Expr.const(1.), node))
+    else:
+        raise NotImplementedError(op)
+    return _mul(g, d[0])
+
+
+def jacobian(exprs, variables) -> np.ndarray:
+    """Dense symbolic Jacobian ``d exprs / d variables`` as an ``(m, n)`` object array (forward mode, one sweep per
+    variable over the nodes that depend on it)."""
+    f = as_vector(exprs)
+    v = as_vector(variables)
+    order = topo_sort(f)
+    J = np.empty((len(f), len(v)), dtype=object)
+    zero = Expr.const(0.)
+    for j, var in enumerate(v):
+        tang: Dict[int, Optional[Expr]] = {}
+        for node in order:
+            if node is var:
+                tang[node.id] = Expr.const(1.)
+            elif not node.args:
+                tang[node.id] = None
+            else:
+                ds = [tang[a.id] for a in node.args]
+                tang[node.id] = None if all(t is None for t in ds) else _deriv_node(node, ds)
+        for i, fi in enumerate(f):
+            t = tang.get(fi.id)
+            J[i, j] = zero if t is None else t
+    return J
+
+
+def gradient(expr, variables) -> np.ndarray:
+    return jacobian(as_vector(expr)[:1], variables)[0]
+
+
+def hessian(expr, variables) -> np.ndarray:
+    g = gradient(expr, variables)
+    H = jacobian(g, variables)
+    # symmetrise structurally (identical by construction up to node ordering)
+    n = H.shape[0]
+    for i in range(n):
+        for j in range(i):
+            H[i, j] = H[j, i]
+    return H
+
+
+# ---------------------------------------------------------------------- printing / code generation
+_INFIX = {'add': '+', 'sub': '-', 'mul': '*', 'div': '/'}
+_C_UNARY = {'sin': 'sin', 'cos': 'cos', 'tan': 'tan', 'exp': 'exp', 'log': 'log', 'sqrt': 'sqrt', 'tanh': 'tanh',
+            'atan': 'atan', 'asin': 'asin', 'acos': 'acos', 'sinh': 'sinh', 'cosh': 'cosh', 'abs': 'fabs'}
+_NP_UNARY = {'sin': 'np.sin', 'cos': 'np.cos', 'tan': 'np.tan', 'exp': 'np.exp', 'log': 'np.log', 'sqrt': 'np.sqrt',
+             'tanh': 'np.tanh', 'atan': 'np.arctan', 'asin': 'np.arcsin', 'acos': 'np.arccos', 'sinh': 'np.sinh',
+             'cosh': 'np.cosh', 'abs': 'np.abs', 'sign': 'np.sign'}
+
+
+def to_string(e: Expr, depth: int = 0) -> str:
+    if depth > 6:
+        return '…'
+    if e.op == 'const':
+        return repr(e.value)
+    if e.op == 'sym':
+        return e.name
+    if e.op in _INFIX:
+        return f'({to_string(e.args[0], depth + 1)} {_INFIX[e.op]} {to_string(e.args[1], depth + 1)})'
+    if e.op == 'neg':
+        return f'(-{to_string(e.args[0], depth + 1)})'
+    return f'{e.op}(' + ', '.join(to_string(a, depth + 1) for a in e.args) + ')'
+
+
+def _c_const(v: float) -> str:
+    if math.isinf(v):
+        return 'HUGE_VAL' if v > 0 else '-HUGE_VAL'
+    if math.isnan(v):
+        return 'NAN'
+    r = repr(float(v))
+    if 'e' not in r and '.' not in r:
+        r += '.0'
+    return r
+
+
+def _emit(outputs: List[Expr], inputs: Dict[int, str], lang: str, tmp: str = 't') -> Tuple[List[str], List[str]]:
+    """Straight-line code for ``outputs``; returns (statements, output operand strings)."""
+    order = topo_sort(outputs)
+    uses: Dict[int, int] = {}
+    for node in order:
+        for a in node.args:
+            uses[a.id] = uses.get(a.id, 0) + 1
+    names: Dict[int, str] = {}
+    lines: List[str] = []
+    k = 0
+    for node in order:
+        if node.op == 'const':
+            names[node.id] = _c_const(node.value) if lang == 'c' else repr(node.value)
+            continue
+        if node.op == 'sym':
+            if node.id not in inputs:
+                raise ValueError(f"Free symbol '{node.name}' is not an input of the function being generated")
+            names[node.id] = inputs[node.id]
+            continue
+        a = [names[x.id] for x in node.args]
+        op = node.op
+        if op in _INFIX:
+            rhs = f'{a[0]} {_INFIX[op]} {a[1]}'
+        elif op == 'neg':
+            rhs = f'-{a[0]}'
+        elif op == 'pow':
+            ex = node.args[1]
+            if ex.op == 'const' and ex.value == int(ex.value) and 2 <= abs(ex.value) <= 4:
+                p = '*'.join([a[0]] * int(abs(ex.value)))
+                rhs = p if ex.value > 0 else f'1.0/({p})'
+            else:
+                rhs = f'pow({a[0]}, {a[1]})' if lang == 'c' else f'np.power({a[0]}, {a[1]})'
+        elif op == 'atan2':
+            rhs = f'atan2({a[0]}, {a[1]})' if lang == 'c' else f'np.arctan2({a[0]}, {a[1]})'
+        elif op == 'fmin':
+            rhs = f'fmin({a[0]}, {a[1]})' if lang == 'c' else f'np.minimum({a[0]}, {a[1]})'
+        elif op == 'fmax':
+            rhs = f'fmax({a[0]}, {a[1]})' if lang == 'c' else f'np.maximum({a[0]}, {a[1]})'
+        elif op == 'sign':
+            rhs = f'(({a[0]} > 0.0) - ({a[0]} < 0.0))' if lang == 'c' else f'np.sign({a[0]})'
+        elif op == 'sigmoid':
+            rhs = f'1.0/(1.0 + exp(-{a[0]}))' if lang == 'c' else f'1.0/(1.0 + np.exp(-{a[0]}))'
+        else:
+            rhs = f'{(_C_UNARY if lang == "c" else _NP_UNARY)[op]}({a[0]})'
+        name = f'{tmp}{k}'
+        k += 1
+        names[node.id] = name
+        lines.append(f'const double {name} = {rhs};' if lang == 'c' else f'{name} = {rhs}')
+    return lines, [names[o.id] for o in outputs]
+
+
+class Function:
+    """Named multi-input/multi-output function of symbolic vectors (the role ``ca.Function`` plays in the
+    reference, e.g. ``hilo_mpc/modules/base.py:320-360``).
+
+    ``inputs``/``outputs`` are (name, array-of-Expr) pairs; arrays may be 1-D or 2-D (2-D outputs are emitted
+    row-major).
+    """
+
+    def __init__(self, name: str, inputs: Sequence[Tuple[str, object]], outputs: Sequence[Tuple[str, object]]):
+        self.name = name
+        self.in_names = [n for n, _ in inputs]
+        self.out_names = [n for n, _ in outputs]
+        self.inputs = [as_vector(v) for _, v in inputs]
+        self.out_shapes = [np.asarray(v, dtype=object).shape if not isinstance(v, Expr) else () for _, v in outputs]
+        self.outputs = [as_vector(v) for _, v in outputs]
+        self._np = None
+
+    # -- numeric evaluation through generated NumPy source (vectorised over a trailing batch axis)
+    def _build_numpy(self) -> Callable:
+        in_map: Dict[int, str] = {}
+        for iname, vec in zip(self.in_names, self.inputs):
+            for k, s in enumerate(vec):
+                if s.op != 'sym':
+                    raise ValueError(f"Input '{iname}' must consist of pure symbols")
+                in_map[s.id] = f'{iname}[{k}]'
+        flat = [o for vec in self.outputs for o in vec]
+        lines, outs = _emit(flat, in_map, 'py')
+        src = [f"def {self.name}({', '.join(self.in_names)}):"]
+        src += ['    ' + ln for ln in lines]
+        pos = 0
+        rets = []
+        for oname, vec in zip(self.out_names, self.outputs):
+            rets.append('[' + ', '.join(outs[pos:pos + len(vec)]) + ']')
+            pos += len(vec)
+        src.append('    return (' + ', '.join(rets) + ',)')
+        ns = {'np': np}
+        exec('\n'.join(src), ns)
+        return ns[self.name]
+
+    def __call__(self, *args):
+        """Evaluate numerically. Each argument is array-like of shape ``(n_i,)`` or ``(n_i, batch)``; outputs are
+        float (or complex, for complex-step differentiation) arrays shaped like the symbolic outputs, with the batch
+        axis appended when present."""
+        if self._np is None:
+            self._np = self._build_numpy()
+        cast = []
+        for a, vec in zip(args, self.inputs):
+            a = np.asarray(a)
+            if a.ndim == 0:
+                a = a.reshape(1)
+            if a.shape[0] != len(vec):
+                a = a.reshape(len(vec), -1) if a.size != len(vec) else a.reshape(len(vec))
+            cast.append(a)
+        res = self._np(*cast)
+        outs = []
+        for r, shp in zip(res, self.out_shapes):
+            if len(r) == 0:
+                outs.append(np.zeros(shp))
+                continue
+            r = np.array(np.broadcast_arrays(*[np.asarray(v) for v in r]))
+            outs.append(r.reshape(shp + r.shape[1:]))
+        return outs[0] if len(outs) == 1 else tuple(outs)
+
+    # -- CUDA / C emission
+    def c_source(self, qualifiers: str = '__host__ __device__ __forceinline__', real: str = 'double',
+                 scalar_inputs: Sequence[str] = (), name: Optional[str] = None) -> str:
+        """Emit ``void name(const real* in0, ..., real* out0, ...)``; 2-D outputs are stored row-major. Inputs listed
+        in ``scalar_inputs`` (length-1 vectors) are passed by value."""
+        in_map: Dict[int, str] = {}
+        sig = []
+        for iname, vec in zip(self.in_names, self.inputs):
+            if iname in scalar_inputs:
+                if len(vec) != 1:
+                    raise ValueError(f"Scalar input '{iname}' must have exactly one element")
+                in_map[vec[0].id] = iname
+                sig.append(f'const {real} {iname}')
+            else:
+                for k, s in enumerate(vec):
+                    in_map[s.id] = f'{iname}[{k}]'
+                sig.append(f'const {real}* __restrict__ {iname}')
+        flat = [o for vec in self.outputs for o in vec]
+        lines, outs = _emit(flat, in_map, 'c')
+        sig += [f'{real}* __restrict__ {n}' for n in self.out_names]
+        src = [f"{qualifiers} void {name or self.name}({', '.join(sig)})", '{']
+        src += ['    ' + ln for ln in lines]
+        pos = 0
+        for oname, vec in zip(self.out_names, self.outputs):
+            for k in range(len(vec)):
+                src.append(f'    {oname}[{k}] = {outs[pos + k]};')
+            pos += len(vec)
+        src.append('}')
+        return '\n'.join(src)
+
+    def n_nodes(self) -> int:
+        return len(topo_sort([o for vec in self.outputs for o in vec]))
+
+
+def evaluate(exprs, symbols, values):
+    """Numerically evaluate ``exprs`` with ``symbols := values`` (convenience for host-side setup code)."""
+    f = Function('f', [('v', as_vector(symbols))], [('o', exprs)])
+    return f(np.asarray(values, dtype=float).reshape(-1))
+
+
+def dot(a, b):
+    return np.dot(np.asarray(a, dtype=object), np.asarray(b, dtype=object))
+
+
+def quad_form(r, W):
+    """``r^T W r`` for an object vector ``r`` and numeric/square ``W``."""
+    r = as_vector(r)
+    W = np.asarray(W)
+    out = Expr.const(0.)
+    for i in range(len(r)):
+        for j in range(len(r)):
+            w = W[i, j]
+            if isinstance(w, Expr) or w != 0.:
+                out = out + r[i] * w * r[j]
+    return out

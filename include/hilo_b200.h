@@ -1,0 +1,92 @@
+/* hilo_b200.h — C ABI of the B200 batched MPC / estimation solve engine.
+ *
+ * The reference (HILO-MPC) has no FFI seam on this path; its seams are Python callables created in setup() and
+ * invoked once per control step:
+ *   NMPC : solver = ca.nlpsol('solver','ipopt',{f,x,p,g},opts); sol = solver(x0=,lbx=,ubx=,lbg=,ubg=,p=)
+ *          hilo_mpc/modules/controller/mpc.py:1778-1787, :722
+ *   MHE  : same shape, hilo_mpc/modules/estimator/mhe.py:782-790, :375
+ *   LMPC : ca.conic('solver','qpoases',{h,a}); solver(h=,g=,a=,lbx=,ubx=,lba=,uba=)   mpc.py:2268-2276, :2374
+ *          (precedent for swapping the back-end: solver='muaompc', hilo_mpc/modules/embedded/muaompc.py:52-128)
+ *   KF/EKF/UKF : self._function(x0=[x|P], y=, p=[u;p], Q=, R=)                          estimator/kf.py:261-265, :304-307
+ *   PF   : self._function(X,y,p,w,v,R) + np.random.choice(n_s, n_s, p=q)                estimator/pf.py:324-328, :374, :406
+ *   GP   : self._function(X=, x0=hyper, p=[X_train; y_train])                           machine_learning/gp/gp.py:623-629, :709
+ * Each entry point below replaces one of those calls for a whole batch of independent instances.
+ *
+ * Conventions: plain pointers and sizes only; every data pointer is a CUDA DEVICE pointer owned by the caller
+ * (e.g. a torch tensor) unless it says "host"; arrays are dense, row-major, fp64; functions return 0 on success,
+ * <0 for API misuse, >0 = cudaError_t; nothing throws across the boundary; work is enqueued on `stream` and is
+ * asynchronous with respect to the host unless documented otherwise.  Per-instance `status` uses the reference's
+ * codes (hilo_mpc/modules/optimizer.py:1091-1104): 1 optimal, 2 acceptable, 5 max iterations, -1 failure.
+ */
+#ifndef HILO_B200_H
+#define HILO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------------ library */
+int hb_version(void);                 /* ABI version (integer, bumps on incompatible change) */
+const char* hb_last_error(void);      /* host string describing the last failure on this thread */
+int hb_device_info(int device, int* sm_count, size_t* total_mem, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------------ NMPC / MHE
+ * A transcribed optimal-control problem lives in a generated module (shared object, built by
+ * hilo_mpc_b200/codegen.py from the Model/cost expressions at NMPC.setup()/MHE.setup() time; it contains the
+ * model's residual/Jacobian device functions).  hb_ocp_open loads it; hb_ocp_solve = one NMPC.optimize /
+ * MHE.estimate for B instances (replaces mpc.py:722 / mhe.py:375).                                            */
+typedef struct hb_ocp_dims {
+  int nx, nu, N, nc;        /* states, inputs, horizon, collocation states per interval (deg*nx or 0)           */
+  int nsp, ntp, nuold, nap; /* per-stage parameters, terminal parameters, previous inputs, arrival parameters   */
+  int stage_doubles;        /* doubles of one stage QP block [A B b Q S R q r] = 2nx^2+2nx*nu+nu^2+2nx+nu        */
+  int elim_doubles;         /* doubles of one elimination block                                                  */
+  int method;               /* 0 collocation, 1 explicit RK, 2 discrete                                         */
+  int fixed_x0;             /* 1: x_0 pinned to the measured state (NMPC), 0: free (MHE)                        */
+  int n_state;              /* doubles of per-instance solver statistics                                        */
+} hb_ocp_dims;
+
+typedef struct hb_ocp_call {
+  int B;                    /* batch size                                                                        */
+  int n_alpha;              /* line-search candidates evaluated in parallel (1 = full step to the boundary rule) */
+  int max_iter;             /* interior-point iteration cap (IPOPT max_iter)                                     */
+  int check_every;          /* host polls the active-instance count every this many iterations                  */
+  double tol, acc_tol;      /* IPOPT tol / acceptable_tol                                                        */
+  double mu_init, mu_min;   /* initial / final barrier parameter (IPOPT mu_init, tol/10)                         */
+  double time0, dt;         /* time of node 0 and sampling interval                                              */
+  const double* x0;         /* [B][nx] measured states (scaled); ignored when fixed_x0 == 0                      */
+  const double* sp;         /* [B|1][N][nsp] per-stage parameters (tvp, cp, references, measurements)            */
+  long long sp_stride;      /* doubles between instances, 0 = shared                                             */
+  const double* tp;         /* [B|1][ntp] terminal parameters                                                    */
+  long long tp_stride;
+  const double* uold;       /* [B|1][nuold] previous inputs for the input-change cost                            */
+  long long uold_stride;
+  const double* ap;         /* [B|1][nap] arrival-cost parameters (MHE)                                          */
+  long long ap_stride;
+  const double *xlb, *xub, *ulb, *uub; /* [nx],[nx],[nu],[nu] bounds (|v| >= 1e19 = none)                        */
+  double* x;                /* in/out [B][N+1][nx] node states: starting point in, solution out                  */
+  double* u;                /* in/out [B][N][nu]                                                                 */
+  double* xc;               /* in/out [B][N][nc] collocation states                                              */
+  double* lam;              /* out    [B][N+1][nx] costates of the continuity constraints                        */
+  int* status;              /* out    [B]                                                                         */
+  int* iters;               /* out    [B+1] iterations per instance; slot B is scratch                           */
+  double* stats;            /* out    [B][n_state] or NULL                                                       */
+  double* work;             /* workspace of hb_ocp_work_doubles(B, n_alpha) doubles                              */
+  size_t work_doubles;
+  void* stream;             /* cudaStream_t                                                                      */
+  int* n_iterations_launched; /* host out or NULL                                                                */
+} hb_ocp_call;
+
+typedef struct hb_ocp* hb_ocp_t;
+int hb_ocp_open(const char* module_path, hb_ocp_t* out);
+int hb_ocp_get_dims(hb_ocp_t h, hb_ocp_dims* dims);
+size_t hb_ocp_work_doubles(hb_ocp_t h, int B, int n_alpha);
+int hb_ocp_solve(hb_ocp_t h, const hb_ocp_call* call);   /* synchronises `stream` only to poll convergence */
+int hb_ocp_close(hb_ocp_t h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HILO_B200_H */

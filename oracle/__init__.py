@@ -1,0 +1,18 @@
+"""CPU oracle — TEST INFRASTRUCTURE ONLY.
+
+A NumPy/SciPy restatement of the HILO-MPC algorithms on the hot path (NMPC/LMPC/MHE transcription and solve,
+KF/EKF/UKF, PF, GP, finite-horizon LQR).  Every function cites the reference file:line it follows
+(paths relative to ``/root/reference``).
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may
+import this package.  The product (``hilo_mpc_b200``) never does; it fails loudly if the CUDA library is missing.
+
+Parity status:
+* KF / EKF / UKF / LQR-Riccati / SE-Gram / GP-LML: pinned by the golden numbers in the reference's own tests
+  (``tests/test_KFs.py``, ``tests/test_LQR.py``, ``tests/test_kernels.py``, ``tests/test_GPs.py``) — reproduced in
+  ``tests/test_oracle_golden.py``.
+* NMPC / LMPC / MHE / PF-estimate: the reference's tests hold NO numeric assertion for these and the reference
+  cannot be executed here (``casadi`` is not installed) -> "parity unpinned" at the IPOPT/qpOASES boundary.  The
+  oracle restates the transcription exactly and is validated by its own KKT residual, by SciPy's independent
+  solvers on small instances and by the LQR golden in the linear-quadratic special case.
+"""
