@@ -1,0 +1,106 @@
+"""ctypes binding of ``libhilo_b200.so`` (the C ABI in ``include/hilo_b200.h``).
+
+There is no CPU fallback: if the library cannot be loaded, or no CUDA device is present when a solve is requested,
+the call raises.  PyTorch is used only to own device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+from .build import LIB_PATH, build_core
+
+_DP = C.POINTER(C.c_double)
+_IP = C.POINTER(C.c_int)
+
+
+class OcpDims(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ('nx', 'nu', 'N', 'nc', 'nsp', 'ntp', 'nuold', 'nap', 'stage_doubles',
+                                       'elim_doubles', 'method', 'fixed_x0', 'n_state')]
+
+
+class OcpCall(C.Structure):
+    _fields_ = [('B', C.c_int), ('n_alpha', C.c_int), ('max_iter', C.c_int), ('check_every', C.c_int),
+                ('tol', C.c_double), ('acc_tol', C.c_double), ('mu_init', C.c_double), ('mu_min', C.c_double),
+                ('time0', C.c_double), ('dt', C.c_double),
+                ('x0', C.c_void_p), ('sp', C.c_void_p), ('sp_stride', C.c_longlong),
+                ('tp', C.c_void_p), ('tp_stride', C.c_longlong),
+                ('uold', C.c_void_p), ('uold_stride', C.c_longlong), ('ap', C.c_void_p), ('ap_stride', C.c_longlong),
+                ('xlb', C.c_void_p), ('xub', C.c_void_p), ('ulb', C.c_void_p), ('uub', C.c_void_p),
+                ('x', C.c_void_p), ('u', C.c_void_p), ('xc', C.c_void_p), ('lam', C.c_void_p),
+                ('status', C.c_void_p), ('iters', C.c_void_p), ('stats', C.c_void_p),
+                ('work', C.c_void_p), ('work_doubles', C.c_size_t), ('stream', C.c_void_p),
+                ('n_iterations_launched', _IP), ('n_kernel_launches', C.POINTER(C.c_longlong)),
+                ('kernel_ms', _DP), ('kernel_count', C.POINTER(C.c_longlong))]
+
+
+_lib: Optional[C.CDLL] = None
+
+
+class EngineUnavailable(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load (building on first use if the toolkit is present) the core library; raises if that is impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = LIB_PATH
+    if not os.path.exists(path):
+        try:
+            build_core()
+        except Exception as exc:  # noqa: BLE001
+            raise EngineUnavailable(f"libhilo_b200.so is missing and could not be built: {exc}") from exc
+    try:
+        lib = C.CDLL(path)
+    except OSError as exc:
+        raise EngineUnavailable(f"Could not load {path}: {exc}. The B200 engine has no CPU fallback.") from exc
+    lib.hb_version.restype = C.c_int
+    lib.hb_last_error.restype = C.c_char_p
+    lib.hb_device_info.argtypes = [C.c_int, _IP, C.POINTER(C.c_size_t), _IP, _IP]
+    lib.hb_ocp_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    lib.hb_ocp_get_dims.argtypes = [C.c_void_p, C.POINTER(OcpDims)]
+    lib.hb_ocp_work_doubles.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.hb_ocp_work_doubles.restype = C.c_size_t
+    lib.hb_ocp_solve.argtypes = [C.c_void_p, C.POINTER(OcpCall)]
+    lib.hb_ocp_close.argtypes = [C.c_void_p]
+    _register_optional(lib)
+    _lib = lib
+    return lib
+
+
+def _register_optional(lib: C.CDLL) -> None:
+    """argtypes for the model-independent kernels (declared in include/hilo_b200.h)."""
+    vp, i, d, ll = C.c_void_p, C.c_int, C.c_double, C.c_longlong
+    sigs = {
+        'hb_riccati_solve': [i, i, i, i, vp, vp, vp, vp, vp, vp, i, vp],
+        'hb_pf_resample': [i, i, vp, vp, vp, vp],
+        'hb_kf_step': [i, i, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i, vp],
+        'hb_gp_fit': [i, i, vp, vp, vp, d, d, vp, vp, vp, vp, vp],
+        'hb_gp_predict': [i, i, i, vp, vp, vp, vp, d, vp, vp, vp, i, vp],
+        'hb_lmpc_solve': None,
+    }
+    for name, args in sigs.items():
+        fn = getattr(lib, name, None)
+        if fn is not None and args is not None:
+            fn.argtypes = args
+            fn.restype = C.c_int
+
+
+def last_error() -> str:
+    return load().hb_last_error().decode()
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"{what} failed with code {rc}: {last_error()}")
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise EngineUnavailable("No CUDA device is visible. hilo_mpc_b200 runs its solvers on a B200 GPU and has "
+                                "no CPU fallback.")
+    return torch

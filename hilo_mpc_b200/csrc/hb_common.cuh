@@ -137,15 +137,16 @@ HB_HD bool lu_solve_aug(double* M) {
 struct BarrierTerm {
   double grad;   // d/dv of  -mu*log(v-lb) - mu*log(ub-v)
   double sigma;  // primal-dual Hessian  zl/(v-lb) + zu/(ub-v)
+  double dz;     // (-zl + zu) - grad : correction that turns the barrier gradient into the multiplier form
 };
 
 HB_HD bool has_lb(double lb) { return lb > -kInfBound; }
 HB_HD bool has_ub(double ub) { return ub < kInfBound; }
 
 HB_HD BarrierTerm barrier_term(double v, double lb, double ub, double zl, double zu, double mu) {
-  BarrierTerm t{0.0, 0.0};
-  if (has_lb(lb)) { const double s = v - lb; t.grad -= mu / s; t.sigma += zl / s; }
-  if (has_ub(ub)) { const double s = ub - v; t.grad += mu / s; t.sigma += zu / s; }
+  BarrierTerm t{0.0, 0.0, 0.0};
+  if (has_lb(lb)) { const double s = v - lb; t.grad -= mu / s; t.sigma += zl / s; t.dz += mu / s - zl; }
+  if (has_ub(ub)) { const double s = ub - v; t.grad += mu / s; t.sigma += zu / s; t.dz -= mu / s - zu; }
   return t;
 }
 

@@ -18,6 +18,60 @@ struct OcpCount {
   }
 };
 
+// Per-kernel device timing with CUDA events recorded on the launching stream (hb_ocp_call.kernel_ms != NULL).
+// Events are only read back at the points where the driver synchronises anyway (convergence polls).
+enum { K_INIT = 0, K_EVAL, K_RICCATI, K_EXPAND, K_PREP, K_TRIAL, K_DECIDE, K_APPLY, K_COMMIT, K_COUNT_ACTIVE, K_NUM };
+
+struct KernelTimer {
+  bool on = false;
+  cudaStream_t s = nullptr;
+#if HB_DEVICE_BUILD
+  static constexpr int kPool = 512;
+  cudaEvent_t ev0[kPool], ev1[kPool];
+  int kind[kPool];
+  int n = 0;
+  bool created = false;
+#endif
+  double* ms = nullptr;        // [K_NUM] accumulated milliseconds
+  long long* count = nullptr;  // [K_NUM] launches
+  long long launches = 0;
+
+  void begin(int k) {
+    ++launches;
+    if (count) count[k] += 1;
+#if HB_DEVICE_BUILD
+    if (!on) return;
+    if (!created) { for (int i = 0; i < kPool; ++i) { cudaEventCreate(&ev0[i]); cudaEventCreate(&ev1[i]); } created = true; }
+    if (n == kPool) flush(true);
+    kind[n] = k;
+    cudaEventRecord(ev0[n], s);
+#endif
+  }
+  void end() {
+#if HB_DEVICE_BUILD
+    if (!on) return;
+    cudaEventRecord(ev1[n], s);
+    ++n;
+#endif
+  }
+  void flush(bool sync) {
+#if HB_DEVICE_BUILD
+    if (!on || n == 0) return;
+    if (sync) cudaStreamSynchronize(s);
+    for (int i = 0; i < n; ++i) {
+      float t = 0.f;
+      if (cudaEventElapsedTime(&t, ev0[i], ev1[i]) == cudaSuccess && ms) ms[kind[i]] += (double)t;
+    }
+    n = 0;
+#endif
+  }
+  ~KernelTimer() {
+#if HB_DEVICE_BUILD
+    if (created) for (int i = 0; i < kPool; ++i) { cudaEventDestroy(ev0[i]); cudaEventDestroy(ev1[i]); }
+#endif
+  }
+};
+
 template <class P>
 struct OcpModule {
   using T = OcpT<P>;
@@ -35,7 +89,7 @@ struct OcpModule {
     w += 2 * b * n1 * T::NX + 2 * b * n * T::NU + 2 * b * n * T::NC;       // z multipliers
     w += b * n * T::SD + b * T::SDN + b * n * T::TD + b * n * T::KD;       // qp, qpN, el, fb
     w += b * n1 * T::NX + b * n * T::NU + b * n * T::NC;                   // dx, du, dxc
-    w += 7 * b * n1;                                                       // per-node scalars
+    w += 8 * b * n1 + b * n1 * T::NX;                                      // per-node scalars, QP costates
     w += 2 * b * (size_t)n_alpha * n1;                                     // line-search table
     w += b * ST_COUNT;                                                     // state
     return w + 64;
@@ -64,25 +118,36 @@ struct OcpModule {
     a.qp = take(b * n * T::SD); a.qpN = take(b * T::SDN); a.el = take(b * n * T::TD); a.fb = take(b * n * T::KD);
     a.dx = take(b * n1 * T::NX); a.du = take(b * n * T::NU); a.dxc = take(b * n * T::NC);
     a.s_cinf = take(b * n1); a.s_c1 = take(b * n1); a.s_phi = take(b * n1); a.s_comp = take(b * n1);
-    a.s_ap = take(b * n1); a.s_ad = take(b * n1); a.s_dphi = take(b * n1);
+    a.s_ap = take(b * n1); a.s_ad = take(b * n1); a.s_dphi = take(b * n1); a.s_rho = take(b * n1);
+    a.lamq = take(b * n1 * T::NX);
     a.ls_phi = take(b * (size_t)c->n_alpha * n1); a.ls_c1 = take(b * (size_t)c->n_alpha * n1);
     a.st = take(b * ST_COUNT);
     cudaStream_t s = (cudaStream_t)c->stream;
 
-    OcpDriver<P>::init(a, s);
+    static thread_local KernelTimer tm;
+    tm.on = c->kernel_ms != nullptr; tm.s = s; tm.ms = c->kernel_ms; tm.count = c->kernel_count; tm.launches = 0;
+    tm.begin(K_INIT); launch_2d<OcpInit<P>>(a, a.B, T::N + 1, s); tm.end();
     const int check_every = c->check_every > 0 ? c->check_every : 4;
     int launched = 0;
     for (int it = 0; it <= c->max_iter; ++it) {
-      OcpDriver<P>::iteration(a, s);
+      tm.begin(K_EVAL); launch_2d<OcpEval<P>>(a, a.B, T::N + 1, s); tm.end();
+      tm.begin(K_RICCATI); launch_1d<OcpRiccati<P>>(a, a.B, s); tm.end();
+      tm.begin(K_EXPAND); launch_2d<OcpExpand<P>>(a, a.B, T::N + 1, s); tm.end();
+      tm.begin(K_PREP); launch_1d<OcpPrep<P>>(a, a.B, s); tm.end();
+      tm.begin(K_TRIAL); launch_3d<OcpTrial<P>>(a, a.B, T::N + 1, a.n_alpha, s); tm.end();
+      tm.begin(K_DECIDE); launch_1d<OcpDecide<P>>(a, a.B, s); tm.end();
+      tm.begin(K_APPLY); launch_2d<OcpApply<P>>(a, a.B, T::N + 1, s); tm.end();
+      tm.begin(K_COMMIT); launch_1d<OcpCommit<P>>(a, a.B, s); tm.end();
       ++launched;
       if ((it + 1) % check_every == 0 || it == c->max_iter) {
         int active = 0;
 #if HB_DEVICE_BUILD
         cudaMemsetAsync(a.iters + a.B, 0, sizeof(int), s);
-        launch_1d<OcpCount>(a, a.B, s);
+        tm.begin(K_COUNT_ACTIVE); launch_1d<OcpCount>(a, a.B, s); tm.end();
         cudaMemcpyAsync(&active, a.iters + a.B, sizeof(int), cudaMemcpyDeviceToHost, s);
         cudaError_t e = cudaStreamSynchronize(s);
         if (e != cudaSuccess) return (int)e;
+        tm.flush(false);
 #else
         a.iters[a.B] = 0;
         launch_1d<OcpCount>(a, a.B, s);
@@ -99,6 +164,7 @@ struct OcpModule {
 #endif
     }
     if (c->n_iterations_launched != nullptr) *c->n_iterations_launched = launched;
+    if (c->n_kernel_launches != nullptr) *c->n_kernel_launches = tm.launches;
 #if HB_DEVICE_BUILD
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : (int)e;

@@ -77,7 +77,14 @@ typedef struct hb_ocp_call {
   size_t work_doubles;
   void* stream;             /* cudaStream_t                                                                      */
   int* n_iterations_launched; /* host out or NULL                                                                */
+  long long* n_kernel_launches; /* host out or NULL: kernels launched by this call                                 */
+  double* kernel_ms;        /* host in/out [HB_OCP_KERNELS] or NULL: accumulates device ms per kernel (CUDA events) */
+  long long* kernel_count;  /* host in/out [HB_OCP_KERNELS] or NULL: accumulates launches per kernel              */
 } hb_ocp_call;
+
+/* kernel indices of kernel_ms / kernel_count */
+#define HB_OCP_KERNELS 10
+#define HB_OCP_KERNEL_NAMES "init,eval,riccati,expand,prep,trial,decide,apply,commit,count"
 
 typedef struct hb_ocp* hb_ocp_t;
 int hb_ocp_open(const char* module_path, hb_ocp_t* out);

@@ -27,7 +27,8 @@ class OcpCall(C.Structure):
                 ('xlb', _DP), ('xub', _DP), ('ulb', _DP), ('uub', _DP),
                 ('x', _DP), ('u', _DP), ('xc', _DP), ('lam', _DP), ('status', _IP), ('iters', _IP), ('stats', _DP),
                 ('work', _DP), ('work_doubles', C.c_size_t), ('stream', C.c_void_p),
-                ('n_iterations_launched', _IP)]
+                ('n_iterations_launched', _IP), ('n_kernel_launches', C.POINTER(C.c_longlong)),
+                ('kernel_ms', _DP), ('kernel_count', C.POINTER(C.c_longlong))]
 
 
 def _dp(a):

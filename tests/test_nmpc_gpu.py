@@ -1,0 +1,89 @@
+"""GPU parity tests for the NMPC path: public API -> C ABI -> sm_100a kernels, compared with the CPU oracle on the
+same seeded inputs (sizes the oracle finishes in seconds) and checked through size-independent properties at the full
+BASELINE size.  Tolerances (scaled coordinates, fp64): |x - x_oracle| <= 2e-6, |u - u_oracle| <= 2e-5, both solvers
+at KKT error <= 1e-8 and barrier parameter 1e-9."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle(nmpc):
+    from oracle.nmpc import FlatNlp
+    return FlatNlp(nmpc.spec, exact_hessian=True)
+
+
+@pytest.mark.parametrize('method,N', [('collocation', 10), ('rk4', 10)])
+def test_cstr_batch_matches_oracle(cuda_device, method, N):
+    import torch
+    from hilo_mpc_b200.examples import cstr_initial_states, cstr_nmpc
+    nmpc = cstr_nmpc(N=N, integration_method=method)
+    x0 = cstr_initial_states(64, seed=5)
+    u0 = nmpc.optimize(torch.tensor(x0, device=cuda_device))
+    assert u0.shape == (64, 2)
+    status = nmpc.solver_status_code.cpu().numpy()
+    assert (status == 1).all()
+    x_pred, u_pred, _ = nmpc.return_prediction()
+    xs, us = np.asarray(nmpc._xs_full), np.asarray(nmpc._us_full)
+    nlp = _oracle(nmpc)
+    for b in (0, 17, 63):
+        res, xo, uo = nlp.solve(x0[b] / xs, dt=nmpc.sampling_interval, finish_barrier=True)
+        assert res.status == 1
+        np.testing.assert_allclose(x_pred[b].cpu().numpy() / xs, xo.T, atol=2e-6)
+        np.testing.assert_allclose(u_pred[b].cpu().numpy() / us, uo.T, atol=2e-5)
+        np.testing.assert_allclose(u0[b].cpu().numpy() / us, uo[:, 0], atol=5e-6)
+
+
+def test_single_instance_api_and_closed_loop(cuda_device):
+    """Drop-in call shape of the reference: x0 with nx entries -> (nu, 1) array; warm-started closed loop drives the
+    plant (here: the prediction model) to the set-point."""
+    from hilo_mpc_b200.examples import cstr_initial_states, cstr_nmpc
+    from hilo_mpc_b200.library import cstr_steady_state
+    nmpc = cstr_nmpc(N=10)
+    x_ss, u_ss = cstr_steady_state()
+    x = cstr_initial_states(1, seed=9)[0]
+    for _ in range(30):
+        u = nmpc.optimize(x)
+        assert u.shape == (2, 1)
+        assert nmpc.solver_status_code == 1
+        x_pred, u_pred, _ = nmpc.return_prediction()
+        assert x_pred.shape == (4, 11) and u_pred.shape == (2, 10)
+        x = x_pred[:, 1]
+    assert np.abs((x - x_ss) / np.array([1., 1., 100., 100.])).max() < 2e-2
+    assert nmpc.solution['u'].shape == (2, 30)
+
+
+def test_full_size_properties(cuda_device):
+    """BASELINE config 2 size (N=50, B=4096): every instance optimal, dynamics residual of the returned trajectory at
+    rounding level, bounds respected, instance b solved alone equals instance b solved inside the batch."""
+    import torch
+    from hilo_mpc_b200.examples import cstr_initial_states, cstr_nmpc
+    nmpc = cstr_nmpc(N=50)
+    x0 = cstr_initial_states(4096, seed=0)
+    u0 = nmpc.optimize(torch.tensor(x0, device=cuda_device))
+    out = nmpc._last
+    assert (out['status'] == 1).all()
+    stats = out['stats'].cpu().numpy()
+    assert stats[:, 10].max() < 1e-8  # primal infeasibility (collocation + continuity residuals)
+    assert stats[:, 9].max() < 1e-8   # dual infeasibility
+    spec = nmpc.spec
+    x, u = out['x'].cpu().numpy(), out['u'].cpu().numpy()
+    assert (x[:, 1:] >= spec.x_lb - 1e-12).all() and (x[:, 1:] <= spec.x_ub + 1e-12).all()
+    assert (u >= spec.u_lb - 1e-12).all() and (u <= spec.u_ub + 1e-12).all()
+    nmpc2 = cstr_nmpc(N=50)
+    u_single = nmpc2.optimize(torch.tensor(x0[1234:1235], device=cuda_device))
+    np.testing.assert_allclose(u_single.cpu().numpy(), u0[1234:1235].cpu().numpy(), rtol=0, atol=1e-9)
+
+
+def test_full_size_one_instance_vs_oracle(cuda_device):
+    import torch
+    from hilo_mpc_b200.examples import cstr_initial_states, cstr_nmpc
+    nmpc = cstr_nmpc(N=50)
+    x0 = cstr_initial_states(8, seed=11)
+    nmpc.optimize(torch.tensor(x0, device=cuda_device))
+    x_pred, u_pred, _ = nmpc.return_prediction()
+    xs, us = np.asarray(nmpc._xs_full), np.asarray(nmpc._us_full)
+    res, xo, uo = _oracle(nmpc).solve(x0[3] / xs, dt=nmpc.sampling_interval, finish_barrier=True)
+    assert res.status == 1
+    np.testing.assert_allclose(x_pred[3].cpu().numpy() / xs, xo.T, atol=2e-6)
+    np.testing.assert_allclose(u_pred[3].cpu().numpy() / us, uo.T, atol=2e-5)

@@ -1,0 +1,90 @@
+"""The symbolic layer replaces CasADi SX on this path: derivatives are checked against complex-step differentiation
+(independent of the AD rules) and the emitted C source is compiled and compared with the NumPy evaluator."""
+import ctypes
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from hilo_mpc_b200 import symbolic as sx
+from hilo_mpc_b200.library import cstr_rhs
+
+
+def _complex_step_jac(fun, x, *rest):
+    n = len(x)
+    cols = []
+    for j in range(n):
+        xp = np.asarray(x, dtype=complex).copy()
+        xp[j] += 1e-30j
+        cols.append(np.asarray(fun(xp, *rest)).imag / 1e-30)
+    return np.stack(cols, axis=1)
+
+
+def test_jacobian_matches_complex_step_cstr():
+    x, u = sx.sym('x', 4), sx.sym('u', 2)
+    f = np.array(cstr_rhs(x, u), dtype=object)
+    F = sx.Function('F', [('x', x), ('u', u)], [('f', f), ('fx', sx.jacobian(f, x)), ('fu', sx.jacobian(f, u))])
+    rng = np.random.default_rng(0)
+    for _ in range(5):
+        xv = np.array([1.2, .9, 125., 120.]) + rng.normal(size=4) * np.array([.2, .2, 5., 5.])
+        uv = np.array([14., -3000.]) + rng.normal(size=2) * np.array([3., 500.])
+        fv, fx, fu = F(xv, uv)
+        ref = np.array(cstr_rhs(xv, uv, exp=np.exp))
+        np.testing.assert_allclose(fv, ref, rtol=1e-13)
+        np.testing.assert_allclose(fx, _complex_step_jac(lambda a, b: F(a, b)[0], xv, uv), rtol=1e-11, atol=1e-9)
+        np.testing.assert_allclose(fu, _complex_step_jac(lambda b, a: F(a, b)[0], uv, xv), rtol=1e-11, atol=1e-12)
+
+
+def test_elementary_functions_and_hessian():
+    x = sx.sym('x', 3)
+    e = sx.sin(x[0]) * sx.exp(-x[1]) + sx.tanh(x[2]) ** 2 + sx.atan(x[0] * x[2]) + sx.sqrt(1 + x[1] ** 2) / (2 + sx.cos(x[2])) \
+        + x[0] ** 3 + sx.log(3 + x[1]) + x[2] ** 1.5
+    g = sx.gradient(e, x)
+    H = sx.hessian(e, x)
+    F = sx.Function('F', [('x', x)], [('e', [e]), ('g', g), ('H', H)])
+    xv = np.array([.3, .7, 1.1])
+    ev, gv, Hv = F(xv)
+    gcs = _complex_step_jac(lambda a: F(a)[0], xv)[0]
+    np.testing.assert_allclose(gv, gcs, rtol=1e-12)
+    Hcs = _complex_step_jac(lambda a: F(a)[1], xv)
+    np.testing.assert_allclose(Hv, Hcs, rtol=1e-11, atol=1e-13)
+    np.testing.assert_allclose(Hv, Hv.T, atol=1e-15)
+
+
+def test_substitute_and_simplification():
+    x = sx.sym('x', 2)
+    e = x[0] * 0. + 1. * x[1] + (x[0] - x[0])
+    assert e is x[1]
+    s = sx.substitute(np.array([x[0] ** 2 + x[1]], dtype=object), x, [2., sx.sym('y')])
+    assert sx.symbols_of(s)[0].name == 'y'
+    assert sx.evaluate(s, sx.symbols_of(s), [3.])[0] == 7.
+
+
+def test_batched_numpy_evaluation():
+    x = sx.sym('x', 2)
+    F = sx.Function('F', [('x', x)], [('o', [x[0] * x[1], x[0] + 1.])])
+    X = np.arange(10.).reshape(2, 5)
+    out = F(X)
+    np.testing.assert_allclose(out, np.stack([X[0] * X[1], X[0] + 1.]))
+
+
+def test_c_source_compiles_and_matches():
+    x, u = sx.sym('x', 4), sx.sym('u', 2)
+    f = np.array(cstr_rhs(x, u), dtype=object)
+    F = sx.Function('cstr', [('x', x), ('u', u)], [('f', f), ('fx', sx.jacobian(f, x))])
+    src = '#include <math.h>\n' + F.c_source(qualifiers='').replace('__restrict__', '')
+    with tempfile.TemporaryDirectory() as tmp:
+        c, so = os.path.join(tmp, 'f.c'), os.path.join(tmp, 'f.so')
+        open(c, 'w').write(src)
+        subprocess.run(['gcc', '-O1', '-shared', '-fPIC', c, '-o', so, '-lm'], check=True)
+        lib = ctypes.CDLL(so)
+        xv = np.array([1.2, .9, 125., 120.])
+        uv = np.array([14., -3000.])
+        fo, jo = np.zeros(4), np.zeros(16)
+        dp = ctypes.POINTER(ctypes.c_double)
+        lib.cstr(xv.ctypes.data_as(dp), uv.ctypes.data_as(dp), fo.ctypes.data_as(dp), jo.ctypes.data_as(dp))
+        fv, fx = F(xv, uv)
+        np.testing.assert_allclose(fo, fv, rtol=1e-14)
+        np.testing.assert_allclose(jo.reshape(4, 4), fx, rtol=1e-13)
