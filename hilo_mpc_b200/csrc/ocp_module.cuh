@@ -87,9 +87,9 @@ struct OcpModule {
     const size_t b = (size_t)B, n1 = T::N + 1, n = T::N;
     size_t w = 0;
     w += 2 * b * n1 * T::NX + 2 * b * n * T::NU + 2 * b * n * T::NC;       // z multipliers
-    w += b * n * T::SD + b * T::SDN + b * n * T::TD + b * n * T::KD;       // qp, qpN, el, fb
+    w += b * n * T::SD + b * T::SDN + b * n * T::TD + b * n * T::KD;       // qa+qh, qpN, el, fb
     w += b * n1 * T::NX + b * n * T::NU + b * n * T::NC;                   // dx, du, dxc
-    w += 8 * b * n1 + b * n1 * T::NX;                                      // per-node scalars, QP costates
+    w += 7 * b * n1;                                                       // per-node scalars
     w += 2 * b * (size_t)n_alpha * n1;                                     // line-search table
     w += b * ST_COUNT;                                                     // state
     return w + 64;
@@ -115,11 +115,10 @@ struct OcpModule {
     a.zlx = take(b * n1 * T::NX); a.zux = take(b * n1 * T::NX);
     a.zlu = take(b * n * T::NU); a.zuu = take(b * n * T::NU);
     a.zlc = take(b * n * T::NC); a.zuc = take(b * n * T::NC);
-    a.qp = take(b * n * T::SD); a.qpN = take(b * T::SDN); a.el = take(b * n * T::TD); a.fb = take(b * n * T::KD);
+    a.qa = take(b * n * T::NAp); a.qh = take(b * n * T::NHp); a.qpN = take(b * T::SDN); a.el = take(b * n * T::TD); a.fb = take(b * n * T::KD);
     a.dx = take(b * n1 * T::NX); a.du = take(b * n * T::NU); a.dxc = take(b * n * T::NC);
     a.s_cinf = take(b * n1); a.s_c1 = take(b * n1); a.s_phi = take(b * n1); a.s_comp = take(b * n1);
-    a.s_ap = take(b * n1); a.s_ad = take(b * n1); a.s_dphi = take(b * n1); a.s_rho = take(b * n1);
-    a.lamq = take(b * n1 * T::NX);
+    a.s_ap = take(b * n1); a.s_ad = take(b * n1); a.s_dphi = take(b * n1);
     a.ls_phi = take(b * (size_t)c->n_alpha * n1); a.ls_c1 = take(b * (size_t)c->n_alpha * n1);
     a.st = take(b * ST_COUNT);
     cudaStream_t s = (cudaStream_t)c->stream;
@@ -134,8 +133,14 @@ struct OcpModule {
       tm.begin(K_RICCATI); launch_1d<OcpRiccati<P>>(a, a.B, s); tm.end();
       tm.begin(K_EXPAND); launch_2d<OcpExpand<P>>(a, a.B, T::N + 1, s); tm.end();
       tm.begin(K_PREP); launch_1d<OcpPrep<P>>(a, a.B, s); tm.end();
-      tm.begin(K_TRIAL); launch_3d<OcpTrial<P>>(a, a.B, T::N + 1, a.n_alpha, s); tm.end();
+      a.ls_phase = 0;
+      tm.begin(K_TRIAL); launch_3d<OcpTrial<P>>(a, a.B, T::N + 1, 1, s); tm.end();
       tm.begin(K_DECIDE); launch_1d<OcpDecide<P>>(a, a.B, s); tm.end();
+      if (a.n_alpha > 1) {
+        a.ls_phase = 1;
+        tm.begin(K_TRIAL); launch_3d<OcpTrial<P>>(a, a.B, T::N + 1, a.n_alpha - 1, s); tm.end();
+        tm.begin(K_DECIDE); launch_1d<OcpDecide<P>>(a, a.B, s); tm.end();
+      }
       tm.begin(K_APPLY); launch_2d<OcpApply<P>>(a, a.B, T::N + 1, s); tm.end();
       tm.begin(K_COMMIT); launch_1d<OcpCommit<P>>(a, a.B, s); tm.end();
       ++launched;
