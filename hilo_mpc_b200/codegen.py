@@ -151,13 +151,17 @@ class OcpGenerator:
         return '\n'.join(L)
 
     def source(self) -> str:
+        body = self.prob_struct()
+        # one namespace per problem: template instantiations (and their function-local statics, which the toolchain
+        # emits as process-wide unique symbols) of different modules loaded into one process must not be merged
+        ns = 'hbgen_' + hashlib.sha256(body.encode()).hexdigest()[:12]
         return '\n'.join([
             f'// Generated by hilo_mpc_b200/codegen.py for problem "{self.spec.name}" — do not edit.',
             '#include "ocp_module.cuh"',
-            'namespace hbgen {',
-            self.prob_struct(),
-            '}  // namespace hbgen',
-            'HB_DEFINE_OCP_MODULE(hbgen::Prob)',
+            f'namespace {ns} {{',
+            body,
+            f'}}  // namespace {ns}',
+            f'HB_DEFINE_OCP_MODULE({ns}::Prob)',
             ''])
 
     # ------------------------------------------------------------------ build

@@ -2,6 +2,7 @@
 // The core library (hilo_b200.cu) dlopens the module and forwards hb_ocp_* calls to these hbm_* symbols.
 #pragma once
 #include "ocp_kernels.cuh"
+#include "riccati.cuh"
 #include "../../include/hilo_b200.h"
 
 namespace hb {
@@ -92,7 +93,7 @@ struct OcpModule {
     w += 7 * b * n1;                                                       // per-node scalars
     w += 2 * b * (size_t)n_alpha * n1;                                     // line-search table
     w += b * ST_COUNT;                                                     // state
-    return w + 64;
+    return w + 128;  // slack for the per-array 16-byte alignment padding
   }
 
   static int solve(const hb_ocp_call* c) {
@@ -111,7 +112,7 @@ struct OcpModule {
     a.status = c->status; a.iters = c->iters;
     const size_t b = (size_t)c->B, n1 = T::N + 1, n = T::N;
     double* w = c->work;
-    auto take = [&](size_t cnt) { double* p = w; w += cnt; return p; };
+    auto take = [&](size_t cnt) { double* p = w; w += (cnt + 1) & ~(size_t)1; return p; };  // keep 16-byte alignment
     a.zlx = take(b * n1 * T::NX); a.zux = take(b * n1 * T::NX);
     a.zlu = take(b * n * T::NU); a.zuu = take(b * n * T::NU);
     a.zlc = take(b * n * T::NC); a.zuc = take(b * n * T::NC);
@@ -130,7 +131,18 @@ struct OcpModule {
     int launched = 0;
     for (int it = 0; it <= c->max_iter; ++it) {
       tm.begin(K_EVAL); launch_2d<OcpEval<P>>(a, a.B, T::N + 1, s); tm.end();
-      tm.begin(K_RICCATI); launch_1d<OcpRiccati<P>>(a, a.B, s); tm.end();
+      tm.begin(K_RICCATI);
+#if HB_DEVICE_BUILD
+      if (c->riccati_variant != 0 && RiccatiTma<P>::SUPPORTED) {
+        cudaError_t e = launch_riccati_tma<P>(a, s);
+        if (e != cudaSuccess) return (int)e;
+      } else {
+        launch_1d<OcpRiccati<P>>(a, a.B, s);
+      }
+#else
+      launch_1d<OcpRiccati<P>>(a, a.B, s);
+#endif
+      tm.end();
       tm.begin(K_EXPAND); launch_2d<OcpExpand<P>>(a, a.B, T::N + 1, s); tm.end();
       tm.begin(K_PREP); launch_1d<OcpPrep<P>>(a, a.B, s); tm.end();
       a.ls_phase = 0;

@@ -92,7 +92,8 @@ class OcpEngine:
     # ------------------------------------------------------------------ solve
     def solve(self, x0, dt: float, time0: float = 0., sp=None, tp=None, uold=None, ap=None, tol: float = 1e-8,
               acc_tol: float = 1e-6, max_iter: int = 3000, n_alpha: int = 8, mu_init: float = .1,
-              mu_min: Optional[float] = None, check_every: int = 4, stream=None, kernel_ms=None, kernel_count=None):
+              mu_min: Optional[float] = None, check_every: int = 4, stream=None, kernel_ms=None, kernel_count=None,
+              riccati_variant: int = 1):
         """``x0``: CUDA tensor ``[B, nx]`` (scaled). Optional ``sp [B|1, N, nsp]``, ``tp``, ``uold``, ``ap`` tensors.
         Returns dict of device tensors: x [B,N+1,nx], u [B,N,nu], xc, lam, status, iters, stats."""
         torch = _lib.require_cuda()
@@ -131,7 +132,8 @@ class OcpEngine:
             work=t['work'].data_ptr(), work_doubles=t['work'].numel(), stream=st.cuda_stream,
             n_iterations_launched=C.pointer(launched), n_kernel_launches=C.pointer(n_launch),
             kernel_ms=None if kernel_ms is None else kernel_ms.ctypes.data_as(_lib._DP),
-            kernel_count=None if kernel_count is None else kernel_count.ctypes.data_as(C.POINTER(C.c_longlong)))
+            kernel_count=None if kernel_count is None else kernel_count.ctypes.data_as(C.POINTER(C.c_longlong)),
+            riccati_variant=riccati_variant)
         _lib.check(lib.hb_ocp_solve(self._handle, C.byref(call)), 'hb_ocp_solve')
         self.last_launched = launched.value
         self.last_kernel_launches = n_launch.value

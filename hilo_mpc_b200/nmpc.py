@@ -193,7 +193,8 @@ class DynamicOptimization:
                     max_iter=int(o.get('ipopt.max_iter', o.get('max_iter', 3000))),
                     mu_init=float(o.get('ipopt.mu_init', .1)),
                     n_alpha=int(o.get('b200.line_search_candidates', 8)),
-                    check_every=int(o.get('b200.check_every', 4)))
+                    check_every=int(o.get('b200.check_every', 4)),
+                    riccati_variant=int(o.get('b200.riccati_variant', 1)))
 
     def is_setup(self) -> bool:
         return self._nlp_setup_done

@@ -80,6 +80,7 @@ typedef struct hb_ocp_call {
   long long* n_kernel_launches; /* host out or NULL: kernels launched by this call                                 */
   double* kernel_ms;        /* host in/out [HB_OCP_KERNELS] or NULL: accumulates device ms per kernel (CUDA events) */
   long long* kernel_count;  /* host in/out [HB_OCP_KERNELS] or NULL: accumulates launches per kernel              */
+  int riccati_variant;      /* 1: TMA-staged multi-lane Riccati sweep (default), 0: one-thread-per-instance sweep  */
 } hb_ocp_call;
 
 /* kernel indices of kernel_ms / kernel_count */
