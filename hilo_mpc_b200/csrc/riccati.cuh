@@ -44,6 +44,16 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// 1/x for x > 0: hardware approximation refined by two Newton steps (full fp64 accuracy, no slow-path branch)
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 template <class P>
@@ -59,7 +69,8 @@ struct RiccatiTma {
   static constexpr int XCHp = (XCH + 1) & ~1;
   // per-instance shared memory (doubles): ring | feedback gains | exchange | mbarriers; the stride is padded so that
   // the instances of a warp start 8 banks apart (conflict-free 128-bit broadcasts)
-  static constexpr int RAW = NBUF * SLOT + N * T::KD + XCHp + NBUF;
+  static constexpr int FBD = (N * T::KD + 1) & ~1;  // feedback-gain store, padded to keep 16-byte alignment behind it
+  static constexpr int RAW = NBUF * SLOT + FBD + XCHp + NBUF;
   static constexpr int STRIDE = ((RAW + 15) / 16) * 16 + 4;  // doubles; (STRIDE*2) % 32 == 8 words
   static constexpr int SMEM_BYTES = WARPS * G * STRIDE * 8;
   static constexpr bool SUPPORTED = (NE + 1 <= 32) && (NX <= 6) && (SMEM_BYTES <= 110 * 1024);
@@ -88,7 +99,7 @@ struct RiccatiTma {
     double* base = smem + (size_t)(warp * G + grp) * STRIDE;
     double* ring = base;
     double* fbs = ring + NBUF * SLOT;
-    double* xch = fbs + N * T::KD;
+    double* xch = fbs + FBD;
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(xch + XCHp);
 
     const double* qa_g = a.qa + (long long)bb * N * T::NAp;
@@ -131,20 +142,40 @@ struct RiccatiTma {
     double edual = 0.0;
     bool ok = true;
 
+    // ---- per-lane offsets (doubles, relative to a ring slot), fixed for the whole sweep
+    int moff[NX];   // column g of [A B] / the affine column b
+    int coff[NE];   // column g of the cost Hessian [Q S^T; S R] / the gradient column [q; r]
+#pragma unroll
+    for (int l = 0; l < NX; ++l)
+      moff[l] = (g < NX) ? (T::oA + l * NX + g) : (g < NE) ? (T::oB + l * NU + (g - NX)) : (T::ob + l);
+#pragma unroll
+    for (int i = 0; i < NE; ++i) {
+      int o;
+      if (g < NX) o = (i < NX) ? (T::oQ + i * NX + g) : (T::oS + (i - NX) * NX + g);
+      else if (g < NE) o = (i < NX) ? (T::oS + (g - NX) * NX + i) : (T::oR + (i - NX) * NU + (g - NX));
+      else o = (i < NX) ? (T::oq + i) : (T::orr + (i - NX));
+      coff[i] = T::NAp + o;
+    }
+    const int goff = T::NAp + T::oqb + (g < NE ? g : 0);
+
     // =============================================================== backward sweep
     for (int j = 0; j < N; ++j) {
       const int k = N - 1 - j, s = j % NBUF;
       mbar_wait(&bars[s], (unsigned)((j / NBUF) & 1));
-      const double* qa = ring + s * SLOT;
-      const double* qh = qa + T::NAp;
-      // column g of M = [A B] (lanes >= NE: the affine column b)
+      const double* slot = ring + s * SLOT;
+      // whole dynamics block [A B] (broadcast 128-bit loads) and the lane's own column
+      double Mf[NX * NE + (NX * NE & 1)];
+      {
+        const double2* v = reinterpret_cast<const double2*>(slot);
+#pragma unroll
+        for (int i = 0; i < (NX * NE + 1) / 2; ++i) { const double2 t2 = v[i]; Mf[2 * i] = t2.x; if (2 * i + 1 < NX * NE + (NX * NE & 1)) Mf[2 * i + 1] = t2.y; }
+      }
       double m[NX];
 #pragma unroll
-      for (int l = 0; l < NX; ++l)
-        m[l] = (g < NX) ? qa[T::oA + l * NX + g] : (g < NE) ? qa[T::oB + l * NU + (g - NX)] : qa[T::ob + l];
+      for (int l = 0; l < NX; ++l) m[l] = slot[moff[l]];
       // adjoint / reduced gradient with lam_{k+1}
       {
-        double acc = (g < NE) ? qh[T::oqb + g] : 0.0;  // qbar | rbar are contiguous
+        double acc = (g < NE) ? slot[goff] : 0.0;
 #pragma unroll
         for (int l = 0; l < NX; ++l) acc += m[l] * lam[l];
         if (g >= NX && g < NE) edual = dmax(edual, dabs(acc));
@@ -165,14 +196,10 @@ struct RiccatiTma {
       double h[NE];
 #pragma unroll
       for (int i = 0; i < NE; ++i) {
-        double c;
-        if (g < NX) c = (i < NX) ? qh[T::oQ + i * NX + g] : qh[T::oS + (i - NX) * NX + g];
-        else if (g < NE) c = (i < NX) ? qh[T::oS + (g - NX) * NX + i] : qh[T::oR + (i - NX) * NU + (g - NX)];
-        else c = (i < NX) ? qh[T::oq + i] : qh[T::orr + (i - NX)];
-        double acc = c;
+        double acc = slot[coff[i]];
 #pragma unroll
         for (int l = 0; l < NX; ++l) {
-          const double mli = (i < NX) ? qa[T::oA + l * NX + i] : qa[T::oB + l * NU + (i - NX)];
+          const double mli = (i < NX) ? Mf[T::oA + l * NX + i] : Mf[T::oB + l * NU + (i - NX)];
           acc += mli * w[l];
         }
         h[i] = acc;
@@ -188,47 +215,50 @@ struct RiccatiTma {
       for (int c = 0; c < NU; ++c)
 #pragma unroll
         for (int i = 0; i < NE; ++i) hu[c][i] = xch[c * NE + i];
-      // Huu (symmetrised) and its Cholesky factor, computed redundantly by every lane
-      double L[NU][NU];
-      double reg = 0.0;
-      for (int attempt = 0; attempt < 12; ++attempt) {
-        bool pd = true;
+      // Huu = L D L^T (unit lower L, no square roots; reciprocals by Newton-refined rcp.approx), every lane redundantly
+      double Lm[NU][NU], dd[NU], dinv[NU];
+      {
+        double reg = 0.0;
+        for (int attempt = 0; attempt < 12; ++attempt) {
+          bool pd = true;
 #pragma unroll
-        for (int jj = 0; jj < NU; ++jj) {
-          double d = 0.5 * (hu[jj][NX + jj] + hu[jj][NX + jj]) + reg;
+          for (int jj = 0; jj < NU; ++jj) {
+            double d = hu[jj][NX + jj] + reg;
 #pragma unroll
-          for (int l = 0; l < jj; ++l) d -= L[jj][l] * L[jj][l];
-          pd = pd && (d > 0.0);
-          d = sqrt(d > 0.0 ? d : 1.0);
-          L[jj][jj] = d;
-          const double inv = 1.0 / d;
+            for (int l = 0; l < jj; ++l) d -= Lm[jj][l] * Lm[jj][l] * dd[l];
+            pd = pd && (d > 0.0);
+            dd[jj] = d > 0.0 ? d : 1.0;
+            dinv[jj] = fast_rcp(dd[jj]);
 #pragma unroll
-          for (int i = jj + 1; i < NU; ++i) {
-            double sacc = 0.5 * (hu[jj][NX + i] + hu[i][NX + jj]);
+            for (int i = jj + 1; i < NU; ++i) {
+              double sacc = 0.5 * (hu[jj][NX + i] + hu[i][NX + jj]);
 #pragma unroll
-            for (int l = 0; l < jj; ++l) sacc -= L[i][l] * L[jj][l];
-            L[i][jj] = sacc * inv;
+              for (int l = 0; l < jj; ++l) sacc -= Lm[i][l] * Lm[jj][l] * dd[l];
+              Lm[i][jj] = sacc * dinv[jj];
+            }
           }
+          if (pd) break;
+          reg = (reg == 0.0) ? 1e-8 : reg * 100.0;
+          if (attempt == 11) ok = false;
         }
-        if (pd) break;
-        reg = (reg == 0.0) ? 1e-8 : reg * 100.0;
-        if (attempt == 11) ok = false;
       }
-      // own feedback column: kk = -Huu^{-1} h[NX..NE)
+      // own feedback column: kk = -Huu^{-1} h[NX..NE)   (L y = -h, z = D^{-1} y, L^T kk = z)
       double kk[NU];
 #pragma unroll
       for (int i = 0; i < NU; ++i) {
         double sacc = -h[NX + i];
 #pragma unroll
-        for (int l = 0; l < i; ++l) sacc -= L[i][l] * kk[l];
-        kk[i] = sacc / L[i][i];
+        for (int l = 0; l < i; ++l) sacc -= Lm[i][l] * kk[l];
+        kk[i] = sacc;
       }
+#pragma unroll
+      for (int i = 0; i < NU; ++i) kk[i] *= dinv[i];
 #pragma unroll
       for (int i = NU - 1; i >= 0; --i) {
         double sacc = kk[i];
 #pragma unroll
-        for (int l = i + 1; l < NU; ++l) sacc -= L[l][i] * kk[l];
-        kk[i] = sacc / L[i][i];
+        for (int l = i + 1; l < NU; ++l) sacc -= Lm[l][i] * kk[l];
+        kk[i] = sacc;
       }
       double* fb = fbs + k * T::KD;
       if (g < NX) {
@@ -250,20 +280,22 @@ struct RiccatiTma {
       __syncwarp();  // everybody has read hu from the exchange buffer
       if (g < NX) {
 #pragma unroll
-        for (int i = 0; i < NX; ++i) xch[i * NX + g] = pn[i];
+        for (int i = 0; i < NX; ++i) xch[g * NX + i] = pn[i];  // column g stored contiguously (P is symmetric)
       } else if (g == NE) {
 #pragma unroll
         for (int i = 0; i < NX; ++i) pv[i] = pn[i];
       }
       __syncwarp();
+      {
+        const double2* v = reinterpret_cast<const double2*>(xch);
+        double Pf[NX * NX + (NX * NX & 1)];
 #pragma unroll
-      for (int i = 0; i < NX; ++i)
+        for (int i = 0; i < (NX * NX + 1) / 2; ++i) { const double2 t2 = v[i]; Pf[2 * i] = t2.x; if (2 * i + 1 < NX * NX + (NX * NX & 1)) Pf[2 * i + 1] = t2.y; }
 #pragma unroll
-        for (int jj = 0; jj < NX; ++jj) Pm[i][jj] = xch[i * NX + jj];
+        for (int i = 0; i < NX; ++i)
 #pragma unroll
-      for (int i = 0; i < NX; ++i)
-#pragma unroll
-        for (int jj = 0; jj < i; ++jj) { const double mm = 0.5 * (Pm[i][jj] + Pm[jj][i]); Pm[i][jj] = mm; Pm[jj][i] = mm; }
+          for (int jj = 0; jj <= i; ++jj) { const double mm = 0.5 * (Pf[jj * NX + i] + Pf[i * NX + jj]); Pm[i][jj] = mm; Pm[jj][i] = mm; }
+      }
       __syncwarp();  // slot s and the exchange buffer are free again
       if (g == 0 && j + NBUF < 2 * N) { fence_proxy_async(); issue(j + NBUF); }
     }
