@@ -6,7 +6,9 @@ from . import symbolic
 from . import symbolic as ca  # CasADi-flavoured helper namespace: ca.cos, ca.sin, ca.exp, ca.sym ...
 from .model import Model
 from .nmpc import NMPC
+from .estimators import EKF, KF, PF, UKF, ExtendedKalmanFilter, KalmanFilter, ParticleFilter, UnscentedKalmanFilter
 
 pi = 3.141592653589793
 
-__all__ = ['Model', 'NMPC', 'symbolic', 'ca']
+__all__ = ['Model', 'NMPC', 'KF', 'EKF', 'UKF', 'PF', 'KalmanFilter', 'ExtendedKalmanFilter', 'UnscentedKalmanFilter',
+           'ParticleFilter', 'symbolic', 'ca']

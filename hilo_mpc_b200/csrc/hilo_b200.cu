@@ -11,6 +11,7 @@
 #include <string>
 
 #include "../../include/hilo_b200.h"
+#include "est_kernels.cuh"
 
 namespace {
 thread_local char g_err[1024] = "";
@@ -28,6 +29,17 @@ struct hb_ocp {
   size_t (*work)(int, int);
   int (*solve)(const hb_ocp_call*);
   hb_ocp_dims d;
+};
+
+struct hb_est {
+  void* dl;
+  void (*dims)(hb_est_dims*);
+  size_t (*work)(int, int);
+  int (*sim)(const hb_est_call*);
+  int (*ekf)(const hb_est_call*);
+  int (*ukf)(const hb_est_call*);
+  int (*pf)(const hb_est_call*);
+  hb_est_dims d;
 };
 
 extern "C" {
@@ -84,6 +96,70 @@ int hb_ocp_solve(hb_ocp_t h, const hb_ocp_call* call) {
   if (rc < 0) set_err("hb_ocp_solve: invalid call (code %d: -1 batch, -2 workspace too small, -3 n_alpha)", rc);
   if (rc > 0) set_err("hb_ocp_solve: CUDA error %d (%s)", rc, cudaGetErrorString((cudaError_t)rc));
   return rc;
+}
+
+int hb_est_open(const char* module_path, hb_est_t* out) {
+  if (module_path == nullptr || out == nullptr) { set_err("hb_est_open: null argument"); return -1; }
+  void* dl = dlopen(module_path, RTLD_NOW | RTLD_LOCAL);
+  if (dl == nullptr) { set_err("hb_est_open: %s", dlerror()); return -2; }
+  hb_est* h = new hb_est();
+  h->dl = dl;
+  h->dims = (void (*)(hb_est_dims*))dlsym(dl, "hbm_est_dims");
+  h->work = (size_t(*)(int, int))dlsym(dl, "hbm_est_work_doubles");
+  h->sim = (int (*)(const hb_est_call*))dlsym(dl, "hbm_sim_step");
+  h->ekf = (int (*)(const hb_est_call*))dlsym(dl, "hbm_ekf_step");
+  h->ukf = (int (*)(const hb_est_call*))dlsym(dl, "hbm_ukf_step");
+  h->pf = (int (*)(const hb_est_call*))dlsym(dl, "hbm_pf_step");
+  if (!h->dims || !h->work || !h->sim || !h->ekf || !h->ukf || !h->pf) {
+    set_err("hb_est_open: %s is not a hilo_b200 estimator module (missing hbm_* symbols)", module_path);
+    dlclose(dl);
+    delete h;
+    return -3;
+  }
+  h->dims(&h->d);
+  *out = h;
+  return 0;
+}
+
+int hb_est_get_dims(hb_est_t h, hb_est_dims* dims) {
+  if (h == nullptr || dims == nullptr) { set_err("hb_est_get_dims: null argument"); return -1; }
+  *dims = h->d;
+  return 0;
+}
+
+size_t hb_est_work_doubles(hb_est_t h, int B, int n_particles) {
+  if (h == nullptr || B <= 0) return 0;
+  return h->work(B, n_particles > 0 ? n_particles : 0);
+}
+
+static int est_forward(const char* what, hb_est_t h, const hb_est_call* c, int (*fn)(const hb_est_call*)) {
+  if (h == nullptr || c == nullptr) { set_err("%s: null argument", what); return -1; }
+  const int rc = fn(c);
+  if (rc < 0) set_err("%s: invalid call (code %d: -1 batch, -2 workspace/particles, -4 missing array)", what, rc);
+  if (rc > 0) set_err("%s: CUDA error %d (%s)", what, rc, cudaGetErrorString((cudaError_t)rc));
+  return rc;
+}
+int hb_sim_step(hb_est_t h, const hb_est_call* c) { return est_forward("hb_sim_step", h, c, h ? h->sim : nullptr); }
+int hb_ekf_step(hb_est_t h, const hb_est_call* c) { return est_forward("hb_ekf_step", h, c, h ? h->ekf : nullptr); }
+int hb_ukf_step(hb_est_t h, const hb_est_call* c) { return est_forward("hb_ukf_step", h, c, h ? h->ukf : nullptr); }
+int hb_pf_step(hb_est_t h, const hb_est_call* c) { return est_forward("hb_pf_step", h, c, h ? h->pf : nullptr); }
+
+int hb_est_close(hb_est_t h) {
+  if (h == nullptr) return -1;
+  if (h->dl) dlclose(h->dl);
+  delete h;
+  return 0;
+}
+
+int hb_pf_resample(int B, int n, const double* q, const double* unif, double* cdf_work, long long* idx, void* stream) {
+  if (B <= 0 || n <= 0 || !q || !unif || !cdf_work || !idx) { set_err("hb_pf_resample: invalid argument"); return -1; }
+  hb::EstArgs a;
+  memset(&a, 0, sizeof(a));
+  a.B = B; a.n_particles = n; a.q = const_cast<double*>(q); a.unif = unif; a.cdf = cdf_work; a.idx = idx;
+  hb::launch_1d<hb::PfResampleOnly>(a, B, (cudaStream_t)stream);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_err("hb_pf_resample: %s", cudaGetErrorString(e)); return (int)e; }
+  return 0;
 }
 
 int hb_ocp_close(hb_ocp_t h) {

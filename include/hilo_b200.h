@@ -94,6 +94,58 @@ size_t hb_ocp_work_doubles(hb_ocp_t h, int B, int n_alpha);
 int hb_ocp_solve(hb_ocp_t h, const hb_ocp_call* call);   /* synchronises `stream` only to poll convergence */
 int hb_ocp_close(hb_ocp_t h);
 
+/* ------------------------------------------------------------------------------------------------ estimators
+ * A generated estimator module holds the model's f / h device functions and their Jacobians.  One call = one
+ * estimate() of the reference for B independent filters:
+ *   hb_ekf_step  KF / EKF predict + update   (estimator/kf.py:71-186, 304-307)
+ *   hb_ukf_step  UKF predict + update        (estimator/kf.py:486-604)
+ *   hb_pf_step   PF propagate / weight / resample / moments (estimator/pf.py:103-166, 363-421)
+ *   hb_sim_step  one sampling interval of Model.simulate   (dynamic_model/dynamic_model.py:3911-4212)           */
+typedef struct hb_est_dims { int nx, nu, np, ny, nye, discrete; } hb_est_dims;
+
+typedef struct hb_est_call {
+  int B;                     /* number of filter instances                                                       */
+  int substeps;              /* RK4 sub-steps per sampling interval for continuous models                        */
+  int n_particles;           /* PF only                                                                          */
+  int do_predict, do_update; /* KF.predict()/update() pass-throughs (kf.py:309-325); estimate() sets both        */
+  double dt, t0;
+  double alpha, beta, kappa; /* UKF tuning (kf.py:428)                                                           */
+  double* x;                 /* in/out [B][nx]                                                                    */
+  double* P;                 /* in/out [B][nx][nx]                                                                */
+  double* X;                 /* UKF: in/out [B][2nx+1][nx] sigma points; PF: in/out [B][n_particles][nx]          */
+  const double* y;           /* [B][nye] measurements                                                             */
+  const double* u;           /* [B|1][nu]                                                                         */
+  long long u_stride;
+  const double* p;           /* [B|1][np]                                                                         */
+  long long p_stride;
+  const double* Q;           /* [nx][nx] process noise covariance                                                 */
+  const double* R;           /* [nye][nye] measurement noise covariance                                           */
+  double* y_pred;            /* out [B][nye]                                                                      */
+  const double* w;           /* PF: [B][n_particles][nx] process-noise samples                                    */
+  const double* v;           /* PF: [B][n_particles][nye] measurement-noise samples                               */
+  const double* unif;        /* PF: [B][n_particles] uniforms consumed by the resampling                          */
+  double* q;                 /* PF out: [B][n_particles] normalised weights                                       */
+  long long* idx;            /* PF out: [B][n_particles] resampled indices (== np.random.choice on the same RNG)  */
+  double* work;              /* PF workspace of hb_est_work_doubles(B, n_particles) doubles                       */
+  size_t work_doubles;
+  int* status;               /* out [B]: 0 ok, -1 numerical failure                                               */
+  void* stream;
+} hb_est_call;
+
+typedef struct hb_est* hb_est_t;
+int hb_est_open(const char* module_path, hb_est_t* out);
+int hb_est_get_dims(hb_est_t h, hb_est_dims* dims);
+size_t hb_est_work_doubles(hb_est_t h, int B, int n_particles);
+int hb_sim_step(hb_est_t h, const hb_est_call* call);
+int hb_ekf_step(hb_est_t h, const hb_est_call* call);
+int hb_ukf_step(hb_est_t h, const hb_est_call* call);
+int hb_pf_step(hb_est_t h, const hb_est_call* call);
+int hb_est_close(hb_est_t h);
+
+/* Model-independent resampling (replaces np.random.choice(n, n, p=q), estimator/pf.py:406): q [B][n], unif [B][n],
+ * cdf_work [B][n] scratch, idx [B][n] out; indices are bit-identical to NumPy's for the same q and uniforms.      */
+int hb_pf_resample(int B, int n, const double* q, const double* unif, double* cdf_work, long long* idx, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,137 @@
+"""GPU parity for the estimator rows of SURVEY.md §8a (a5 KF/EKF, a6 UKF, a7 PF) through the public API and the C ABI.
+Golden numbers are the reference's own (tests/test_KFs.py); batched cases are compared with the NumPy oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from test_hostsim_estimators import _cstr, kf_model, scalar_model  # model builders shared with the CPU tests
+
+
+def test_kalman_filter_one_step_and_passthroughs(cuda_device):
+    from hilo_mpc_b200 import KF
+    model = kf_model()
+    kf = KF(model)
+    kf.setup()
+    model.set_initial_conditions([.8, 0.])
+    model.set_initial_parameter_values([.5, .4])
+    kf.R = .064
+    kf.Q = [.01, .01]
+    kf.set_initial_guess([.8, 0.])
+    kf.set_initial_parameter_values([.5, .4])
+    model.simulate(u=.8)
+    np.testing.assert_allclose(model.solution['x:f'], [[1.2], [.4]], rtol=1e-12)  # ERK1 of the linear model
+    kf.estimate(y=.3894626, u=.8)
+    np.testing.assert_allclose(kf.solution.get_by_id('x:f'), np.array([[1.19614861], [.39044856]]), rtol=1e-7)
+    # tests/test_KFs.py:489-522
+    kf2 = KF(model)
+    kf2.setup()
+    pred = kf2.predict(np.append(np.array([[.8], [0.]]), np.eye(2), axis=1), np.append([.8], [.5, .4]), .01 * np.eye(2))
+    np.testing.assert_allclose(pred, np.array([[1.2, .26, .25], [.4, .25, .62]]))
+    upd, y_pred = kf2.update(np.array([[1.2, .26, .25], [.4, .25, .62]]), .322052, np.append([.8], [.5, .4]), .064)
+    np.testing.assert_allclose(upd, np.array([[1.17151023, .16862573, .023391813], [.32934538, .023391813, .0580117]]),
+                               rtol=2e-7)
+    np.testing.assert_allclose(y_pred, np.array([[.4]]))
+
+
+def test_ekf_ukf_one_step_golden(cuda_device):
+    from hilo_mpc_b200 import EKF, UKF
+    for cls, ref in ((EKF, 7.206059), (UKF, 7.2739647)):
+        est_ = cls(scalar_model())
+        est_.setup()
+        est_.Q = 10.
+        est_.R = 1.
+        est_.set_initial_guess(9.)
+        est_.estimate(y=2.59109)
+        np.testing.assert_allclose(est_.solution.get_by_id('x:f'), np.array([[ref]]), rtol=1e-7)
+
+
+def test_kf_rejects_nonlinear_and_ekf_warns_on_linear():
+    from hilo_mpc_b200 import EKF, KF, UKF
+    with pytest.raises(ValueError):
+        KF(scalar_model())
+    with pytest.warns(UserWarning):
+        EKF(kf_model())
+    with pytest.warns(UserWarning):
+        UKF(kf_model())
+
+
+def test_batched_ukf_cstr_matches_oracle(cuda_device):
+    import torch
+    from hilo_mpc_b200 import UKF
+    from oracle import estimators as est
+    m, f, hfun, x_ss, u_ss = _cstr()
+    B = 512
+    rng = np.random.default_rng(2)
+    x0 = x_ss + rng.normal(size=(B, 4)) * np.array([.05, .05, 1., 1.])
+    ys = np.column_stack([x_ss[1] + rng.normal(size=B) * .02, x_ss[2] + rng.normal(size=B) * .3])
+    Q, R = np.diag([1e-4, 1e-4, 1e-2, 1e-2]), np.diag([1e-3, 1e-1])
+    ukf = UKF(m, alpha=.5)
+    ukf.setup()
+    ukf.Q, ukf.R = Q, R
+    P0 = np.diag([1e-2, 1e-2, 1., 1.])
+    ukf.set_initial_guess(x0, P0=P0)
+    x, P = ukf.estimate(y=ys, u=u_ss)
+    x, P = x.cpu().numpy(), P.cpu().numpy()
+    for b in (0, 100, 511):
+        xp, Pp, X = est.ukf_predict(f, x0[b], P0, u_ss, None, Q, dt=0.005, discrete=False, substeps=10, alpha=.5)
+        xo, Po, _ = est.ukf_update(hfun, xp, Pp, X, ys[b], u_ss, None, R, alpha=.5)
+        np.testing.assert_allclose(x[b], xo, rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose(P[b], Po, rtol=1e-7, atol=1e-12)
+
+
+def test_particle_filter_indices_bit_exact(cuda_device):
+    import torch
+    from hilo_mpc_b200 import PF
+    from oracle import estimators as est
+    pf = PF(scalar_model())
+    pf.setup(n_samples=200)
+    pf.Q, pf.R = 10., 1.
+    B, ns = 256, 200
+    rng = np.random.default_rng(7)
+    pf.set_initial_guess(np.full((B, 1), 9.))
+    X = rng.normal(9., 1., size=(B, ns, 1))
+    pf.set_particles(X)
+    w = rng.normal(0., np.sqrt(10.), size=(B, ns, 1))
+    v = rng.normal(0., 1., size=(B, ns, 1))
+    unif = rng.random((B, ns))
+    y = rng.uniform(1., 8., size=(B, 1))
+    x, P = pf.estimate(y=y, w=w, v=v, uniforms=unif)
+    q = pf.last_weights.cpu().numpy()
+    idx = pf.last_indices.cpu().numpy()
+    f, hfun = (lambda x_, u, p: x_ / 2 + 25 * x_ / (1 + x_ ** 2)), (lambda x_, u, p: x_ ** 2 / 20)
+    for b in range(B):
+        np.testing.assert_array_equal(idx[b], est.pf_resample_indices(q[b], unif[b]))
+    for b in (0, 255):
+        xm, Pm, _, qo, io = est.pf_step(f, hfun, X[b].T, y[b], None, None, w[b].T, v[b].T, np.array([[1.]]), unif[b])
+        np.testing.assert_allclose(q[b], qo, rtol=1e-12)
+        np.testing.assert_array_equal(idx[b], io)
+        np.testing.assert_allclose(x[b].cpu().numpy(), xm, rtol=1e-12)
+
+
+def test_pf_resample_entry_matches_numpy_choice(cuda_device):
+    """hb_pf_resample vs np.random.choice on the legacy global RNG (pf.py:406), including a large ragged case."""
+    import ctypes as C
+    import torch
+    from hilo_mpc_b200 import _lib
+    lib = _lib.load()
+    for n in (15, 1000, 4097):
+        B = 7
+        rngq = np.random.default_rng(n)
+        q = rngq.random((B, n))
+        q /= q.sum(axis=1, keepdims=True)
+        ref, unif = [], []
+        for b in range(B):
+            np.random.seed(100 + b)
+            ref.append(np.random.choice(n, size=n, replace=True, p=q[b]))
+            np.random.seed(100 + b)
+            unif.append(np.random.random_sample(n))
+        qt = torch.tensor(q, device=cuda_device)
+        ut = torch.tensor(np.stack(unif), device=cuda_device)
+        cdf = torch.empty_like(qt)
+        idx = torch.zeros(B, n, dtype=torch.int64, device=cuda_device)
+        lib.hb_pf_resample.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        rc = lib.hb_pf_resample(B, n, qt.data_ptr(), ut.data_ptr(), cdf.data_ptr(), idx.data_ptr(),
+                                torch.cuda.current_stream().cuda_stream)
+        assert rc == 0
+        np.testing.assert_array_equal(idx.cpu().numpy(), np.stack(ref))

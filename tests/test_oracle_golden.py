@@ -1,0 +1,96 @@
+"""Pins the oracle restatements on the golden numbers held by the reference's own tests."""
+import numpy as np
+
+from oracle import estimators as est
+from oracle.gp import GpOracle, se_kernel
+from oracle.lqr import lqr_gain
+
+
+def _kf_model():
+    # tests/test_KFs.py:252-262: dx1 = -k1 x1 + u, dx2 = k1 x1 - k2 x2, y = x2, ERK1 with dt = 1
+    def f(x, u, p):
+        return np.array([x[0] + (-p[0] * x[0] + u[0]), x[1] + (p[0] * x[0] - p[1] * x[1])])
+
+    def h(x, u, p):
+        return np.array([x[1]])
+    return f, h
+
+
+def test_kf_predict_golden():  # tests/test_KFs.py:489-503
+    f, _ = _kf_model()
+    x, P = est.ekf_predict(f, np.array([.8, 0.]), np.eye(2), np.array([.8]), np.array([.5, .4]), .01 * np.eye(2))
+    np.testing.assert_allclose(np.column_stack([x, P]), [[1.2, .26, .25], [.4, .25, .62]], rtol=1e-12)
+
+
+def test_kf_update_golden():  # tests/test_KFs.py:505-522
+    _, h = _kf_model()
+    pred = np.array([[1.2, .26, .25], [.4, .25, .62]])
+    x, P, yp = est.ekf_update(h, pred[:, 0], pred[:, 1:], .322052, np.array([.8]), np.array([.5, .4]), np.array([[.064]]))
+    np.testing.assert_allclose(np.column_stack([x, P]), [[1.17151023, .16862573, .023391813],
+                                                         [.32934538, .023391813, .0580117]], rtol=2e-7)
+    np.testing.assert_allclose(yp, [.4])
+
+
+def test_kf_one_step_golden():  # tests/test_KFs.py:298-335
+    f, h = _kf_model()
+    u, p = np.array([.8]), np.array([.5, .4])
+    x, P = est.ekf_predict(f, np.array([.8, 0.]), np.eye(2), u, p, .01 * np.eye(2))
+    x, P, _ = est.ekf_update(h, x, P, .3894626, u, p, np.array([[.064]]))
+    np.testing.assert_allclose(x, [1.19614861, .39044856], rtol=1e-7)
+
+
+def _scalar_model():
+    # tests/test_KFs.py:553-557: x+ = x/2 + 25 dt x/(1+x^2), y = x^2/20, dt = 1
+    return (lambda x, u, p: x / 2 + 25 * x / (1 + x ** 2)), (lambda x, u, p: x ** 2 / 20)
+
+
+def test_ekf_one_step_golden():  # tests/test_KFs.py:548-566
+    f, h = _scalar_model()
+    x, P = est.ekf_predict(f, np.array([9.]), np.eye(1), None, None, 10. * np.eye(1))
+    x, P, _ = est.ekf_update(h, x, P, 2.59109, None, None, np.eye(1))
+    np.testing.assert_allclose(x, [7.206059], rtol=1e-7)
+
+
+def test_ukf_one_step_golden():  # tests/test_KFs.py:606-624 (alpha=1e-3, beta=2, kappa=0)
+    f, h = _scalar_model()
+    x, P, X = est.ukf_predict(f, np.array([9.]), np.eye(1), None, None, 10. * np.eye(1))
+    x, P, _ = est.ukf_update(h, x, P, X, 2.59109, None, None, np.eye(1))
+    np.testing.assert_allclose(x, [7.2739647], rtol=1e-7)
+
+
+def test_lqr_riccati_golden():  # tests/test_LQR.py:314-342: x+ = x + dt(2y + p u), y+ = y - dt x, z+ = z + dt w
+    for p, K_ref in ((1., [[1.39207671, 1.35221712, 0.], [0., 0., .61802575]]),
+                     (0., [[0., 0., 0.], [0., 0., .61802575]])):
+        A = np.array([[1., 2., 0.], [-1., 1., 0.], [0., 0., 1.]])
+        B = np.array([[p, 0.], [0., 0.], [0., 1.]])
+        K, _ = lqr_gain(A, B, np.eye(3), np.eye(2), horizon=5)
+        np.testing.assert_allclose(K, K_ref, rtol=1e-7, atol=1e-12)
+
+
+def test_se_gram_golden():  # tests/test_kernels.py:262-277, 370-388
+    x = np.array([[1., 2., 3., 4., 5.]])
+    np.testing.assert_allclose(se_kernel(x)[0], [1., .60653066, .135335283, .0111089965, .000335462628], rtol=1e-7)
+    cov = se_kernel(x, x / 2.)
+    np.testing.assert_allclose(cov[0], [.8824969, 1., .8824969, .60653066, .32465247], rtol=1e-7)
+    np.testing.assert_allclose(cov[4], [.0000400652974, .000335462628, .0021874911, .0111089965, .04393693], rtol=1e-7)
+
+
+def test_gp_log_marginal_likelihood_golden():  # tests/test_GPs.py:327-363
+    X = np.array([[0., .5, 1. / np.sqrt(2.), np.sqrt(3.) / 2., 1., 0.],
+                  [1., np.sqrt(3.) / 2., 1. / np.sqrt(2.), .5, 0., -1.]])
+    y = np.array([0., np.pi / 6., np.pi / 4., np.pi / 3., np.pi / 2., np.pi])
+    gp = GpOracle(X, y, noise_variance=1., signal_variance=1., length_scales=1.)
+    np.testing.assert_approx_equal(gp.log_marginal_likelihood(), -9.82229944, significant=9)
+
+
+def test_pf_resampling_matches_numpy_choice():
+    """pf.py:406: indices must be bit-identical to ``np.random.choice(n, n, p=q)`` on the legacy global RNG."""
+    rng_q = np.random.default_rng(3)
+    for n in (15, 64, 1000):
+        q = rng_q.random(n)
+        q /= q.sum()
+        np.random.seed(1234)
+        ref = np.random.choice(n, size=n, replace=True, p=q)
+        np.random.seed(1234)
+        u = np.random.random_sample(n)
+        np.testing.assert_array_equal(est.pf_resample_indices(q, u), ref)
