@@ -1,0 +1,295 @@
+// Gaussian-process regression kernels (squared-exponential covariance, exact inference) — model independent.
+//
+// Replace the reference's symbolic graph (hilo_mpc/modules/machine_learning/gp/inference.py:197-217: K = kernel(X, X),
+// L = chol(sigma_n^2 I + K), alpha = L^-T L^-1 (y - m), LML, mu* = m + K*^T alpha, var* = k** - v^T v with v = L^-1 K*;
+// SE covariance hilo_mpc/modules/machine_learning/gp/kernel.py:650-734: k = sigma_f^2 exp(-1/2 sum_k ((x_k - x'_k)/l_k)^2)).
+// Data layout as in the reference: X is (n_features, n_observations), row-major.
+//
+// The dense contractions (trailing update of the blocked Cholesky, L^-1 K* for the predictive variance) run on the
+// fp64 tensor pipe (mma.sync m8n8k4 f64 — tcgen05 has no fp64 path); the Gram/cross-covariance entries need one exp
+// each and are elementwise.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+
+#include "../../include/hilo_b200.h"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ covariance
+// C[i][j] = sf2 * exp(-0.5 * sum_k ((A[k][i] - B[k][j]) / ls[k])^2) (+ noise on the diagonal when A == B)
+__global__ void se_cov_kernel(int d, int na, int nb, const double* __restrict__ A, const double* __restrict__ Bm,
+                              const double* __restrict__ ls, double sf2, double noise, double* __restrict__ C, int ldc) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y;
+  if (j >= nb) return;
+  double d2 = 0.0;
+  for (int k = 0; k < d; ++k) {
+    const double r = (A[(size_t)k * na + i] - Bm[(size_t)k * nb + j]) / ls[k];
+    d2 += r * r;
+  }
+  double v = sf2 * exp(-0.5 * d2);
+  if (noise != 0.0 && i == j) v += noise;
+  C[(size_t)i * ldc + j] = v;
+}
+
+// ------------------------------------------------------------------------------------------------ DMMA GEMM
+// C (M x N, row-major, ldc) = beta * C + alpha * A (M x K, row-major, lda) * op(B)
+//   transB == 0: B is K x N row-major (ldb);  transB == 1: B is N x K row-major (ldb), i.e. C += A * B^T
+// lower_only: skip tiles strictly above the diagonal (symmetric rank-k update); tri_k: A is lower triangular, so the
+// K loop of a row tile stops at its last column.
+constexpr int TM = 32, TN = 32, TK = 16;
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(128) dgemm_dmma_kernel(int M, int N, int K, double alpha, const double* __restrict__ A,
+                                                         int lda, const double* __restrict__ B, int ldb, int transB,
+                                                         double beta, double* __restrict__ C, int ldc, int lower_only,
+                                                         int tri_k) {
+  const int tm = blockIdx.y * TM, tn = blockIdx.x * TN;
+  if (lower_only && tn > tm + TM - 1) return;
+  __shared__ double As[TM][TK + 1];
+  __shared__ double Bs[TK][TN + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wm = (warp >> 1) * 16, wn = (warp & 1) * 16;  // each warp: 16 x 16 = 2 x 2 mma tiles
+  double acc[2][2][2] = {};
+  const int kmax = tri_k ? min(K, tm + TM) : K;
+  for (int k0 = 0; k0 < kmax; k0 += TK) {
+    for (int e = threadIdx.x; e < TM * TK; e += 128) {
+      const int r = e / TK, c = e % TK;
+      const int gr = tm + r, gc = k0 + c;
+      As[r][c] = (gr < M && gc < K) ? A[(size_t)gr * lda + gc] : 0.0;
+    }
+    for (int e = threadIdx.x; e < TK * TN; e += 128) {
+      const int r = e / TN, c = e % TN;  // r: k index, c: n index
+      const int gk = k0 + r, gn = tn + c;
+      double v = 0.0;
+      if (gk < K && gn < N) v = transB ? B[(size_t)gn * ldb + gk] : B[(size_t)gk * ldb + gn];
+      Bs[r][c] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < TK; kk += 4) {
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) {
+        const double a = As[wm + mi * 8 + (lane >> 2)][kk + (lane & 3)];
+#pragma unroll
+        for (int ni = 0; ni < 2; ++ni) {
+          const double b = Bs[kk + (lane & 3)][wn + ni * 8 + (lane >> 2)];
+          dmma(acc[mi][ni][0], acc[mi][ni][1], a, b);
+        }
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int r = tm + wm + mi * 8 + (lane >> 2), c = tn + wn + ni * 8 + 2 * (lane & 3) + e;
+        if (r < M && c < N) {
+          const double old = (beta == 0.0) ? 0.0 : beta * C[(size_t)r * ldc + c];
+          C[(size_t)r * ldc + c] = old + alpha * acc[mi][ni][e];
+        }
+      }
+}
+
+void dgemm_dmma(int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb, int transB,
+                double beta, double* C, int ldc, int lower_only, int tri_k, cudaStream_t s) {
+  if (M <= 0 || N <= 0) return;
+  dim3 grid((N + TN - 1) / TN, (M + TM - 1) / TM);
+  dgemm_dmma_kernel<<<grid, 128, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, transB, beta, C, ldc, lower_only, tri_k);
+}
+
+// ------------------------------------------------------------------------------------------------ blocked Cholesky
+constexpr int NB = 32;
+
+// factor the diagonal block (nb x nb, nb <= 32) in place, one CTA of 32 threads; flag != 0 on a non-positive pivot
+__global__ void potrf_block_kernel(double* __restrict__ A, int lda, int j0, int nb, int* __restrict__ flag) {
+  __shared__ double T[NB][NB + 1];
+  const int t = threadIdx.x;
+  for (int c = 0; c < nb; ++c)
+    if (t < nb) T[t][c] = A[(size_t)(j0 + t) * lda + j0 + c];
+  __syncwarp();
+  for (int j = 0; j < nb; ++j) {
+    double d = T[j][j];
+    if (t == 0) {
+      if (!(d > 0.0)) { *flag = j0 + j + 1; d = 1.0; }
+      T[j][j] = sqrt(d);
+    }
+    __syncwarp();
+    const double piv = T[j][j];
+    if (t > j && t < nb) T[t][j] /= piv;
+    __syncwarp();
+    if (t > j && t < nb)
+      for (int c = j + 1; c <= t; ++c) T[t][c] -= T[t][j] * T[c][j];
+    __syncwarp();
+  }
+  for (int c = 0; c < nb; ++c)
+    if (t < nb) A[(size_t)(j0 + t) * lda + j0 + c] = (c <= t) ? T[t][c] : 0.0;
+}
+
+// rows below the diagonal block: A[i, j0:j0+nb] <- A[i, j0:j0+nb] * L_jj^-T  (one thread per row)
+__global__ void trsm_panel_kernel(double* __restrict__ A, int lda, int n, int j0, int nb) {
+  __shared__ double Ld[NB][NB + 1];
+  for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) Ld[e / nb][e % nb] = A[(size_t)(j0 + e / nb) * lda + j0 + e % nb];
+  __syncthreads();
+  const int i = j0 + nb + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double row[NB];
+  for (int c = 0; c < nb; ++c) row[c] = A[(size_t)i * lda + j0 + c];
+  for (int c = 0; c < nb; ++c) {
+    double s = row[c];
+    for (int l = 0; l < c; ++l) s -= row[l] * Ld[c][l];
+    row[c] = s / Ld[c][c];
+  }
+  for (int c = 0; c < nb; ++c) A[(size_t)i * lda + j0 + c] = row[c];
+}
+
+__global__ void zero_upper_kernel(double* __restrict__ A, int lda, int n) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  if (j < n && j > i) A[(size_t)i * lda + j] = 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------ triangular inverse
+// Linv = L^-1 (lower): column j by forward substitution, one CTA per column; rows are processed in order with the
+// inner products reduced across the CTA.
+__global__ void __launch_bounds__(128) tri_inverse_kernel(int n, const double* __restrict__ L, int ldl,
+                                                          double* __restrict__ X, int ldx) {
+  extern __shared__ double xs[];  // column j of the inverse
+  __shared__ double red[4];
+  const int j = blockIdx.x;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) xs[i] = 0.0;
+  __syncthreads();
+  for (int i = j; i < n; ++i) {
+    double s = 0.0;
+    for (int k = j + threadIdx.x; k < i; k += blockDim.x) s += L[(size_t)i * ldl + k] * xs[k];
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const double tot = red[0] + red[1] + red[2] + red[3];
+      xs[i] = (((i == j) ? 1.0 : 0.0) - tot) / L[(size_t)i * ldl + i];
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) X[(size_t)i * ldx + j] = xs[i];
+}
+
+// out[i] = sum_k op(M)[i][k] v[k]   (one warp per row; trans: use column i of M)
+__global__ void gemv_kernel(int n, const double* __restrict__ Mx, int ld, int trans, const double* __restrict__ v,
+                            double* __restrict__ out) {
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (i >= n) return;
+  double s = 0.0;
+  for (int k = lane; k < n; k += 32) s += (trans ? Mx[(size_t)k * ld + i] : Mx[(size_t)i * ld + k]) * v[k];
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if (lane == 0) out[i] = s;
+}
+
+__global__ void residual_kernel(int n, const double* __restrict__ y, double mean, double* __restrict__ r) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) r[i] = y[i] - mean;
+}
+
+// lml = -1/2 r^T alpha - sum log L_ii - n/2 log(2 pi)   (single CTA)
+__global__ void lml_kernel(int n, const double* __restrict__ r, const double* __restrict__ alpha,
+                           const double* __restrict__ L, int ldl, double* __restrict__ out) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += -0.5 * r[i] * alpha[i] - log(L[(size_t)i * ldl + i]);
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) tot += red[w];
+    out[0] = tot - 0.5 * n * log(2.0 * M_PI);
+  }
+}
+
+// mean[m] = prior + sum_i Ks[i][m] alpha[i];   var[m] = sf2 (+ noise) - sum_i V[i][m]^2
+__global__ void predict_reduce_kernel(int n, int M, const double* __restrict__ Ks, const double* __restrict__ V,
+                                      const double* __restrict__ alpha, double prior, double sf2, double noise,
+                                      double* __restrict__ mean, double* __restrict__ var) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  double mu = prior, vv = 0.0;
+  for (int i = 0; i < n; ++i) {
+    mu += Ks[(size_t)i * M + m] * alpha[i];
+    if (V != nullptr) { const double t = V[(size_t)i * M + m]; vv += t * t; }
+  }
+  mean[m] = mu;
+  if (var != nullptr) var[m] = sf2 + noise - vv;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t hb_gp_fit_work_doubles(int n) { return (size_t)n * 2 + 8; }
+
+int hb_gp_fit(int n, int d, const double* X, const double* y, const double* length_scales, double signal_variance,
+              double noise_variance, double prior_mean, double* L, double* Linv, double* alpha, double* lml,
+              double* work, int* info, void* stream) {
+  if (n <= 0 || d <= 0 || !X || !y || !length_scales || !L || !Linv || !alpha || !lml || !work || !info) return -1;
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaMemsetAsync(info, 0, sizeof(int), s);
+  {
+    dim3 grid((n + 127) / 128, n);
+    se_cov_kernel<<<grid, 128, 0, s>>>(d, n, n, X, X, length_scales, signal_variance, noise_variance, L, n);
+  }
+  for (int j0 = 0; j0 < n; j0 += NB) {
+    const int nb = (n - j0 < NB) ? (n - j0) : NB;
+    potrf_block_kernel<<<1, 32, 0, s>>>(L, n, j0, nb, info);
+    const int rest = n - j0 - nb;
+    if (rest > 0) {
+      trsm_panel_kernel<<<(rest + 63) / 64, 64, 0, s>>>(L, n, n, j0, nb);
+      // trailing update A22 -= L21 L21^T on the tensor pipe (lower triangle only)
+      const double* L21 = L + (size_t)(j0 + nb) * n + j0;
+      double* A22 = L + (size_t)(j0 + nb) * n + (j0 + nb);
+      dgemm_dmma(rest, rest, nb, -1.0, L21, n, L21, n, 1, 1.0, A22, n, 1, 0, s);
+    }
+  }
+  {
+    dim3 grid((n + 127) / 128, n);
+    zero_upper_kernel<<<grid, 128, 0, s>>>(L, n, n);
+  }
+  tri_inverse_kernel<<<n, 128, (size_t)n * sizeof(double), s>>>(n, L, n, Linv, n);
+  double* r = work;
+  double* tmp = work + n;
+  residual_kernel<<<(n + 127) / 128, 128, 0, s>>>(n, y, prior_mean, r);
+  gemv_kernel<<<(n + 3) / 4, 128, 0, s>>>(n, Linv, n, 0, r, tmp);      // tmp = L^-1 r
+  gemv_kernel<<<(n + 3) / 4, 128, 0, s>>>(n, Linv, n, 1, tmp, alpha);  // alpha = L^-T tmp
+  lml_kernel<<<1, 256, 0, s>>>(n, r, alpha, L, n, lml);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
+size_t hb_gp_predict_work_doubles(int n, int M) { return (size_t)2 * n * M + 8; }
+
+int hb_gp_predict(int n, int d, int M, const double* X, const double* Xq, const double* length_scales,
+                  double signal_variance, double noise_variance, double prior_mean, const double* Linv,
+                  const double* alpha, double* mean, double* var, double* work, void* stream) {
+  if (n <= 0 || d <= 0 || M <= 0 || !X || !Xq || !length_scales || !alpha || !mean || !work) return -1;
+  if (var != nullptr && Linv == nullptr) return -1;
+  cudaStream_t s = (cudaStream_t)stream;
+  double* Ks = work;                  // [n][M] cross covariance
+  double* V = work + (size_t)n * M;   // [n][M] L^-1 K*
+  dim3 grid((M + 127) / 128, n);
+  se_cov_kernel<<<grid, 128, 0, s>>>(d, n, M, X, Xq, length_scales, signal_variance, 0.0, Ks, M);
+  if (var != nullptr) dgemm_dmma(n, M, n, 1.0, Linv, n, Ks, M, 0, 0.0, V, M, 0, 1, s);
+  predict_reduce_kernel<<<(M + 127) / 128, 128, 0, s>>>(n, M, Ks, var ? V : nullptr, alpha, prior_mean,
+                                                        signal_variance, noise_variance, mean, var);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
+}  // extern "C"

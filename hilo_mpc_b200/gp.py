@@ -1,0 +1,225 @@
+"""Gaussian-process regression with the reference's API (squared-exponential kernel, exact inference) on the GPU.
+
+Mirrors ``hilo_mpc/modules/machine_learning/gp/gp.py`` (``GaussianProcess`` :112, ``set_training_data`` :378, ``setup``
+:522, ``predict`` :699, ``log_marginal_likelihood`` :653, ``noise_variance`` :302) and ``kernel.py``
+(``Kernel.squared_exponential`` :229-260, ``SquaredExponentialKernel`` :704-734).  Numeric queries run the
+``hb_gp_fit`` / ``hb_gp_predict`` kernels (Gram, blocked Cholesky with fp64 tensor-core trailing updates, ``L^-1 K*`` on
+the tensor pipe); symbolic queries (``predict(x_sym)``, which is how the reference embeds a GP into a ``Model``,
+``dynamic_model.py:3040-3080``) return the posterior mean/variance as expressions of the fitted numbers.
+Hyper-parameter training (``fit_model``) is a "next" row and not implemented.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import warnings
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from . import symbolic as sx
+
+
+class SquaredExponentialKernel:
+    acronym = 'SE'
+
+    def __init__(self, active_dims=None, signal_variance=1., length_scales=1., ard=False, bounds=None):
+        self.active_dims = None if active_dims is None else list(active_dims)
+        self.signal_variance = float(signal_variance)
+        self.length_scales = np.atleast_1d(np.asarray(length_scales, dtype=float))
+        self.ard = bool(ard)
+
+    def length_scale_vector(self, d: int) -> np.ndarray:
+        ls = self.length_scales
+        if ls.size == 1:
+            return np.full(d, float(ls[0]))
+        if ls.size != d:
+            raise ValueError("Length scales vector dimension does not equal input space dimension.")
+        return ls.copy()
+
+    def __call__(self, X, X_bar=None):
+        """Numeric covariance matrix (kernel.py:97-140) — small host-side helper used by tests / set-up code."""
+        X = np.atleast_2d(np.asarray(X, dtype=float))
+        Xb = X if X_bar is None else np.atleast_2d(np.asarray(X_bar, dtype=float))
+        if X.shape[0] != Xb.shape[0]:
+            raise AssertionError("X and X_bar do not have the same input space dimensions")
+        ls = self.length_scale_vector(X.shape[0])
+        d2 = (((X[:, :, None] - Xb[:, None, :]) / ls[:, None, None]) ** 2).sum(0)
+        return self.signal_variance * np.exp(-.5 * d2)
+
+
+class Kernel:
+    @staticmethod
+    def squared_exponential(active_dims=None, signal_variance=1., length_scales=1., ard=False, bounds=None):
+        return SquaredExponentialKernel(active_dims, signal_variance, length_scales, ard, bounds)
+
+    @staticmethod
+    def _unsupported(name):
+        def factory(*args, **kwargs):
+            raise NotImplementedError(f"Kernel '{name}' is not supported by the B200 engine yet (SURVEY.md §2 row 7: "
+                                      f"only the squared-exponential kernel is on the hot path)")
+        return factory
+
+
+for _name in ('matern_32', 'matern_52', 'exponential', 'rational_quadratic', 'periodic', 'linear', 'polynomial',
+              'constant', 'neural_network', 'gamma_exponential', 'piecewise_polynomial', 'dot_product'):
+    setattr(Kernel, _name, staticmethod(Kernel._unsupported(_name)))
+
+
+class GaussianProcess:
+    def __init__(self, features, labels, inference=None, likelihood=None, mean=None, kernel=None, noise_variance=1.,
+                 hyperprior=None, id=None, name=None, solver=None, solver_options=None, **kwargs):
+        self.features = [features] if isinstance(features, str) else list(features)
+        labels = [labels] if isinstance(labels, str) else list(labels)
+        if len(labels) > 1:
+            raise ValueError("Training a GP on multiple labels is not supported. Please use 'GPArray'.")  # gp.py:133-135
+        self.labels = labels
+        self.kernel = kernel if kernel is not None else Kernel.squared_exponential()
+        if not isinstance(self.kernel, SquaredExponentialKernel):
+            raise NotImplementedError("Only the squared-exponential kernel is supported by the B200 engine")
+        self.prior_mean = 0. if mean is None else float(mean)
+        self.noise_variance = float(noise_variance)
+        self.id, self.name = id, name or 'GP'
+        self._X = self._y = None
+        self._is_setup = False
+        self._fit = None  # device tensors: X, L, Linv, alpha, ls ; host copies: alpha, lml
+
+    @property
+    def n_features(self):
+        return len(self.features)
+
+    @property
+    def X_train(self):
+        return self._X
+
+    @property
+    def y_train(self):
+        return self._y
+
+    def set_training_data(self, X, y) -> None:
+        X = np.atleast_2d(np.asarray(X, dtype=float))
+        y = np.atleast_2d(np.asarray(y, dtype=float))
+        if X.shape[0] != self.n_features:
+            raise ValueError(f"Dimension of training inputs does not match the number of features: {X.shape[0]} vs "
+                             f"{self.n_features}")  # gp.py:347-354
+        if y.shape[0] != 1 or y.shape[1] != X.shape[1]:
+            raise ValueError("Number of observations in training matrix and target vector do not match!")
+        if self._is_setup:
+            warnings.warn("Dimensions of training data set changed. Please run setup() method again.")
+        self._X, self._y = X, y
+        self._is_setup = False
+
+    def is_setup(self) -> bool:
+        return self._is_setup
+
+    def setup(self, **kwargs) -> None:
+        """Fit on the device: Gram + Cholesky + alpha + log marginal likelihood (gp.py:522-641, inference.py:197-210)."""
+        if self._X is None or self._y is None:
+            raise RuntimeError("The training data has not been set. Please run the method set_training_data() to "
+                               "proceed.")
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        dev = torch.device('cuda', torch.cuda.current_device())
+        f8 = dict(dtype=torch.float64, device=dev)
+        d, n = self._X.shape
+        ls = self.kernel.length_scale_vector(d)
+        Xt = torch.tensor(self._X, **f8).contiguous()
+        yt = torch.tensor(self._y.reshape(-1), **f8).contiguous()
+        lst = torch.tensor(ls, **f8)
+        L = torch.empty(n, n, **f8)
+        Linv = torch.empty(n, n, **f8)
+        alpha = torch.empty(n, **f8)
+        lml = torch.zeros(1, **f8)
+        info = torch.zeros(1, dtype=torch.int32, device=dev)
+        lib.hb_gp_fit_work_doubles.restype = C.c_size_t
+        work = torch.empty(lib.hb_gp_fit_work_doubles(n), **f8)
+        vp, i, dd = C.c_void_p, C.c_int, C.c_double
+        lib.hb_gp_fit.argtypes = [i, i, vp, vp, vp, dd, dd, dd, vp, vp, vp, vp, vp, vp, vp]
+        rc = lib.hb_gp_fit(n, d, Xt.data_ptr(), yt.data_ptr(), lst.data_ptr(), self.kernel.signal_variance,
+                           self.noise_variance, self.prior_mean, L.data_ptr(), Linv.data_ptr(), alpha.data_ptr(),
+                           lml.data_ptr(), work.data_ptr(), info.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, 'hb_gp_fit')
+        if int(info.item()) != 0:
+            raise RuntimeError(f"Covariance matrix is not positive definite (pivot {int(info.item()) - 1}); increase "
+                               f"the noise variance")
+        self._fit = dict(X=Xt, ls=lst, L=L, Linv=Linv, alpha=alpha, lml=float(lml.item()),
+                         alpha_host=alpha.cpu().numpy(), dev=dev)
+        self._is_setup = True
+
+    def fit_model(self, *args, **kwargs):
+        raise NotImplementedError("Hyper-parameter training is not part of the B200 hot path yet (SURVEY.md §8f-3); set "
+                                  "the hyper-parameters and call setup()")
+
+    def log_marginal_likelihood(self) -> float:
+        if not self._is_setup:
+            raise RuntimeError("The GP has not been set up yet. Please run the setup() method before.")
+        return self._fit['lml']
+
+    def predict(self, X_query, noise_free: bool = False, mean_only: bool = False):
+        """``(mean[1, m], var[1, m])`` for numeric ``X_query`` of shape ``(d, m)`` (NumPy in -> NumPy out, CUDA tensor in
+        -> CUDA tensors out); symbolic queries return expressions (gp.py:699-718)."""
+        if not self._is_setup:
+            raise RuntimeError("The GP has not been set up yet. Please run the setup() method before.")
+        if sx.is_symbolic(X_query):
+            return self._predict_symbolic(sx.as_vector(X_query), noise_free)
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        fit = self._fit
+        is_tensor = torch.is_tensor(X_query)
+        Xq = X_query if is_tensor else torch.as_tensor(np.atleast_2d(np.asarray(X_query, dtype=float)))
+        Xq = Xq.to(device=fit['dev'], dtype=torch.float64)
+        if Xq.dim() == 1:
+            Xq = Xq.reshape(-1, 1)
+        d, n = self._X.shape
+        if Xq.shape[0] != d:
+            raise ValueError(f"Dimension of the query points does not match the number of features: {Xq.shape[0]} vs {d}")
+        Xq = Xq.contiguous()
+        M = Xq.shape[1]
+        f8 = dict(dtype=torch.float64, device=fit['dev'])
+        mean = torch.empty(M, **f8)
+        var = None if mean_only else torch.empty(M, **f8)
+        lib.hb_gp_predict_work_doubles.restype = C.c_size_t
+        lib.hb_gp_predict_work_doubles.argtypes = [C.c_int, C.c_int]
+        work = torch.empty(lib.hb_gp_predict_work_doubles(n, M), **f8)
+        vp, i, dd = C.c_void_p, C.c_int, C.c_double
+        lib.hb_gp_predict.argtypes = [i, i, i, vp, vp, vp, dd, dd, dd, vp, vp, vp, vp, vp, vp]
+        rc = lib.hb_gp_predict(n, d, M, fit['X'].data_ptr(), Xq.data_ptr(), fit['ls'].data_ptr(),
+                               self.kernel.signal_variance, 0. if noise_free else self.noise_variance, self.prior_mean,
+                               fit['Linv'].data_ptr(), fit['alpha'].data_ptr(), mean.data_ptr(),
+                               None if var is None else var.data_ptr(), work.data_ptr(),
+                               torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, 'hb_gp_predict')
+        if is_tensor:
+            return mean.reshape(1, M), (None if var is None else var.reshape(1, M))
+        return mean.cpu().numpy().reshape(1, M), (None if var is None else var.cpu().numpy().reshape(1, M))
+
+    def _predict_symbolic(self, xq, noise_free):
+        d, n = self._X.shape
+        if len(xq) != d:
+            raise ValueError(f"Dimension of the query point does not match the number of features: {len(xq)} vs {d}")
+        ls = self.kernel.length_scale_vector(d)
+        alpha = self._fit['alpha_host']
+        mean = sx.Expr.const(self.prior_mean)
+        ks = []
+        for i in range(n):
+            d2 = sx.Expr.const(0.)
+            for k in range(d):
+                r = (xq[k] - self._X[k, i]) / ls[k]
+                d2 = d2 + r * r
+            ki = self.kernel.signal_variance * sx.exp(-.5 * d2)
+            ks.append(ki)
+            mean = mean + alpha[i] * ki
+        Linv = self._fit['Linv'].cpu().numpy()
+        var = sx.Expr.const(self.kernel.signal_variance + (0. if noise_free else self.noise_variance))
+        if n <= 64:  # the variance expression is O(n^2); only built for small training sets
+            for i in range(n):
+                vi = sx.Expr.const(0.)
+                for j in range(i + 1):
+                    vi = vi + Linv[i, j] * ks[j]
+                var = var - vi * vi
+        else:
+            var = None
+        return np.array([mean], dtype=object), (None if var is None else np.array([var], dtype=object))
+
+
+GP = GaussianProcess

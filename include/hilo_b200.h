@@ -146,6 +146,23 @@ int hb_est_close(hb_est_t h);
  * cdf_work [B][n] scratch, idx [B][n] out; indices are bit-identical to NumPy's for the same q and uniforms.      */
 int hb_pf_resample(int B, int n, const double* q, const double* unif, double* cdf_work, long long* idx, void* stream);
 
+/* ------------------------------------------------------------------------------------------------ Gaussian process
+ * Exact inference with the squared-exponential kernel (machine_learning/gp/inference.py:197-217, kernel.py:650-734).
+ * X is (d, n) row-major like the reference's training data (gp.py:347-354); hyper-parameters are passed in natural
+ * units (signal variance sigma_f^2, length scales l_k, noise variance sigma_n^2).
+ *   hb_gp_fit     : L = chol(sigma_n^2 I + K) [n][n], Linv = L^-1 [n][n], alpha [n], lml [1]; info [1] != 0 when the
+ *                   matrix is not positive definite (index of the failing pivot + 1)
+ *   hb_gp_predict : mean [M] and (if var != NULL) variance [M] at the M query points Xq (d, M); replaces
+ *                   GaussianProcess.predict -> self._function(X=, x0=hyper, p=[X_train; y_train])  (gp.py:623-629, :709) */
+size_t hb_gp_fit_work_doubles(int n);
+int hb_gp_fit(int n, int d, const double* X, const double* y, const double* length_scales, double signal_variance,
+              double noise_variance, double prior_mean, double* L, double* Linv, double* alpha, double* lml,
+              double* work, int* info, void* stream);
+size_t hb_gp_predict_work_doubles(int n, int M);
+int hb_gp_predict(int n, int d, int M, const double* X, const double* Xq, const double* length_scales,
+                  double signal_variance, double noise_variance, double prior_mean, const double* Linv,
+                  const double* alpha, double* mean, double* var, double* work, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

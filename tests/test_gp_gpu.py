@@ -1,0 +1,51 @@
+"""GPU parity for the GP row: golden LML of the reference (tests/test_GPs.py:354-363), SE Gram golden
+(tests/test_kernels.py), predictions vs the NumPy/SciPy oracle at the BASELINE size (n=512, d=6), self-consistency
+properties the reference tests (noise-free variance < noisy variance, tests/test_GPs.py:654-699)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_gp_log_marginal_likelihood_golden(cuda_device):
+    from hilo_mpc_b200.gp import GP
+    gp = GP(['x', 'y'], 'z')
+    X = np.array([[0., .5, 1. / np.sqrt(2.), np.sqrt(3.) / 2., 1., 0.],
+                  [1., np.sqrt(3.) / 2., 1. / np.sqrt(2.), .5, 0., -1.]])
+    y = np.array([[0., np.pi / 6., np.pi / 4., np.pi / 3., np.pi / 2., np.pi]])
+    gp.set_training_data(X, y)
+    gp.setup()
+    np.testing.assert_approx_equal(gp.log_marginal_likelihood(), -9.82229944, significant=9)
+
+
+@pytest.mark.parametrize('n,d', [(512, 6), (100, 3), (37, 1)])
+def test_gp_fit_and_predict_match_oracle(cuda_device, n, d):
+    from hilo_mpc_b200.gp import GP, Kernel
+    from oracle.gp import GpOracle
+    rng = np.random.default_rng(n)
+    X = rng.uniform(-1., 1., size=(d, n))
+    ls = rng.uniform(.5, 1.5, size=d)
+    ytrue = np.sin(X.sum(0)) + .1 * X[0] ** 2
+    y = ytrue + rng.normal(size=n) * 1e-2
+    gp = GP([f'f{k}' for k in range(d)], 'y', kernel=Kernel.squared_exponential(signal_variance=1.3, length_scales=ls,
+                                                                                 ard=True), noise_variance=1e-4)
+    gp.set_training_data(X, y[None])
+    gp.setup()
+    orc = GpOracle(X, y, noise_variance=1e-4, signal_variance=1.3, length_scales=ls)
+    np.testing.assert_allclose(gp.log_marginal_likelihood(), orc.log_marginal_likelihood(), rtol=1e-9)
+    L = gp._fit['L'].cpu().numpy()
+    np.testing.assert_allclose(L, orc.L, rtol=1e-8, atol=1e-11)
+    np.testing.assert_allclose(gp._fit['alpha_host'], orc.alpha, rtol=1e-5, atol=1e-6)
+    Xq = rng.uniform(-1., 1., size=(d, 1000 + 3))
+    mean, var = gp.predict(Xq)
+    mo, vo = orc.predict(Xq)
+    np.testing.assert_allclose(mean[0], mo, rtol=1e-7, atol=1e-8)
+    np.testing.assert_allclose(var[0], vo, rtol=1e-6, atol=1e-9)
+    _, var_nf = gp.predict(Xq, noise_free=True)
+    assert (var_nf < var).all()
+    # symbolic prediction (how a GP enters a Model) evaluates to the same mean
+    from hilo_mpc_b200 import symbolic as sx
+    xs = sx.sym('x', d)
+    ms, _ = gp.predict(xs)
+    F = sx.Function('m', [('x', xs)], [('m', ms)])
+    np.testing.assert_allclose(F(Xq[:, :5])[0], mo[:5], rtol=1e-7, atol=1e-8)
