@@ -6,9 +6,14 @@ from . import symbolic
 from . import symbolic as ca  # CasADi-flavoured helper namespace: ca.cos, ca.sin, ca.exp, ca.sym ...
 from .model import Model
 from .nmpc import NMPC
+from .lmpc import LMPC
+from .mhe import MHE, MovingHorizonEstimator
+from .gp import GP, GaussianProcess, Kernel
+from .ann import ANN, Layer
 from .estimators import EKF, KF, PF, UKF, ExtendedKalmanFilter, KalmanFilter, ParticleFilter, UnscentedKalmanFilter
 
 pi = 3.141592653589793
 
-__all__ = ['Model', 'NMPC', 'KF', 'EKF', 'UKF', 'PF', 'KalmanFilter', 'ExtendedKalmanFilter', 'UnscentedKalmanFilter',
+__all__ = ['Model', 'NMPC', 'LMPC', 'MHE', 'MovingHorizonEstimator', 'GP', 'GaussianProcess', 'Kernel', 'ANN', 'Layer',
+           'KF', 'EKF', 'UKF', 'PF', 'KalmanFilter', 'ExtendedKalmanFilter', 'UnscentedKalmanFilter',
            'ParticleFilter', 'symbolic', 'ca']

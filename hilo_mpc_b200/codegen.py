@@ -53,7 +53,7 @@ def _indent(src: str, n: int = 2) -> str:
     return '\n'.join(pad + ln for ln in src.split('\n'))
 
 
-def cost_derivatives(total, ls_terms, rest, x, u):
+def cost_derivatives(total, ls_terms, rest, x, u, exact=False):
     """Gradient (exact) and Gauss-Newton Hessian blocks of a cost ``total = sum_i r_i^T W_i r_i + rest`` with respect
     to ``(x, u)``.  The least-squares part contributes ``2 J^T W J`` (exact whenever the residuals are affine, which
     is the reference's quadratic cost, modeling.py:283); ``rest`` contributes its exact Hessian."""
@@ -61,6 +61,8 @@ def cost_derivatives(total, ls_terms, rest, x, u):
     n = len(xu)
     g = sx.gradient(total, xu) if n else np.zeros(0, dtype=object)
     H = np.full((n, n), sx.Expr.const(0.), dtype=object)
+    if exact:
+        ls_terms, rest = [], total  # exact Hessian of the whole cost (what IPOPT gets from CasADi AD)
     for r, W in ls_terms:
         r = sx.as_vector(r)
         J = sx.jacobian(r, xu)
@@ -89,7 +91,8 @@ class OcpGenerator:
         for k, v in ints.items():
             L.append(f'  static constexpr int {k} = {int(v)};')
         bools = dict(OBJ_DISCRETE=(s.objective == 'discrete' or s.method == 'discrete'), FIXED_X0=s.fixed_x0,
-                     HAS_GADD=s.gadd is not None, HAS_ARR=s.arr is not None)
+                     HAS_GADD=s.gadd is not None, HAS_ARR=s.arr is not None,
+                     EXACT_HESS=bool(s.exact_hessian) and s.method != 'erk')
         for k, v in bools.items():
             L.append(f'  static constexpr bool {k} = {"true" if v else "false"};')
         if s.method == 'collocation':
@@ -112,8 +115,18 @@ class OcpGenerator:
         L.append(_indent(sx.Function('f_val', ins, [('f', s.ode)]).c_source(QUAL, scalar_inputs=scal)))
         L.append(_indent(sx.Function('f_jac', ins, [('f', s.ode), ('fx', fx), ('fu', fu)])
                          .c_source(QUAL, scalar_inputs=scal)))
+        # Hessian of lam^T f with respect to (x, u): the constraint-curvature part of the Lagrangian Hessian
+        lamf = sx.sym('lamf', s.nx)
+        ex = bool(s.exact_hessian) and s.method != 'erk'
+        if ex:
+            Hf = sx.hessian(sx.dot(lamf, s.ode), np.concatenate([s.x, s.u]))
+        else:
+            Hf = np.full((s.nx + s.nu, s.nx + s.nu), sx.Expr.const(0.), dtype=object)
+        L.append(_indent(sx.Function('f_hess', ins + [('lamf', lamf)],
+                                     [('hxx', Hf[:s.nx, :s.nx]), ('hux', Hf[s.nx:, :s.nx]), ('huu', Hf[s.nx:, s.nx:])])
+                         .c_source(QUAL, scalar_inputs=scal)))
         # ---- Lagrange term
-        lx, lu, lxx, lux, luu = cost_derivatives(s.lag, s.lag_ls, s.lag_rest, s.x, s.u)
+        lx, lu, lxx, lux, luu = cost_derivatives(s.lag, s.lag_ls, s.lag_rest, s.x, s.u, exact=ex)
         L.append(_indent(sx.Function('lag_raw', ins, [('l', [s.lag])]).c_source(QUAL, scalar_inputs=scal)))
         L.append(f'  {QUAL} double lag_val(const double* x, const double* u, const double* sp, double t, double dt) '
                  f'{{ double l; lag_raw(x, u, sp, t, dt, &l); return l; }}')
@@ -132,7 +145,7 @@ class OcpGenerator:
         # ---- Mayer term
         ins_m = [('x', s.x), ('tp', s.tp), ('t', t)]
         may = s.may if s.may is not None else sx.Expr.const(0.)
-        Ex, _, Exx, _, _ = cost_derivatives(may, s.may_ls, s.may_rest, s.x, [])
+        Ex, _, Exx, _, _ = cost_derivatives(may, s.may_ls, s.may_rest, s.x, [], exact=ex)
         L.append(_indent(sx.Function('may_raw', ins_m, [('E', [may])]).c_source(QUAL, scalar_inputs=('t',))))
         L.append(f'  {QUAL} double may_val(const double* x, const double* tp, double t) '
                  f'{{ double E; may_raw(x, tp, t, &E); return E; }}')
@@ -142,7 +155,7 @@ class OcpGenerator:
         ap = s.ap if s.ap is not None else np.zeros(0, dtype=object)
         arr = s.arr if s.arr is not None else sx.Expr.const(0.)
         ins_a = [('x', s.x), ('ap', ap)]
-        ax, _, axx, _, _ = cost_derivatives(arr, s.arr_ls, None if s.arr_ls else arr, s.x, [])
+        ax, _, axx, _, _ = cost_derivatives(arr, s.arr_ls, None if s.arr_ls else arr, s.x, [], exact=ex)
         L.append(_indent(sx.Function('arr_raw', ins_a, [('v', [arr])]).c_source(QUAL)))
         L.append(f'  {QUAL} double arr_val(const double* x, const double* ap) '
                  f'{{ double v; arr_raw(x, ap, &v); return v; }}')

@@ -37,3 +37,88 @@ def cstr_initial_states(B: int, seed: int = 0) -> np.ndarray:
     x_ss, _ = cstr_steady_state()
     rng = np.random.default_rng(seed)
     return x_ss + np.array([.2, .2, 5., 5.]) * rng.uniform(-1., 1., size=(B, 4))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+_ANN_CACHE = {}
+
+
+def bicycle_ann(hidden: int = 32, seed: int = 0):
+    """MLP (1 x ``hidden`` tanh, z-scored inputs/outputs) of the kinematic-bicycle right-hand side as a function of
+    ``(v, phi, a, delta)``: random hidden layer + least-squares output layer fitted on samples of the true dynamics
+    (deterministic stand-in for the offline-trained network of BASELINE config 5)."""
+    from .ann import ANN, Layer
+    from .library import bicycle_rhs
+    rng = np.random.default_rng(seed)
+    n = 6000
+    Z = np.column_stack([rng.uniform(-2., 8., n), rng.uniform(-np.pi, np.pi, n), rng.uniform(-1., 1., n),
+                         rng.uniform(-.6, .6, n)])
+    F = np.array([bicycle_rhs([0., 0., z[0], z[1]], [z[2], z[3]], sin=np.sin, cos=np.cos, tan=np.tan, atan=np.arctan)
+                  for z in Z])
+    zm, zs = Z.mean(0), Z.std(0)
+    fm, fs = F.mean(0), F.std(0)
+    fs[fs == 0.] = 1.
+    key = (hidden, seed)
+    if key not in _ANN_CACHE:
+        # random tanh features + least-squares read-out, refined by a few hundred full-batch L-BFGS steps (PyTorch, CPU,
+        # deterministic): training is not part of the hot path, only the resulting weights are
+        import torch
+        torch.manual_seed(seed)
+        Zn = torch.tensor((Z - zm) / zs)
+        Fn = torch.tensor((F - fm) / fs)
+        lin1 = torch.nn.Linear(4, hidden).double()
+        lin2 = torch.nn.Linear(hidden, 4).double()
+        params = list(lin1.parameters()) + list(lin2.parameters())
+        opt = torch.optim.LBFGS(params, lr=1., max_iter=400, history_size=30, line_search_fn='strong_wolfe')
+
+        def closure():
+            opt.zero_grad()
+            loss = ((lin2(torch.tanh(lin1(Zn))) - Fn) ** 2).mean()
+            loss.backward()
+            return loss
+        opt.step(closure)
+        _ANN_CACHE[key] = tuple(t.detach().numpy().copy() for t in (lin1.weight, lin1.bias, lin2.weight, lin2.bias))
+    W1, b1, W2, b2 = _ANN_CACHE[key]
+    net = ANN(['v', 'phi', 'a', 'delta'], ['dpx', 'dpy', 'dv', 'dphi'], name='bicycle_mlp')
+    net.add_layers(Layer.dense(hidden, 'tanh'))
+    net.setup()
+    net.set_weights([W1, W2], [b1, b2], input_scaling=(zm, zs), output_scaling=(fm, fs))
+    return net
+
+
+def robot_nn_nmpc(N: int = 30, dt: float = 1., integration_method: str = 'collocation', setup: bool = True,
+                  hidden: int = 32) -> NMPC:
+    """Config 5: path-following NMPC of a mobile robot whose right-hand side is an MLP
+    (docs/docsource/examples/mpc_formula1.ipynb: path ``(30 - 14 cos(theta), 30 - 16 sin(theta))``, ``u_pf in [0.1, 1]``)."""
+    from . import symbolic as sx
+    from .model import Model
+    net = bicycle_ann(hidden)
+    model = Model(name=f'robot_mlp{hidden}')
+    x = model.set_dynamical_states(['px', 'py', 'v', 'phi'])
+    u = model.set_inputs(['a', 'delta'])
+    model.set_dynamical_equations(net.predict(np.array([x[2], x[3], u[0], u[1]], dtype=object)))
+    model.setup(dt=dt)
+    nmpc = NMPC(model)
+    nmpc.horizon = N
+    theta = nmpc.create_path_variable(name='theta', u_pf_lb=.1, u_pf_ub=1., u_pf_ref=.5, u_pf_weight=10.,
+                                      theta_guess=0., theta_lb=0., theta_ub=100.)
+    nmpc.quad_stage_cost.add_states(names=['px', 'py'], weights=[1., 1.],
+                                    ref=np.array([30. - 14. * sx.cos(theta), 30. - 16. * sx.sin(theta)], dtype=object),
+                                    path_following=True)
+    nmpc.quad_stage_cost.add_inputs(names=['a', 'delta'], weights=[.1, .1])
+    nmpc.quad_terminal_cost.add_states(names=['px', 'py'], weights=[1., 1.],
+                                       ref=np.array([30. - 14. * sx.cos(theta), 30. - 16. * sx.sin(theta)], dtype=object),
+                                       path_following=True)
+    nmpc.set_box_constraints(x_ub=[100., 100., 10., 100.], x_lb=[-100., -100., -10., -100.], u_ub=[1., 1.],
+                             u_lb=[-1., -1.])
+    nmpc.set_initial_guess(x_guess=[15., 30., 0., 0.], u_guess=[0., 0.])
+    nmpc.set_nlp_options(integration_method=integration_method)
+    if setup:
+        nmpc.setup()
+    return nmpc
+
+
+def robot_initial_states(B: int, seed: int = 3) -> np.ndarray:
+    """``x0 = [15, 30, 0, 0] + diag([2, 2, .5, .2]) U(-1, 1)`` (cfg 5)."""
+    rng = np.random.default_rng(seed)
+    return np.array([15., 30., 0., 0.]) + np.array([2., 2., .5, .2]) * rng.uniform(-1., 1., size=(B, 4))

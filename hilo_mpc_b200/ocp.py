@@ -64,6 +64,9 @@ class OcpSpec:
     arr: Optional[sx.Expr] = None
     arr_ls: List[Tuple[np.ndarray, np.ndarray]] = field(default_factory=list)
     ap: Optional[np.ndarray] = None
+    # exact Hessian of the Lagrangian (constraint curvature through the collocation multipliers) like IPOPT; False =
+    # Gauss-Newton (always used for the explicit RK transcription)
+    exact_hessian: bool = True
     name: str = 'ocp'
 
     @property

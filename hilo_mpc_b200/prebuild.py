@@ -1,6 +1,8 @@
 """Builds, for sm_100a, every generated module the tests / smoke / bench use, so the binaries travel with the tree."""
 from __future__ import annotations
 
+import numpy as np
+
 
 def build_all():
     from .estgen import build_est_module
@@ -24,4 +26,37 @@ def build_all():
     s.setup(dt=1.)
     paths.append(build_est_module(s))
     paths.append(build_est_module(cstr_model(dt=0.005)))
+    # LMPC double integrator (BASELINE config 1 / tests/test_LMPC.py:8-33) and its plant model
+    from .lmpc import LMPC
+    di = Model(discrete=True)
+    di.A = np.array([[1, di.dt], [0, 1]])
+    di.B = np.array([[di.dt ** 2 / 2], [di.dt]])
+    di.setup(dt=.5)
+    paths.append(build_est_module(di))
+    mpc = LMPC(di)
+    mpc.Q, mpc.R, mpc.horizon = np.eye(2), 1, 10
+    mpc.set_box_constraints(x_lb=[-5, -5], x_ub=[5, 5], u_lb=[-1], u_ub=[1])
+    mpc.setup()
+    paths.append(mpc.engine.module_path)
+    # MHE test problem and BASELINE config 5 (MLP dynamics + path following)
+    from .mhe import MHE
+    rm = Model(name='reaction')
+    x = rm.set_dynamical_states(['ca', 'cb'])
+    u = rm.set_inputs(['f'])
+    p = rm.set_parameters(['k'])
+    rm.set_measurements(['y'])
+    rm.set_measurement_equations([x[1]])
+    rm.set_dynamical_equations([u[0] * (1. - x[0]) - p[0] * x[0], p[0] * x[0] - u[0] * x[1]])
+    rm.setup(dt=.25)
+    mhe = MHE(rm)
+    mhe.horizon = 6
+    mhe.quad_arrival_cost.add_states(weights=[10., 10.], guess=[.5, .2])
+    mhe.quad_arrival_cost.add_parameters(weights=[1.], guess=[1.])
+    mhe.quad_stage_cost.add_measurements(weights=[100.])
+    mhe.quad_stage_cost.add_state_noise(weights=[20., 20.])
+    mhe.set_box_constraints(x_lb=[0., 0.], x_ub=[1., 1.], p_lb=[.1], p_ub=[5.])
+    mhe.setup()
+    paths.append(mhe.engine.module_path)
+    from .examples import robot_nn_nmpc
+    paths.append(robot_nn_nmpc(N=30).engine.module_path)
     return paths

@@ -57,7 +57,8 @@ class FlatNlp:
         uk = sx.sym('uk', nu)
         xn = sx.sym('xn', nx)
         t, dt = sx.sym('t'), sx.sym('dt')
-        sp_, tp_, uo = sx.sym('sp', s.nsp), sx.sym('tp', s.ntp), sx.sym('uo', s.nuold)
+        sp_, tp_ = sx.sym('sp', s.nsp), sx.sym('tp', s.ntp)
+        uo = sx.sym('uo', s.nuold + s.nap)  # stage-0 parameters: previous inputs, then arrival-cost parameters
 
         def f_at(tt, xx, uu):
             return sx.substitute(s.ode, np.concatenate([[s.t], s.x, s.u, s.sp, [s.dt]]),
@@ -69,7 +70,7 @@ class FlatNlp:
             if with_du and s.nuold > 0:
                 # the input-change cost is part of the Lagrange term (modeling.py:243-249); for stages >= 1 the
                 # reference passes u_old := u_k itself, so the term vanishes identically there
-                e = e + sx.substitute(s.lag_du, np.concatenate([s.u, s.uold]), np.concatenate([uu, uo]))
+                e = e + sx.substitute(s.lag_du, np.concatenate([s.u, s.uold]), np.concatenate([uu, uo[:s.nuold]]))
             return e
 
         zero = sx.Expr.const(0.)
@@ -124,6 +125,8 @@ class FlatNlp:
                 J = J + lag_at(t, xk, uk)  # mpc.py:1676-1679
             else:
                 J = J + quad
+        if with_du and s.arr is not None:  # arrival cost on the first node (mhe.py:738-740)
+            J = J + sx.substitute(s.arr, np.concatenate([s.x, s.ap]), np.concatenate([xk, uo[s.nuold:]]))
         if with_may:
             J = J + sx.substitute(s.may, np.concatenate([[s.t], s.x, s.tp]), np.concatenate([[t + dt], xf, tp_]))
         return dict(w=w, g=g, J=J, t=t, dt=dt, sp=sp_, tp=tp_, uo=uo)
@@ -241,7 +244,7 @@ class FlatNlp:
             lb[self.x_ind[0]] = ub[self.x_ind[0]] = x0  # mpc.py:801-802
         return lb, ub, v0
 
-    def solve(self, x0, v0=None, time=0., dts=None, sps=None, tp=None, uold=None, dt=None, **ipm_opts):
+    def solve(self, x0, v0=None, time=0., dts=None, sps=None, tp=None, uold=None, dt=None, ap=None, **ipm_opts):
         """One ``NMPC.optimize`` call (mpc.py:744-857) in scaled coordinates. Returns (IpmResult, x_pred, u_pred)."""
         s = self.spec
         if dts is None:
@@ -252,6 +255,8 @@ class FlatNlp:
             tp = np.zeros(s.ntp)
         if uold is None:
             uold = np.zeros(s.nuold)
+        if s.nap:
+            uold = np.concatenate([np.asarray(uold, dtype=float).reshape(-1), np.asarray(ap, dtype=float).reshape(-1)])
         lb, ub, vg = self.bounds_and_guess(x0)
         if v0 is None:
             v0 = vg

@@ -1,0 +1,106 @@
+"""GPU parity through the public API for LMPC (a3), MHE (a4) and the config-5 problem (MLP dynamics + path following)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from test_hostsim_lmpc_mhe import _dense_qp_reference, double_integrator, reaction_model
+
+
+def test_lmpc_closed_loop_like_reference_test(cuda_device):
+    """tests/test_LMPC.py:21-44: 200 closed-loop steps of the double integrator; every first move is checked against an
+    independent dense-QP solve for the first steps, the loop must reach the origin."""
+    from hilo_mpc_b200 import LMPC
+    model = double_integrator()
+    model.set_initial_conditions(x0=[1, 1])
+    mpc = LMPC(model)
+    mpc.Q = np.eye(2)
+    mpc.R = 1
+    mpc.horizon = 10
+    mpc.set_box_constraints(x_lb=[-5, -5], x_ub=[5, 5], u_lb=[-1], u_ub=[1])
+    mpc.setup(solver_options={'ipopt.tol': 1e-10})
+    x0 = np.array([1., 1.])
+    for i in range(60):
+        u = mpc.optimize(x0=x0)
+        assert u.shape == (1, 1) and mpc.solver_status_code == 1
+        if i < 5:
+            np.testing.assert_allclose(u[0, 0], _dense_qp_reference(x0, 10)[0], atol=2e-6)
+        model.simulate(u=u)
+        x0 = model.solution['x:f'].reshape(-1)
+    assert np.abs(x0).max() < 1e-3
+    x_pred, u_pred = mpc.return_prediction()
+    assert x_pred.shape == (2, 11) and u_pred.shape == (1, 10)
+    with pytest.raises(NotImplementedError):
+        mpc.set_stage_constraints()
+
+
+def test_lmpc_rejects_nonlinear_or_continuous_models():
+    from hilo_mpc_b200 import LMPC
+    from hilo_mpc_b200.library import cstr_model
+    with pytest.raises(TypeError):
+        LMPC(cstr_model())
+
+
+def test_mhe_batched_matches_oracle(cuda_device):
+    import torch
+    from hilo_mpc_b200 import MHE
+    from oracle.estimators import rk4
+    from oracle.nmpc import FlatNlp
+    N, B = 6, 64
+    mhe = MHE(reaction_model())
+    mhe.horizon = N
+    mhe.quad_arrival_cost.add_states(weights=[10., 10.], guess=[.5, .2])
+    mhe.quad_arrival_cost.add_parameters(weights=[1.], guess=[1.])
+    mhe.quad_stage_cost.add_measurements(weights=[100.])
+    mhe.quad_stage_cost.add_state_noise(weights=[20., 20.])
+    mhe.set_box_constraints(x_lb=[0., 0.], x_ub=[1., 1.], p_lb=[.1], p_ub=[5.])
+    mhe.setup(nlp_opts={'ipopt.tol': 1e-10})
+    rng = np.random.default_rng(0)
+    f = lambda x, u, p: np.array([u[0] * (1 - x[0]) - p[0] * x[0], p[0] * x[0] - u[0] * x[1]])
+    k_true = rng.uniform(1.2, 2.2, size=B)
+    xt = np.tile([.6, .25], (B, 1))
+    ys = []
+    est = (None, None)
+    for k in range(N):
+        y = xt[:, 1:2] + rng.normal(size=(B, 1)) * 5e-3
+        ys.append(y)
+        mhe.add_measurements(y, u_meas=[.4])
+        est = mhe.estimate()
+        if k < N - 1:
+            assert est == (None, None)  # horizon not reached yet (mhe.py:300-302)
+        xt = np.stack([rk4(f, xt[b], [.4], [k_true[b]], .25, 20) for b in range(B)])
+    x_est, p_est = est
+    assert x_est.shape == (B, 2) and p_est.shape == (B, 1)
+    assert (mhe.solver_status_code == 1).all()
+    spec = mhe.spec
+    nlp = FlatNlp(spec, exact_hessian=True)
+    Y = np.stack(ys, axis=1)
+    for b in (0, 31, 63):
+        sp = np.concatenate([np.full((N, 1), .4), Y[b]], axis=1)
+        res, xo, uo = nlp.solve(None, dt=.25, sps=sp, ap=np.array([.5, .2, 1.]), finish_barrier=True, tol=1e-10)
+        assert res.status == 1
+        np.testing.assert_allclose(x_est[b].cpu().numpy(), xo[:2, -1], atol=2e-7)
+        np.testing.assert_allclose(p_est[b].cpu().numpy(), xo[2:, -1], atol=2e-7)
+    # the estimates moved from the arrival guess (k = 1) towards the true rate constants
+    err0 = np.abs(1. - k_true).mean()
+    err = np.abs(p_est.cpu().numpy()[:, 0] - k_true).mean()
+    assert err < err0
+
+
+def test_robot_nn_path_following_batch(cuda_device):
+    """Config 5 (N=30, MLP 1x32 tanh, path variable): all instances reach a KKT point; the path parameter advances
+    monotonically (u_theta >= 0.1) and the robot tracks the path in closed loop."""
+    import torch
+    from hilo_mpc_b200.examples import robot_initial_states, robot_nn_nmpc
+    nmpc = robot_nn_nmpc(N=30)
+    x0 = torch.tensor(robot_initial_states(256), device=cuda_device)
+    u = nmpc.optimize(x0)
+    assert u.shape == (256, 2)
+    st = nmpc.solver_status_code
+    assert (st == 1).float().mean().item() > .98
+    out = nmpc._last
+    theta = out['x'][:, :, 4]
+    assert (theta[:, 1:] - theta[:, :-1] >= .1 - 1e-6).all()
+    stats = out['stats'].cpu().numpy()
+    ok = st.cpu().numpy() == 1
+    assert stats[ok, 10].max() < 1e-8 and stats[ok, 9].max() < 1e-8
