@@ -188,6 +188,10 @@ def main():
     ap.add_argument('--batch', type=int, default=BATCH_PER_GPU, help='instances per GPU')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-sample', type=int, default=16)
+    ap.add_argument('--hessian', default='exact', choices=['exact', 'gauss-newton'])
+    ap.add_argument('--warm-start', type=int, default=1, help='1: reuse multipliers + small initial barrier parameter '
+                                                              'between closed-loop steps; 0: IPOPT-default restart')
+    ap.add_argument('--warm-mu', type=float, default=1e-4)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     if args.impl == 'reference':
@@ -210,7 +214,8 @@ def main():
         dist.init_process_group('nccl', device_id=dev)
 
     B = args.batch
-    nmpc = cstr_nmpc(N=N_HORIZON)
+    nmpc = cstr_nmpc(N=N_HORIZON, solver_options={'b200.hessian': args.hessian, 'b200.warm_start': args.warm_start,
+                                                  'b200.warm_start_mu': args.warm_mu})
     eng = nmpc.engine
     xs = torch.tensor(nmpc._xs_full, dtype=torch.float64, device=dev)
     us = torch.tensor(nmpc._us_full, dtype=torch.float64, device=dev)
@@ -337,6 +342,7 @@ def main():
                                f'warm-started closed loop with seeded disturbances, tol=1e-8',
                    'batch_per_gpu': B, 'horizon': N_HORIZON, 'parallelism': f'batch-shard x{world}',
                    'l2': f'working set {work_mb:.0f} MB per step > 126 MB L2 (no explicit flush)',
+                   'hessian': args.hessian, 'warm_start': bool(args.warm_start), 'warm_start_mu': args.warm_mu,
                    'ipm_iterations_mean': iters_mean, 'ipm_iterations_max_per_step': iters_hist,
                    'status_optimal_frac': status_ok},
         'e2e': {'value': e2e_value, 'unit': 'steps/s', 'h2d_bytes_per_step': B * NX * 8,

@@ -174,6 +174,19 @@ HB_HD double push_interior(double v, double lb, double ub) {
   return v;
 }
 
+// Warm start: keep the point where it is unless it sits (numerically) on a bound; multipliers are kept but bounded
+// away from zero / infinity relative to the starting barrier parameter.
+HB_HD double push_interior_warm(double v, double lb, double ub) {
+  const double k = 1e-9;
+  if (has_lb(lb)) v = dmax(v, lb + k * dmax(1.0, dabs(lb)));
+  if (has_ub(ub)) v = dmin(v, ub - k * dmax(1.0, dabs(ub)));
+  return v;
+}
+HB_HD double warm_z(double z, double mu) {
+  if (!(z == z) || z <= 0.0) return 1.0;
+  return dmin(dmax(z, 1e-3 * mu), 1e12);
+}
+
 // Largest alpha in (0, 1] with  s + alpha*ds >= (1 - tau) * s  for a positive quantity s.
 HB_HD double frac_to_boundary(double s, double ds, double tau, double amax) {
   if (ds < 0.0) { const double a = -tau * s / ds; if (a < amax) amax = a; }

@@ -104,7 +104,8 @@ struct OcpModule {
     memset(&a, 0, sizeof(a));
     a.B = c->B; a.n_alpha = c->n_alpha; a.max_iter = c->max_iter;
     a.tol = c->tol; a.acc_tol = c->acc_tol; a.mu_init = c->mu_init; a.mu_min = c->mu_min;
-    a.time0 = c->time0; a.dt = c->dt;
+    a.time0 = c->time0; a.dt = c->dt; a.warm = c->warm_start;
+    if (a.warm) a.mu_init = c->mu_init_warm;
     a.x0 = c->x0; a.sp = c->sp; a.sp_stride = c->sp_stride; a.tp = c->tp; a.tp_stride = c->tp_stride;
     a.uold = c->uold; a.uold_stride = c->uold_stride; a.ap = c->ap; a.ap_stride = c->ap_stride;
     a.xlb = c->xlb; a.xub = c->xub; a.ulb = c->ulb; a.uub = c->uub;

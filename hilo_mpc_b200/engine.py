@@ -84,6 +84,7 @@ class OcpEngine:
     def reset_guess(self, v0: Optional[dict] = None):
         """Forget the warm start (next solve starts from the tiled guess, mpc.py:1465-1506) or install ``v0``."""
         self._batch = 0 if v0 is None else self._batch
+        self._solved_once = False
         if v0 is not None:
             for k in ('x', 'u', 'xc'):
                 if k in v0 and v0[k] is not None:
@@ -93,7 +94,7 @@ class OcpEngine:
     def solve(self, x0, dt: float, time0: float = 0., sp=None, tp=None, uold=None, ap=None, tol: float = 1e-8,
               acc_tol: float = 1e-6, max_iter: int = 3000, n_alpha: int = 8, mu_init: float = .1,
               mu_min: Optional[float] = None, check_every: int = 4, stream=None, kernel_ms=None, kernel_count=None,
-              riccati_variant: int = 1):
+              riccati_variant: int = 1, warm_start: int = 0, mu_init_warm: float = 1e-4):
         """``x0``: CUDA tensor ``[B, nx]`` (scaled). Optional ``sp [B|1, N, nsp]``, ``tp``, ``uold``, ``ap`` tensors.
         Returns dict of device tensors: x [B,N+1,nx], u [B,N,nu], xc, lam, status, iters, stats."""
         torch = _lib.require_cuda()
@@ -133,9 +134,12 @@ class OcpEngine:
             n_iterations_launched=C.pointer(launched), n_kernel_launches=C.pointer(n_launch),
             kernel_ms=None if kernel_ms is None else kernel_ms.ctypes.data_as(_lib._DP),
             kernel_count=None if kernel_count is None else kernel_count.ctypes.data_as(C.POINTER(C.c_longlong)),
-            riccati_variant=riccati_variant)
+            riccati_variant=riccati_variant,
+            warm_start=int(bool(warm_start) and getattr(self, '_solved_once', False) and self._solved_batch == B),
+            mu_init_warm=mu_init_warm)
         _lib.check(lib.hb_ocp_solve(self._handle, C.byref(call)), 'hb_ocp_solve')
         self.last_launched = launched.value
+        self._solved_once, self._solved_batch = True, B
         self.last_kernel_launches = n_launch.value
         self.total_kernel_launches = getattr(self, 'total_kernel_launches', 0) + n_launch.value
         self._keep = (x0, spv, tpv, uov, apv)  # keep inputs alive until the stream has consumed them

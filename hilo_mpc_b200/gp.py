@@ -109,6 +109,14 @@ class GaussianProcess:
         self._X, self._y = X, y
         self._is_setup = False
 
+    def set_training_shards(self, X_shard, y_shard) -> None:
+        """Training data distributed over the ranks of the process group by observations: all-gather the shards (NCCL
+        over NVLink on GPUs; the one collective of the whole path) and keep the full set on every rank,
+        so that the fit and the predictions stay replicated and local."""
+        from .distributed import all_gather_training_shards
+        X, y = all_gather_training_shards(X_shard, y_shard)
+        self.set_training_data(X.cpu().numpy(), y.cpu().numpy())
+
     def is_setup(self) -> bool:
         return self._is_setup
 

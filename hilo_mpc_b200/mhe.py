@@ -200,7 +200,8 @@ class MovingHorizonEstimator(DynamicOptimization):
             x_lb=np.concatenate([self._x_lb / xs_sc, self._p_lb / ps_sc]),
             x_ub=np.concatenate([self._x_ub / xs_sc, self._p_ub / ps_sc]), u_lb=w_lb, u_ub=w_ub,
             x_guess=np.concatenate([self._x_guess / xs_sc, self._p_guess / ps_sc]), u_guess=w_guess, gadd=gadd,
-            fixed_x0=False, lag_from=1, arr=arrival, arr_ls=arr_ls, ap=ap, name=f'mhe_{m.name}_{method}_N{N}')
+            fixed_x0=False, lag_from=1, arr=arrival, arr_ls=arr_ls, ap=ap, exact_hessian=self._exact_hessian(),
+            name=f'mhe_{m.name}_{method}_N{N}')
         from .engine import OcpEngine
         self._engine = OcpEngine(self._spec, build=getattr(self, '_build_module', True))
         self._solution = TimeSeries(t=['t'], x=m.dynamical_state_names, p=m.parameter_names)

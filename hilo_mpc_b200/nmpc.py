@@ -194,10 +194,22 @@ class DynamicOptimization:
                     mu_init=float(o.get('ipopt.mu_init', .1)),
                     n_alpha=int(o.get('b200.line_search_candidates', 8)),
                     check_every=int(o.get('b200.check_every', 4)),
-                    riccati_variant=int(o.get('b200.riccati_variant', 1)))
+                    riccati_variant=int(o.get('b200.riccati_variant', 1)),
+                    warm_start=int(o.get('b200.warm_start', 0)),
+                    mu_init_warm=float(o.get('b200.warm_start_mu', 1e-4)))
 
     def is_setup(self) -> bool:
         return self._nlp_setup_done
+
+    @property
+    def solver_status_code(self):
+        return self._solver_status_code
+
+    def _exact_hessian(self) -> bool:
+        h = str(self._nlp_opts.get('b200.hessian', 'exact')).lower()
+        if h not in ('exact', 'gauss-newton'):
+            raise ValueError("b200.hessian must be 'exact' or 'gauss-newton'")
+        return h == 'exact'
 
     @property
     def solution(self):
@@ -414,7 +426,7 @@ class NMPC(DynamicOptimization):
             objective=opts['objective_function'], x_lb=np.asarray(x_lb, dtype=float) / x_scale,
             x_ub=np.asarray(x_ub, dtype=float) / x_scale, u_lb=np.asarray(u_lb, dtype=float) / u_scale,
             u_ub=np.asarray(u_ub, dtype=float) / u_scale, x_guess=np.asarray(x_guess, dtype=float) / x_scale,
-            u_guess=np.asarray(u_guess, dtype=float) / u_scale, name=name)
+            u_guess=np.asarray(u_guess, dtype=float) / u_scale, exact_hessian=self._exact_hessian(), name=name)
         self._xs_full, self._us_full = x_scale, u_scale
         self._nx0, self._nu0 = nx0, nu0
         from .engine import OcpEngine

@@ -58,5 +58,5 @@ def build_all():
     mhe.setup()
     paths.append(mhe.engine.module_path)
     from .examples import robot_nn_nmpc
-    paths.append(robot_nn_nmpc(N=30).engine.module_path)
+    paths.append(robot_nn_nmpc(N=5, hidden=8).engine.module_path)
     return paths

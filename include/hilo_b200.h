@@ -81,6 +81,10 @@ typedef struct hb_ocp_call {
   double* kernel_ms;        /* host in/out [HB_OCP_KERNELS] or NULL: accumulates device ms per kernel (CUDA events) */
   long long* kernel_count;  /* host in/out [HB_OCP_KERNELS] or NULL: accumulates launches per kernel              */
   int riccati_variant;      /* 1: TMA-staged multi-lane Riccati sweep (default), 0: one-thread-per-instance sweep  */
+  int warm_start;           /* 0: IPOPT-default start (push 1e-2 into the bounds, z = 1, mu = mu_init);
+                               1: x/u/xc AND the bound multipliers kept in `work` by the previous call are reused,
+                                  tiny push, mu = mu_init_warm (needs the same `work` buffer and batch as before)    */
+  double mu_init_warm;
 } hb_ocp_call;
 
 /* kernel indices of kernel_ms / kernel_count */

@@ -106,3 +106,29 @@ def test_tma_riccati_matches_thread_per_instance_sweep(cuda_device):
     assert (res[0]['x'] - res[1]['x']).abs().max().item() < 1e-9
     assert (res[0]['u'] - res[1]['u']).abs().max().item() < 1e-8
     assert (res[0]['lam'] - res[1]['lam']).abs().max().item() < 1e-8
+
+
+def test_warm_start_mode_reaches_the_same_solution_in_fewer_iterations(cuda_device):
+    """Closed loop with disturbances: the warm-start mode (multipliers kept, small initial barrier parameter) must return
+    the same inputs as the IPOPT-default restart (mu = 0.1, z = 1) and need fewer interior-point iterations."""
+    import torch
+    from hilo_mpc_b200.examples import cstr_initial_states, cstr_nmpc
+    x0 = torch.tensor(cstr_initial_states(512, seed=4), device=cuda_device)
+    gen = torch.Generator(device=cuda_device)
+    gen.manual_seed(0)
+    noise = (torch.rand(4, 512, 4, generator=gen, device=cuda_device, dtype=torch.float64) * 2 - 1) * \
+        torch.tensor([.02, .02, .5, .5], dtype=torch.float64, device=cuda_device)
+    runs = {}
+    for warm in (0, 1):
+        nmpc = cstr_nmpc(N=50, solver_options={'b200.warm_start': warm, 'ipopt.tol': 1e-9})
+        x, us, its = x0.clone(), [], []
+        for k in range(4):
+            us.append(nmpc.optimize(x).clone())
+            assert (nmpc.solver_status_code == 1).all()
+            its.append(nmpc._last['iters'].double().mean().item())
+            xp, _, _ = nmpc.return_prediction()
+            x = xp[:, 1, :4] + noise[k]
+        runs[warm] = (us, its)
+    for ua, ub in zip(runs[0][0], runs[1][0]):
+        assert (ua - ub).abs().max().item() < 1e-4 * ua.abs().max().item()
+    assert np.mean(runs[1][1][1:]) < np.mean(runs[0][1][1:])
