@@ -186,10 +186,10 @@ class OcpGenerator:
 
 
 def _dep_hash() -> str:
+    import glob
     h = hashlib.sha256()
-    for fn in ('hb_common.cuh', 'ocp_kernels.cuh', 'ocp_module.cuh', 'riccati.cuh', 'est_kernels.cuh',
-               'est_module.cuh', os.path.join('..', '..', 'include', 'hilo_b200.h')):
-        p = os.path.join(CSRC, fn)
+    deps = sorted(glob.glob(os.path.join(CSRC, '*.cuh'))) + [os.path.join(CSRC, '..', '..', 'include', 'hilo_b200.h')]
+    for p in deps:
         if os.path.exists(p):
             with open(p, 'rb') as f:
                 h.update(f.read())

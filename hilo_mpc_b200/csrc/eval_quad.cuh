@@ -1,0 +1,448 @@
+// Node evaluation, sm_100a version for the collocation transcription: 4 lanes per (instance, interval).
+//
+// The one-thread-per-node kernel (OcpEval) keeps the deg*nx x (deg*nx + nx + nu + 1) elimination matrix in local
+// memory (3 KB per thread, 253 registers) and is bound by local-memory latency.  Here the matrix is row-distributed over
+// the four lanes of a quad and lives in registers (row r belongs to lane r % 4); Gauss-Jordan elimination with
+// (implicit) partial pivoting broadcasts the normalised pivot row through shared memory; everything else that several
+// lanes need (model derivatives at the collocation points, the solved T block) is exchanged through a small per-quad
+// shared-memory scratch pad.  Work split:
+//   lanes 0..deg-1 : model + cost derivatives at "their" collocation point (generated device functions)
+//   lane  3        : barrier terms of x_k and u_k
+//   all lanes      : their rows of the (transposed and plain) collocation systems, rows of A/B/b, a share of the
+//                    reduced Hessian entries, a share of the output copy.
+// Supported: collocation, NMPC-type problems (x_0 pinned, continuous objective, no additive input, no arrival cost)
+// with deg <= 4 and rows_per_lane * columns <= 64 doubles; everything else uses OcpEval.  Terminal nodes are evaluated
+// by OcpEvalTerminal (one thread per instance).
+#pragma once
+#include "ocp_kernels.cuh"
+
+namespace hb {
+
+// terminal node only (the k == N branch of OcpEval), launched over instances
+template <class P>
+struct OcpEvalTerminal {
+  static HB_HD void run(const OcpArgs& a, int b) { OcpEval<P>::run(a, b, OcpT<P>::N); }
+};
+
+#if HB_DEVICE_BUILD
+
+template <class P>
+struct EvalQuad {
+  using T = OcpT<P>;
+  static constexpr int NX = T::NX, NU = T::NU, NC = T::NC, NE = T::NE, N = T::N, D = P::DEG;
+  static constexpr int RPL = (NC + 3) / 4;   // rows per lane
+  static constexpr int W = NC + NE + 1;      // columns of the plain system  [G_X | G_x G_u | c]
+  static constexpr int WT = NC + 1;          // columns of the transposed system
+  static constexpr bool SUPPORTED = (P::METHOD == METHOD_COLLOCATION) && P::FIXED_X0 && !P::HAS_GADD && !P::HAS_ARR &&
+                                    !P::OBJ_DISCRETE && (D <= 3) && (RPL * W <= 64) && (NC >= 4);
+  // per-quad scratch (doubles)
+  static constexpr int FSZ = NX + NX * NX + NX * NU;                             // f | fx | fu of one point
+  static constexpr int LSZ = 1 + NX + NU + NX * NX + NU * NX + NU * NU;          // l | lx | lu | lxx | lux | luu (weighted)
+  static constexpr int oF = 0, oL = oF + D * FSZ, oPB = oL + D * LSZ, oT = oPB + 2 * W, oNU = oT + NC * (NE + 1),
+                       oGX = oNU + NC, oDGX = oGX + NC, oSGX = oDGX + NC, oXU = oSGX + NC,  // gx dgx sigx gu dgu sigu
+                       oEND = oXU + 3 * NX + 3 * NU,
+                       oHT = oF;  // H*T rows reuse the model-derivative area (dead once the plain system is assembled)
+  static_assert(D * NX * (NE + 1) <= D * FSZ, "HT alias does not fit");
+  static constexpr int SCR = ((oEND + 1) & ~1) + 3;  // odd multiple keeps neighbouring quads on different banks
+  static constexpr int QUADS = 32;                   // quads (nodes) per CTA, 128 threads
+  static constexpr int SMEM_BYTES = QUADS * SCR * 8;
+
+  static __device__ __forceinline__ double qshfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m, 4); }
+  static __device__ __forceinline__ int qshfl_xor(int v, int m) { return __shfl_xor_sync(0xffffffffu, v, m, 4); }
+
+  // Gauss-Jordan on rows R[RPL][NCOLS] (row lr of lane q is global row lr*4 + q), pivot columns 0..NPIV-1.
+  // On return row lr of lane q holds, in columns >= NPIV, the solution of variable pivvar[lr].
+  template <int NCOLS, int NPIV>
+  static __device__ __forceinline__ bool gauss_jordan(double (&R)[RPL][NCOLS], int (&pivvar)[RPL], int q, double* pb) {
+    bool ok = true;
+#pragma unroll
+    for (int lr = 0; lr < RPL; ++lr) pivvar[lr] = (lr * 4 + q < NPIV) ? -1 : -2;  // -2: row does not exist
+#pragma unroll
+    for (int c = 0; c < NPIV; ++c) {
+      double best = -1.0;
+      int code = 0;
+#pragma unroll
+      for (int lr = 0; lr < RPL; ++lr) {
+        const double v = (pivvar[lr] == -1) ? fabs(R[lr][c]) : -1.0;
+        if (v > best) { best = v; code = q * RPL + lr; }
+      }
+#pragma unroll
+      for (int m = 1; m < 4; m <<= 1) {
+        const double ob = qshfl_xor(best, m);
+        const int oc = qshfl_xor(code, m);
+        if (ob > best || (ob == best && oc < code)) { best = ob; code = oc; }
+      }
+      ok = ok && (best > 0.0);
+      const int po = code / RPL, plr = code % RPL;
+      double* prow = pb + (c & 1) * NCOLS;  // double-buffered broadcast row
+      if (q == po) {
+#pragma unroll
+        for (int lr = 0; lr < RPL; ++lr)
+          if (lr == plr) {
+            const double inv = 1.0 / R[lr][c];
+#pragma unroll
+            for (int j = c + 1; j < NCOLS; ++j) { R[lr][j] *= inv; prow[j] = R[lr][j]; }
+            pivvar[lr] = c;
+          }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int lr = 0; lr < RPL; ++lr) {
+        const bool is_piv = (q == po) && (lr == plr);
+        const double f = is_piv ? 0.0 : R[lr][c];
+#pragma unroll
+        for (int j = c + 1; j < NCOLS; ++j) R[lr][j] -= f * prow[j];
+      }
+    }
+    __syncwarp();
+    return ok;
+  }
+
+  static __device__ void run(const OcpArgs& a) {
+    extern __shared__ __align__(16) double smem[];
+    const int quad = threadIdx.x >> 2, q = threadIdx.x & 3;
+    const long long node = (long long)blockIdx.x * QUADS + quad;
+    const long long total = (long long)a.B * N;
+    const bool valid = node < total;
+    const long long nn = valid ? node : (total - 1);
+    const int b = (int)(nn / N), k = (int)(nn % N);
+    const double* st = a.st + (long long)b * ST_COUNT;
+    const bool active = valid && st[ST_ACTIVE] != 0.0;
+    // a whole warp (8 nodes) leaves together; partially active warps compute everything and mask the stores
+    if (!__any_sync(0xffffffffu, active)) return;
+    double* S = smem + (size_t)quad * SCR;
+    const double mu = st[ST_MU];
+    const long long nb = (long long)b * (N + 1) + k, sb = (long long)b * N + k;
+    const double t = a.time0 + k * a.dt, dt = a.dt;
+    const double* sp = a.sp + (long long)b * a.sp_stride + (long long)k * T::NSP;
+    const double* uo = a.uold + (long long)b * a.uold_stride;
+    const bool with_lag = k >= P::LAG_FROM;
+    const bool first = (k == 0) && (T::NUOLD > 0);
+    const bool x_free = (k > 0);
+
+    // run-time indexed accesses go to global memory (L1-resident); register arrays are only indexed statically
+    const double* xg = a.x + nb * NX;
+    const double* xng = a.x + (nb + 1) * NX;
+    const double* Xg = a.xc + sb * NC;
+    double x[NX], u[NU], Xq[NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) { x[i] = xg[i]; Xq[i] = Xg[(q < D ? q : 0) * NX + i]; }
+#pragma unroll
+    for (int i = 0; i < NU; ++i) u[i] = a.u[sb * NU + i];
+
+    double phi = 0.0, comp = 0.0, c1 = 0.0, cinf = 0.0;
+    // ---------------------------------------------------------------- 1. derivatives at the collocation points
+    if (q < D) {
+      const int i = q + 1;
+      const double ti = t + dt * P::CTAU(i - 1);
+      double* F = S + oF + q * FSZ;
+      P::f_jac(Xq, u, sp, ti, dt, F, F + NX, F + NX + NX * NX);
+      double* L = S + oL + q * LSZ;
+      double l = 0.0, lx[NX], lu[NU], lxx[NX * NX], lux[NU * NX], luu[NU * NU];
+      if (with_lag) {
+        P::lag_all(Xq, u, sp, ti, dt, &l, lx, lu, lxx, lux, luu);
+        if (first) {
+          double l2, lu2[NU], luu2[NU * NU];
+          P::lagdu_all(u, uo, &l2, lu2, luu2);
+          l += l2;
+#pragma unroll
+          for (int j = 0; j < NU; ++j) lu[j] += lu2[j];
+#pragma unroll
+          for (int j = 0; j < NU * NU; ++j) luu[j] += luu2[j];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < NX; ++j) lx[j] = 0.0;
+#pragma unroll
+        for (int j = 0; j < NU; ++j) lu[j] = 0.0;
+#pragma unroll
+        for (int j = 0; j < NX * NX; ++j) lxx[j] = 0.0;
+#pragma unroll
+        for (int j = 0; j < NU * NX; ++j) lux[j] = 0.0;
+#pragma unroll
+        for (int j = 0; j < NU * NU; ++j) luu[j] = 0.0;
+      }
+      const double w = dt * P::CB(i);
+      phi += w * l;
+      L[0] = w * l;
+#pragma unroll
+      for (int j = 0; j < NX; ++j) L[1 + j] = w * lx[j];
+#pragma unroll
+      for (int j = 0; j < NU; ++j) L[1 + NX + j] = w * lu[j];
+#pragma unroll
+      for (int j = 0; j < NX * NX; ++j) L[1 + NX + NU + j] = w * lxx[j];
+#pragma unroll
+      for (int j = 0; j < NU * NX; ++j) L[1 + NX + NU + NX * NX + j] = w * lux[j];
+#pragma unroll
+      for (int j = 0; j < NU * NU; ++j) L[1 + NX + NU + NX * NX + NU * NX + j] = w * luu[j];
+    }
+    if (q == 3) {  // barrier terms of x_k, u_k  (layout at oXU: gx | dgx | sigx | gu | dgu | sigu)
+      double* XU = S + oXU;
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        double g = 0.0, dg = 0.0, sg = 0.0;
+        if (x_free) {
+          const double zl = a.zlx[nb * NX + i], zu = a.zux[nb * NX + i];
+          const BarrierTerm bt = barrier_term(x[i], a.xlb[i], a.xub[i], zl, zu, mu);
+          g = bt.grad; dg = bt.dz; sg = bt.sigma;
+          phi += barrier_value(x[i], a.xlb[i], a.xub[i], mu);
+          if (has_lb(a.xlb[i])) comp = dmax(comp, dabs((x[i] - a.xlb[i]) * zl - mu));
+          if (has_ub(a.xub[i])) comp = dmax(comp, dabs((a.xub[i] - x[i]) * zu - mu));
+        }
+        XU[i] = g; XU[NX + i] = dg; XU[2 * NX + i] = sg;
+      }
+#pragma unroll
+      for (int i = 0; i < NU; ++i) {
+        const double zl = a.zlu[sb * NU + i], zu = a.zuu[sb * NU + i];
+        const BarrierTerm bt = barrier_term(u[i], a.ulb[i], a.uub[i], zl, zu, mu);
+        phi += barrier_value(u[i], a.ulb[i], a.uub[i], mu);
+        if (has_lb(a.ulb[i])) comp = dmax(comp, dabs((u[i] - a.ulb[i]) * zl - mu));
+        if (has_ub(a.uub[i])) comp = dmax(comp, dabs((a.uub[i] - u[i]) * zu - mu));
+        XU[3 * NX + i] = bt.grad; XU[3 * NX + NU + i] = bt.dz; XU[3 * NX + 2 * NU + i] = bt.sigma;
+      }
+    }
+    // barrier terms of the collocation states, one entry per own row
+#pragma unroll
+    for (int lr = 0; lr < RPL; ++lr) {
+      const int r = lr * 4 + q;
+      if (r < NC) {
+        const int j = r % NX;
+        const double zl = a.zlc[sb * NC + r], zu = a.zuc[sb * NC + r];
+        const double Xr = Xg[r];
+        const BarrierTerm bt = barrier_term(Xr, a.xlb[j], a.xub[j], zl, zu, mu);
+        S[oGX + r] = bt.grad; S[oDGX + r] = bt.dz; S[oSGX + r] = bt.sigma;
+        phi += barrier_value(Xr, a.xlb[j], a.xub[j], mu);
+        if (has_lb(a.xlb[j])) comp = dmax(comp, dabs((Xr - a.xlb[j]) * zl - mu));
+        if (has_ub(a.xub[j])) comp = dmax(comp, dabs((a.xub[j] - Xr) * zu - mu));
+      }
+    }
+    __syncwarp();
+    // gX (cost + barrier) for every collocation state: gXf[r] = w*lx_i[j] + barrier grad
+#pragma unroll
+    for (int lr = 0; lr < RPL; ++lr) {
+      const int r = lr * 4 + q;
+      if (r < NC) S[oGX + r] += S[oL + (r / NX) * LSZ + 1 + (r % NX)];
+    }
+    __syncwarp();
+
+    // ---------------------------------------------------------------- 2. exact Hessian: collocation multipliers
+    if (P::EXACT_HESS) {
+      const double* lam1 = a.lam + (nb + 1) * NX;
+      double Rt[RPL][WT];
+      int pv[RPL];
+#pragma unroll
+      for (int lr = 0; lr < RPL; ++lr) {
+        const int r = lr * 4 + q;       // row (i', cc) of G_X^T  = column of G_X
+        const int ip = r / NX, cc = r % NX;  // ip = i' - 1
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const int i = c / NX, rr = c % NX;   // column (i, rr): row of G_X
+          double v = 0.0;
+          if (r < NC) {
+            if (i == ip) v = dt * S[oF + ip * FSZ + NX + rr * NX + cc];
+            if (rr == cc) v -= P::CC((ip + 1) * (D + 1) + (i + 1));
+          }
+          Rt[lr][c] = v;
+        }
+        Rt[lr][NC] = (r < NC) ? -(S[oGX + r] + S[oDGX + r] + P::CD(ip + 1) * lam1[cc]) : 0.0;
+      }
+      const bool okT = gauss_jordan<WT, NC>(Rt, pv, q, S + oPB);
+#pragma unroll
+      for (int lr = 0; lr < RPL; ++lr)
+        if (pv[lr] >= 0) S[oNU + pv[lr]] = okT ? Rt[lr][NC] : 0.0;
+      __syncwarp();
+      if (q < D) {
+        double nu[NX], hxx[NX * NX], hux[NU * NX], huu[NU * NU];
+#pragma unroll
+        for (int rr = 0; rr < NX; ++rr) nu[rr] = dt * S[oNU + q * NX + rr];
+        P::f_hess(Xq, u, sp, t + dt * P::CTAU(q), dt, nu, hxx, hux, huu);
+        double* L = S + oL + q * LSZ;
+#pragma unroll
+        for (int j = 0; j < NX * NX; ++j) L[1 + NX + NU + j] += hxx[j];
+#pragma unroll
+        for (int j = 0; j < NU * NX; ++j) L[1 + NX + NU + NX * NX + j] += hux[j];
+#pragma unroll
+        for (int j = 0; j < NU * NU; ++j) L[1 + NX + NU + NX * NX + NU * NX + j] += huu[j];
+      }
+      __syncwarp();
+    }
+
+    // ---------------------------------------------------------------- 3. plain system  G_X dX + G_x dx + G_u du + c = 0
+    double R[RPL][W];
+    int pivvar[RPL];
+#pragma unroll
+    for (int lr = 0; lr < RPL; ++lr) {
+      const int r = lr * 4 + q;  // row (i, rr)
+      const int ii = r / NX, rr = r % NX;  // ii = i - 1
+      const bool rv = r < NC;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const int jp = c / NX, cc = c % NX;  // column (j, cc), jp = j - 1
+        double v = 0.0;
+        if (rv) {
+          if (jp == ii) v = dt * S[oF + ii * FSZ + NX + rr * NX + cc];
+          if (cc == rr) v -= P::CC((jp + 1) * (D + 1) + (ii + 1));
+        }
+        R[lr][c] = v;
+      }
+#pragma unroll
+      for (int c = 0; c < NX; ++c) R[lr][NC + c] = (rv && c == rr) ? -P::CC(0 * (D + 1) + (ii + 1)) : 0.0;
+#pragma unroll
+      for (int c = 0; c < NU; ++c) R[lr][NC + NX + c] = rv ? dt * S[oF + ii * FSZ + NX + NX * NX + rr * NU + c] : 0.0;
+      double res = 0.0;
+      if (rv) {
+        double xp = P::CC(0 * (D + 1) + (ii + 1)) * xg[rr];
+#pragma unroll
+        for (int j = 1; j <= D; ++j) xp += P::CC(j * (D + 1) + (ii + 1)) * Xg[(j - 1) * NX + rr];
+        res = dt * S[oF + ii * FSZ + rr] - xp;
+        c1 += dabs(res); cinf = dmax(cinf, dabs(res));
+      }
+      R[lr][NC + NE] = res;
+    }
+    gauss_jordan<W, NC>(R, pivvar, q, S + oPB);
+    // T rows (negated solution) to the scratch pad, indexed by variable
+#pragma unroll
+    for (int lr = 0; lr < RPL; ++lr)
+      if (pivvar[lr] >= 0) {
+        double* Tr = S + oT + pivvar[lr] * (NE + 1);
+#pragma unroll
+        for (int j = 0; j <= NE; ++j) Tr[j] = -R[lr][NC + j];
+      }
+    __syncwarp();
+
+    // ---------------------------------------------------------------- 4. reduced stage data
+    double* qa = a.qa + sb * T::NAp;
+    double* qh = a.qh + sb * T::NHp;
+    double* el = a.el + sb * T::TD;
+    const double* Tm = S + oT;
+    // dynamics rows (lane q -> state rows q, q+4, ...)
+    for (int rr = q; rr < NX; rr += 4) {
+      double xf = P::CD(0) * xg[rr], bsum = 0.0;
+#pragma unroll
+      for (int i = 1; i <= D; ++i) { xf += P::CD(i) * Xg[(i - 1) * NX + rr]; bsum += P::CD(i) * Tm[((i - 1) * NX + rr) * (NE + 1) + NE]; }
+      const double res = xf - xng[rr];
+      c1 += dabs(res); cinf = dmax(cinf, dabs(res));
+      if (active) {
+#pragma unroll
+        for (int c = 0; c < NX; ++c) {
+          double s = (rr == c) ? P::CD(0) : 0.0;
+#pragma unroll
+          for (int i = 1; i <= D; ++i) s += P::CD(i) * Tm[((i - 1) * NX + rr) * (NE + 1) + c];
+          qa[T::oA + rr * NX + c] = s;
+        }
+#pragma unroll
+        for (int c = 0; c < NU; ++c) {
+          double s = 0.0;
+#pragma unroll
+          for (int i = 1; i <= D; ++i) s += P::CD(i) * Tm[((i - 1) * NX + rr) * (NE + 1) + NX + c];
+          qa[T::oB + rr * NU + c] = s;
+        }
+        qa[T::ob + rr] = bsum + res;
+      }
+    }
+    // HT_i = HXX_i T_i  and  wv_i = gX_i + HXX_i t0_i   (row l = own rows), HXX_i = cost/constraint Hessian + sigma
+#pragma unroll
+    for (int lr = 0; lr < RPL; ++lr) {
+      const int r = lr * 4 + q;
+      if (r < NC) {
+        const int ii = r / NX, l = r % NX;
+        const double* Hx = S + oL + ii * LSZ + 1 + NX + NU;
+        double* HT = S + oHT + r * (NE + 1);
+#pragma unroll
+        for (int c = 0; c <= NE; ++c) {
+          double s = (c == NE) ? S[oGX + r] : 0.0;
+#pragma unroll
+          for (int l2 = 0; l2 < NX; ++l2) {
+            double hv = Hx[l * NX + l2];
+            if (l2 == l) hv += S[oSGX + r];
+            s += hv * Tm[(ii * NX + l2) * (NE + 1) + c];
+          }
+          HT[c] = s;
+        }
+      }
+    }
+    __syncwarp();
+    const double* XU = S + oXU;
+    // reduced Hessian entries, round robin over the quad
+    for (int e = q; e < NE * NE; e += 4) {
+      const int ii = e / NE, jj = e % NE;
+      if (ii < NX && jj > ii) continue;            // Q: lower triangle computed, mirrored below
+      double s = 0.0;
+#pragma unroll
+      for (int r = 0; r < NC; ++r) s += Tm[r * (NE + 1) + ii] * S[oHT + r * (NE + 1) + jj];
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        const double* Hu = S + oL + i * LSZ + 1 + NX + NU + NX * NX;
+        if (ii >= NX)
+#pragma unroll
+          for (int l = 0; l < NX; ++l) s += Hu[(ii - NX) * NX + l] * Tm[(i * NX + l) * (NE + 1) + jj];
+        if (jj >= NX)
+#pragma unroll
+          for (int l = 0; l < NX; ++l) s += Hu[(jj - NX) * NX + l] * Tm[(i * NX + l) * (NE + 1) + ii];
+        if (ii >= NX && jj >= NX) s += S[oL + i * LSZ + 1 + NX + NU + NX * NX + NU * NX + (ii - NX) * NU + (jj - NX)];
+      }
+      if (ii == jj) s += (ii < NX) ? XU[2 * NX + ii] : XU[3 * NX + 2 * NU + (ii - NX)];
+      if (active) {
+        if (ii < NX && jj < NX) { qh[T::oQ + ii * NX + jj] = s; qh[T::oQ + jj * NX + ii] = s; }
+        else if (ii >= NX && jj < NX) qh[T::oS + (ii - NX) * NX + jj] = s;
+        else if (ii >= NX && jj >= NX) qh[T::oR + (ii - NX) * NU + (jj - NX)] = s;
+      }
+    }
+    // gradients: Newton form (q, r) and multiplier form (qbar, rbar)
+    for (int ii = q; ii < NE; ii += 4) {
+      double g = (ii < NX) ? XU[ii] : XU[3 * NX + (ii - NX)];
+      double gb = g + ((ii < NX) ? XU[NX + ii] : XU[3 * NX + NU + (ii - NX)]);
+      if (ii >= NX)
+#pragma unroll
+        for (int i = 0; i < D; ++i) { const double lu = S[oL + i * LSZ + 1 + NX + (ii - NX)]; g += lu; gb += lu; }
+      const double g_plain = g;  // unreduced gradient wrt x / u (cost + barrier), for the line-search derivative
+#pragma unroll
+      for (int r = 0; r < NC; ++r) {
+        const double tri = Tm[r * (NE + 1) + ii];
+        g += tri * S[oHT + r * (NE + 1) + NE];
+        gb += tri * (S[oGX + r] + S[oDGX + r]);
+      }
+      if (ii >= NX)
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+          const double* Hu = S + oL + i * LSZ + 1 + NX + NU + NX * NX;
+#pragma unroll
+          for (int l = 0; l < NX; ++l) g += Hu[(ii - NX) * NX + l] * Tm[(i * NX + l) * (NE + 1) + NE];
+        }
+      if (active) {
+        if (ii < NX) { qh[T::oq + ii] = g; qh[T::oqb + ii] = gb; el[T::ogx + ii] = g_plain; }
+        else { qh[T::orr + (ii - NX)] = g; qh[T::orb + (ii - NX)] = gb; el[T::ogu + (ii - NX)] = g_plain; }
+      }
+    }
+    // elimination block for Expand: T | t0 | gX
+    if (active) {
+      for (int e = q; e < NC * NE; e += 4) el[T::oT + e] = Tm[(e / NE) * (NE + 1) + (e % NE)];
+      for (int r = q; r < NC; r += 4) { el[T::ot0 + r] = Tm[r * (NE + 1) + NE]; el[T::ogX + r] = S[oGX + r]; }
+    }
+    // ---------------------------------------------------------------- 5. per-node scalars
+#pragma unroll
+    for (int m = 1; m < 4; m <<= 1) {
+      phi += qshfl_xor(phi, m); c1 += qshfl_xor(c1, m);
+      comp = dmax(comp, qshfl_xor(comp, m)); cinf = dmax(cinf, qshfl_xor(cinf, m));
+    }
+    if (active && q == 0) { a.s_cinf[nb] = cinf; a.s_c1[nb] = c1; a.s_phi[nb] = phi; a.s_comp[nb] = comp; }
+  }
+};
+
+template <class P>
+__global__ void __launch_bounds__(128) eval_quad_kernel(OcpArgs a) { EvalQuad<P>::run(a); }
+
+template <class P>
+inline cudaError_t launch_eval_quad(const OcpArgs& a, cudaStream_t s) {
+  using E = EvalQuad<P>;
+  cudaError_t e = cudaFuncSetAttribute(eval_quad_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, E::SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  const long long nodes = (long long)a.B * OcpT<P>::N;
+  const int grid = (int)((nodes + E::QUADS - 1) / E::QUADS);
+  eval_quad_kernel<P><<<grid, 128, E::SMEM_BYTES, s>>>(a);
+  launch_1d<OcpEvalTerminal<P>>(a, a.B, s);
+  return cudaGetLastError();
+}
+
+#endif  // HB_DEVICE_BUILD
+}  // namespace hb

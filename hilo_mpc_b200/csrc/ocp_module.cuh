@@ -3,6 +3,7 @@
 #pragma once
 #include "ocp_kernels.cuh"
 #include "riccati.cuh"
+#include "eval_quad.cuh"
 #include "../../include/hilo_b200.h"
 
 namespace hb {
@@ -131,7 +132,18 @@ struct OcpModule {
     const int check_every = c->check_every > 0 ? c->check_every : 4;
     int launched = 0;
     for (int it = 0; it <= c->max_iter; ++it) {
-      tm.begin(K_EVAL); launch_2d<OcpEval<P>>(a, a.B, T::N + 1, s); tm.end();
+      tm.begin(K_EVAL);
+#if HB_DEVICE_BUILD
+      if (c->eval_variant != 0 && EvalQuad<P>::SUPPORTED) {
+        cudaError_t e = launch_eval_quad<P>(a, s);
+        if (e != cudaSuccess) return (int)e;
+      } else {
+        launch_2d<OcpEval<P>>(a, a.B, T::N + 1, s);
+      }
+#else
+      launch_2d<OcpEval<P>>(a, a.B, T::N + 1, s);
+#endif
+      tm.end();
       tm.begin(K_RICCATI);
 #if HB_DEVICE_BUILD
       if (c->riccati_variant != 0 && RiccatiTma<P>::SUPPORTED) {

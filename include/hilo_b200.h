@@ -85,6 +85,8 @@ typedef struct hb_ocp_call {
                                1: x/u/xc AND the bound multipliers kept in `work` by the previous call are reused,
                                   tiny push, mu = mu_init_warm (needs the same `work` buffer and batch as before)    */
   double mu_init_warm;
+  int eval_variant;         /* 1: 4-lanes-per-node register-resident evaluation kernel where supported (default),
+                               0: one-thread-per-node kernel                                                       */
 } hb_ocp_call;
 
 /* kernel indices of kernel_ms / kernel_count */

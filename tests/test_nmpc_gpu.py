@@ -132,3 +132,22 @@ def test_warm_start_mode_reaches_the_same_solution_in_fewer_iterations(cuda_devi
     for ua, ub in zip(runs[0][0], runs[1][0]):
         assert (ua - ub).abs().max().item() < 1e-4 * ua.abs().max().item()
     assert np.mean(runs[1][1][1:]) < np.mean(runs[0][1][1:])
+
+
+def test_quad_eval_kernel_matches_thread_per_node_kernel(cuda_device):
+    """The 4-lanes-per-node register-resident evaluation kernel and the plain one-thread-per-node kernel linearise the same
+    NLP: complete solves driven by either must agree to rounding level (exact and Gauss-Newton Hessians, N=50)."""
+    import torch
+    from hilo_mpc_b200.examples import cstr_initial_states, cstr_nmpc
+    x0 = torch.tensor(cstr_initial_states(777, seed=31), device=cuda_device)
+    for hess in ('exact', 'gauss-newton'):
+        res = []
+        for variant in (0, 1):
+            nmpc = cstr_nmpc(N=50, solver_options={'b200.eval_variant': variant, 'b200.hessian': hess})
+            nmpc.optimize(x0)
+            out = nmpc._last
+            assert (out['status'] == 1).all()
+            res.append({k: out[k].clone() for k in ('x', 'u', 'lam', 'iters')})
+        assert (res[0]['iters'] - res[1]['iters']).abs().max().item() <= 1
+        assert (res[0]['x'] - res[1]['x']).abs().max().item() < 1e-8
+        assert (res[0]['u'] - res[1]['u']).abs().max().item() < 1e-7
