@@ -134,9 +134,13 @@ struct OcpModule {
     for (int it = 0; it <= c->max_iter; ++it) {
       tm.begin(K_EVAL);
 #if HB_DEVICE_BUILD
-      if (c->eval_variant != 0 && EvalQuad<P>::SUPPORTED) {
-        cudaError_t e = launch_eval_quad<P>(a, s);
-        if (e != cudaSuccess) return (int)e;
+      if constexpr (EvalQuad<P>::SUPPORTED) {
+        if (c->eval_variant != 0) {
+          cudaError_t e = launch_eval_quad<P>(a, s);
+          if (e != cudaSuccess) return (int)e;
+        } else {
+          launch_2d<OcpEval<P>>(a, a.B, T::N + 1, s);
+        }
       } else {
         launch_2d<OcpEval<P>>(a, a.B, T::N + 1, s);
       }
@@ -146,9 +150,13 @@ struct OcpModule {
       tm.end();
       tm.begin(K_RICCATI);
 #if HB_DEVICE_BUILD
-      if (c->riccati_variant != 0 && RiccatiTma<P>::SUPPORTED) {
-        cudaError_t e = launch_riccati_tma<P>(a, s);
-        if (e != cudaSuccess) return (int)e;
+      if constexpr (RiccatiTma<P>::SUPPORTED) {
+        if (c->riccati_variant != 0) {
+          cudaError_t e = launch_riccati_tma<P>(a, s);
+          if (e != cudaSuccess) return (int)e;
+        } else {
+          launch_1d<OcpRiccati<P>>(a, a.B, s);
+        }
       } else {
         launch_1d<OcpRiccati<P>>(a, a.B, s);
       }
