@@ -24,6 +24,14 @@ struct OcpEvalTerminal {
   static HB_HD void run(const OcpArgs& a, int b) { OcpEval<P>::run(a, b, OcpT<P>::N); }
 };
 
+// nodes whose statically pivoted elimination met a degenerate pivot are recomputed with partial pivoting
+template <class P>
+struct OcpEvalFlagged {
+  static HB_HD void run(const OcpArgs& a, int b, int k) {
+    if (a.nflag[(long long)b * OcpT<P>::N + k] != 0) OcpEval<P>::run(a, b, k);
+  }
+};
+
 #if HB_DEVICE_BUILD
 
 template <class P>
@@ -31,6 +39,7 @@ struct EvalQuad {
   using T = OcpT<P>;
   static constexpr int NX = T::NX, NU = T::NU, NC = T::NC, NE = T::NE, N = T::N, D = P::DEG;
   static constexpr int RPL = (NC + 3) / 4;   // rows per lane
+  static constexpr bool NX4 = (NX % 4 == 0); // then the collocation point of a local row is a compile-time constant
   static constexpr int W = NC + NE + 1;      // columns of the plain system  [G_X | G_x G_u | c]
   static constexpr int WT = NC + 1;          // columns of the transposed system
   static constexpr bool SUPPORTED = (P::METHOD == METHOD_COLLOCATION) && P::FIXED_X0 && !P::HAS_GADD && !P::HAS_ARR &&
@@ -41,61 +50,57 @@ struct EvalQuad {
   static constexpr int oF = 0, oL = oF + D * FSZ, oPB = oL + D * LSZ, oT = oPB + 2 * W, oNU = oT + NC * (NE + 1),
                        oGX = oNU + NC, oDGX = oGX + NC, oSGX = oDGX + NC, oXU = oSGX + NC,  // gx dgx sigx gu dgu sigu
                        oEND = oXU + 3 * NX + 3 * NU,
-                       oHT = oF;  // H*T rows reuse the model-derivative area (dead once the plain system is assembled)
-  static_assert(D * NX * (NE + 1) <= D * FSZ, "HT alias does not fit");
-  static constexpr int SCR = ((oEND + 1) & ~1) + 3;  // odd multiple keeps neighbouring quads on different banks
+                       oRED = oEND;  // quad-reduction area: 4 lanes x (NE x (NE+1) partial Hessian/gradient + NE)
+  static constexpr int NRED = NE * (NE + 1) + NE;
+  static constexpr int SCR = ((oRED + 4 * NRED + 1) & ~1) + 3;  // odd multiple keeps neighbouring quads on different banks
   static constexpr int QUADS = 32;                   // quads (nodes) per CTA, 128 threads
   static constexpr int SMEM_BYTES = QUADS * SCR * 8;
 
   static __device__ __forceinline__ double qshfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m, 4); }
   static __device__ __forceinline__ int qshfl_xor(int v, int m) { return __shfl_xor_sync(0xffffffffu, v, m, 4); }
 
-  // Gauss-Jordan on rows R[RPL][NCOLS] (row lr of lane q is global row lr*4 + q), pivot columns 0..NPIV-1.
-  // On return row lr of lane q holds, in columns >= NPIV, the solution of variable pivvar[lr].
+  // 1/x (either sign): hardware approximation + two Newton steps
+  static __device__ __forceinline__ double rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+  }
+
+  // Gauss-Jordan on rows R[RPL][NCOLS] (row lr of lane q is global row lr*4 + q) with the STATIC pivot order
+  // "row c for column c": no search, no row selection; the owner lane and its local row are compile-time constants.
+  // The collocation matrix is dt*blkdiag(f_x) - C^T (x) I, whose unpivoted pivots are about (-3.2, -2.1, -9.0) per
+  // state for the Radau-3 constants; the smallest pivot magnitude met is returned so that the caller can hand nodes
+  // with a degenerate pivot (stiff dt*f_x) to the partially pivoted one-thread-per-node kernel.
+  // On return row r holds, in columns >= NPIV, the solution of variable r.
   template <int NCOLS, int NPIV>
-  static __device__ __forceinline__ bool gauss_jordan(double (&R)[RPL][NCOLS], int (&pivvar)[RPL], int q, double* pb) {
-    bool ok = true;
-#pragma unroll
-    for (int lr = 0; lr < RPL; ++lr) pivvar[lr] = (lr * 4 + q < NPIV) ? -1 : -2;  // -2: row does not exist
+  static __device__ __forceinline__ double gauss_jordan(double (&R)[RPL][NCOLS], int q, double* pb) {
+    double minpiv = 1e300;
 #pragma unroll
     for (int c = 0; c < NPIV; ++c) {
-      double best = -1.0;
-      int code = 0;
-#pragma unroll
-      for (int lr = 0; lr < RPL; ++lr) {
-        const double v = (pivvar[lr] == -1) ? fabs(R[lr][c]) : -1.0;
-        if (v > best) { best = v; code = q * RPL + lr; }
-      }
-#pragma unroll
-      for (int m = 1; m < 4; m <<= 1) {
-        const double ob = qshfl_xor(best, m);
-        const int oc = qshfl_xor(code, m);
-        if (ob > best || (ob == best && oc < code)) { best = ob; code = oc; }
-      }
-      ok = ok && (best > 0.0);
-      const int po = code / RPL, plr = code % RPL;
-      double* prow = pb + (c & 1) * NCOLS;  // double-buffered broadcast row
+      const int po = c & 3, plr = c >> 2;   // owner lane / local row of the pivot row
+      double* prow = pb + (c & 1) * NCOLS;   // double-buffered broadcast row
       if (q == po) {
+        const double piv = R[plr][c];
+        const double inv = rcp(piv);
+        prow[c] = fabs(piv);
 #pragma unroll
-        for (int lr = 0; lr < RPL; ++lr)
-          if (lr == plr) {
-            const double inv = 1.0 / R[lr][c];
-#pragma unroll
-            for (int j = c + 1; j < NCOLS; ++j) { R[lr][j] *= inv; prow[j] = R[lr][j]; }
-            pivvar[lr] = c;
-          }
+        for (int j = c + 1; j < NCOLS; ++j) { R[plr][j] *= inv; prow[j] = R[plr][j]; }
       }
       __syncwarp();
+      minpiv = fmin(minpiv, prow[c]);
 #pragma unroll
       for (int lr = 0; lr < RPL; ++lr) {
-        const bool is_piv = (q == po) && (lr == plr);
+        const bool is_piv = (lr == plr) && (q == po);
         const double f = is_piv ? 0.0 : R[lr][c];
 #pragma unroll
         for (int j = c + 1; j < NCOLS; ++j) R[lr][j] -= f * prow[j];
       }
     }
     __syncwarp();
-    return ok;
+    return (minpiv == minpiv) ? minpiv : 0.0;
   }
 
   static __device__ void run(const OcpArgs& a) {
@@ -130,7 +135,7 @@ struct EvalQuad {
 #pragma unroll
     for (int i = 0; i < NU; ++i) u[i] = a.u[sb * NU + i];
 
-    double phi = 0.0, comp = 0.0, c1 = 0.0, cinf = 0.0;
+    double phi = 0.0, comp = 0.0, c1 = 0.0, cinf = 0.0, minpiv = 1e300;
     // ---------------------------------------------------------------- 1. derivatives at the collocation points
     if (q < D) {
       const int i = q + 1;
@@ -229,11 +234,10 @@ struct EvalQuad {
     if (P::EXACT_HESS) {
       const double* lam1 = a.lam + (nb + 1) * NX;
       double Rt[RPL][WT];
-      int pv[RPL];
 #pragma unroll
       for (int lr = 0; lr < RPL; ++lr) {
         const int r = lr * 4 + q;       // row (i', cc) of G_X^T  = column of G_X
-        const int ip = r / NX, cc = r % NX;  // ip = i' - 1
+        const int ip = NX4 ? (lr * 4) / NX : r / NX, cc = NX4 ? ((lr * 4) % NX + q) : r % NX;  // ip = i' - 1
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
           const int i = c / NX, rr = c % NX;   // column (i, rr): row of G_X
@@ -246,10 +250,10 @@ struct EvalQuad {
         }
         Rt[lr][NC] = (r < NC) ? -(S[oGX + r] + S[oDGX + r] + P::CD(ip + 1) * lam1[cc]) : 0.0;
       }
-      const bool okT = gauss_jordan<WT, NC>(Rt, pv, q, S + oPB);
+      minpiv = fmin(minpiv, gauss_jordan<WT, NC>(Rt, q, S + oPB));
 #pragma unroll
       for (int lr = 0; lr < RPL; ++lr)
-        if (pv[lr] >= 0) S[oNU + pv[lr]] = okT ? Rt[lr][NC] : 0.0;
+        if (lr * 4 + q < NC) S[oNU + lr * 4 + q] = Rt[lr][NC];
       __syncwarp();
       if (q < D) {
         double nu[NX], hxx[NX * NX], hux[NU * NX], huu[NU * NU];
@@ -269,11 +273,10 @@ struct EvalQuad {
 
     // ---------------------------------------------------------------- 3. plain system  G_X dX + G_x dx + G_u du + c = 0
     double R[RPL][W];
-    int pivvar[RPL];
 #pragma unroll
     for (int lr = 0; lr < RPL; ++lr) {
       const int r = lr * 4 + q;  // row (i, rr)
-      const int ii = r / NX, rr = r % NX;  // ii = i - 1
+      const int ii = NX4 ? (lr * 4) / NX : r / NX, rr = NX4 ? ((lr * 4) % NX + q) : r % NX;  // ii = i - 1
       const bool rv = r < NC;
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
@@ -299,15 +302,18 @@ struct EvalQuad {
       }
       R[lr][NC + NE] = res;
     }
-    gauss_jordan<W, NC>(R, pivvar, q, S + oPB);
-    // T rows (negated solution) to the scratch pad, indexed by variable
+    minpiv = fmin(minpiv, gauss_jordan<W, NC>(R, q, S + oPB));
+    // own T rows (negated solution) stay in registers and are published to the scratch pad for the other lanes
+    double Tr[RPL][NE + 1];
 #pragma unroll
-    for (int lr = 0; lr < RPL; ++lr)
-      if (pivvar[lr] >= 0) {
-        double* Tr = S + oT + pivvar[lr] * (NE + 1);
+    for (int lr = 0; lr < RPL; ++lr) {
+      const int r = lr * 4 + q;
 #pragma unroll
-        for (int j = 0; j <= NE; ++j) Tr[j] = -R[lr][NC + j];
+      for (int j = 0; j <= NE; ++j) {
+        Tr[lr][j] = (r < NC) ? -R[lr][NC + j] : 0.0;
+        if (r < NC) S[oT + r * (NE + 1) + j] = Tr[lr][j];
       }
+    }
     __syncwarp();
 
     // ---------------------------------------------------------------- 4. reduced stage data
@@ -340,78 +346,99 @@ struct EvalQuad {
         qa[T::ob + rr] = bsum + res;
       }
     }
-    // HT_i = HXX_i T_i  and  wv_i = gX_i + HXX_i t0_i   (row l = own rows), HXX_i = cost/constraint Hessian + sigma
+    // Partial sums over the OWN rows r = (i, l), all operands in registers:
+    //   Pq[ii][jj] += T[r][ii] * HT[r][jj]        HT[r][:] = (H_i + diag sigma)[l][:] T_i[:][:]  (+ gX[r] in column NE)
+    //   Pq[NX+a][jj] += Hu_i[a][l] * T[r][jj]     (jj = 0..NE; column NE is the gradient)
+    //   Pq[ii][NX+a] += Hu_i[a][l] * T[r][ii]
+    //   gb[ii]      += T[r][ii] * (gX + dz)[r]    multiplier-form gradient
+    double Pq[NE][NE + 1], gbp[NE];
+#pragma unroll
+    for (int ii = 0; ii < NE; ++ii) {
+      gbp[ii] = 0.0;
+#pragma unroll
+      for (int jj = 0; jj <= NE; ++jj) Pq[ii][jj] = 0.0;
+    }
 #pragma unroll
     for (int lr = 0; lr < RPL; ++lr) {
       const int r = lr * 4 + q;
       if (r < NC) {
-        const int ii = r / NX, l = r % NX;
-        const double* Hx = S + oL + ii * LSZ + 1 + NX + NU;
-        double* HT = S + oHT + r * (NE + 1);
+        const int ii0 = NX4 ? (lr * 4) / NX : r / NX, l = NX4 ? ((lr * 4) % NX + q) : r % NX;
+        const double* Hx = S + oL + ii0 * LSZ + 1 + NX + NU + l * NX;
+        const double* Hu = S + oL + ii0 * LSZ + 1 + NX + NU + NX * NX;
+        double HTr[NE + 1];
 #pragma unroll
-        for (int c = 0; c <= NE; ++c) {
-          double s = (c == NE) ? S[oGX + r] : 0.0;
+        for (int c = 0; c <= NE; ++c) HTr[c] = (c == NE) ? S[oGX + r] : 0.0;
 #pragma unroll
-          for (int l2 = 0; l2 < NX; ++l2) {
-            double hv = Hx[l * NX + l2];
-            if (l2 == l) hv += S[oSGX + r];
-            s += hv * Tm[(ii * NX + l2) * (NE + 1) + c];
-          }
-          HT[c] = s;
+        for (int l2 = 0; l2 < NX; ++l2) {
+          double hv = Hx[l2];
+          if (l2 == l) hv += S[oSGX + r];
+          const double* T2 = Tm + (ii0 * NX + l2) * (NE + 1);
+#pragma unroll
+          for (int c = 0; c <= NE; ++c) HTr[c] += hv * T2[c];
         }
+        const double gbx = S[oGX + r] + S[oDGX + r];
+#pragma unroll
+        for (int ii = 0; ii < NE; ++ii) {
+          gbp[ii] += Tr[lr][ii] * gbx;
+#pragma unroll
+          for (int jj = 0; jj <= NE; ++jj) Pq[ii][jj] += Tr[lr][ii] * HTr[jj];
+        }
+#pragma unroll
+        for (int aa = 0; aa < NU; ++aa) {
+          const double hu = Hu[aa * NX + l];
+#pragma unroll
+          for (int jj = 0; jj <= NE; ++jj) Pq[NX + aa][jj] += hu * Tr[lr][jj];
+#pragma unroll
+          for (int ii = 0; ii < NE; ++ii) Pq[ii][NX + aa] += hu * Tr[lr][ii];
+        }
+      }
+    }
+    // quad reduction through the scratch pad, then every lane finalises a share of the entries
+    {
+      double* red = S + oRED + q * NRED;
+#pragma unroll
+      for (int ii = 0; ii < NE; ++ii) {
+#pragma unroll
+        for (int jj = 0; jj <= NE; ++jj) red[ii * (NE + 1) + jj] = Pq[ii][jj];
+        red[NE * (NE + 1) + ii] = gbp[ii];
       }
     }
     __syncwarp();
     const double* XU = S + oXU;
-    // reduced Hessian entries, round robin over the quad
-    for (int e = q; e < NE * NE; e += 4) {
-      const int ii = e / NE, jj = e % NE;
-      if (ii < NX && jj > ii) continue;            // Q: lower triangle computed, mirrored below
-      double s = 0.0;
+    for (int e = q; e < NRED; e += 4) {
+      const double s = S[oRED + e] + S[oRED + NRED + e] + S[oRED + 2 * NRED + e] + S[oRED + 3 * NRED + e];
+      if (e < NE * (NE + 1)) {
+        const int ii = e / (NE + 1), jj = e % (NE + 1);
+        if (jj < NE) {  // Hessian entry
+          double v = s;
+          if (ii >= NX && jj >= NX)
 #pragma unroll
-      for (int r = 0; r < NC; ++r) s += Tm[r * (NE + 1) + ii] * S[oHT + r * (NE + 1) + jj];
+            for (int i = 0; i < D; ++i) v += S[oL + i * LSZ + 1 + NX + NU + NX * NX + NU * NX + (ii - NX) * NU + (jj - NX)];
+          if (ii == jj) v += (ii < NX) ? XU[2 * NX + ii] : XU[3 * NX + 2 * NU + (ii - NX)];
+          if (active) {
+            if (ii < NX && jj < NX) qh[T::oQ + ii * NX + jj] = v;
+            else if (ii >= NX && jj < NX) qh[T::oS + (ii - NX) * NX + jj] = v;
+            else if (ii >= NX && jj >= NX) qh[T::oR + (ii - NX) * NU + (jj - NX)] = v;
+          }
+        } else {        // Newton-form gradient q / r
+          double g = (ii < NX) ? XU[ii] : XU[3 * NX + (ii - NX)];
+          if (ii >= NX)
 #pragma unroll
-      for (int i = 0; i < D; ++i) {
-        const double* Hu = S + oL + i * LSZ + 1 + NX + NU + NX * NX;
+            for (int i = 0; i < D; ++i) g += S[oL + i * LSZ + 1 + NX + (ii - NX)];
+          if (active) {
+            if (ii < NX) { qh[T::oq + ii] = g + s; el[T::ogx + ii] = g; }
+            else { qh[T::orr + (ii - NX)] = g + s; el[T::ogu + (ii - NX)] = g; }
+          }
+        }
+      } else {          // multiplier-form gradient qbar / rbar
+        const int ii = e - NE * (NE + 1);
+        double g = (ii < NX) ? (XU[ii] + XU[NX + ii]) : (XU[3 * NX + (ii - NX)] + XU[3 * NX + NU + (ii - NX)]);
         if (ii >= NX)
 #pragma unroll
-          for (int l = 0; l < NX; ++l) s += Hu[(ii - NX) * NX + l] * Tm[(i * NX + l) * (NE + 1) + jj];
-        if (jj >= NX)
-#pragma unroll
-          for (int l = 0; l < NX; ++l) s += Hu[(jj - NX) * NX + l] * Tm[(i * NX + l) * (NE + 1) + ii];
-        if (ii >= NX && jj >= NX) s += S[oL + i * LSZ + 1 + NX + NU + NX * NX + NU * NX + (ii - NX) * NU + (jj - NX)];
-      }
-      if (ii == jj) s += (ii < NX) ? XU[2 * NX + ii] : XU[3 * NX + 2 * NU + (ii - NX)];
-      if (active) {
-        if (ii < NX && jj < NX) { qh[T::oQ + ii * NX + jj] = s; qh[T::oQ + jj * NX + ii] = s; }
-        else if (ii >= NX && jj < NX) qh[T::oS + (ii - NX) * NX + jj] = s;
-        else if (ii >= NX && jj >= NX) qh[T::oR + (ii - NX) * NU + (jj - NX)] = s;
-      }
-    }
-    // gradients: Newton form (q, r) and multiplier form (qbar, rbar)
-    for (int ii = q; ii < NE; ii += 4) {
-      double g = (ii < NX) ? XU[ii] : XU[3 * NX + (ii - NX)];
-      double gb = g + ((ii < NX) ? XU[NX + ii] : XU[3 * NX + NU + (ii - NX)]);
-      if (ii >= NX)
-#pragma unroll
-        for (int i = 0; i < D; ++i) { const double lu = S[oL + i * LSZ + 1 + NX + (ii - NX)]; g += lu; gb += lu; }
-      const double g_plain = g;  // unreduced gradient wrt x / u (cost + barrier), for the line-search derivative
-#pragma unroll
-      for (int r = 0; r < NC; ++r) {
-        const double tri = Tm[r * (NE + 1) + ii];
-        g += tri * S[oHT + r * (NE + 1) + NE];
-        gb += tri * (S[oGX + r] + S[oDGX + r]);
-      }
-      if (ii >= NX)
-#pragma unroll
-        for (int i = 0; i < D; ++i) {
-          const double* Hu = S + oL + i * LSZ + 1 + NX + NU + NX * NX;
-#pragma unroll
-          for (int l = 0; l < NX; ++l) g += Hu[(ii - NX) * NX + l] * Tm[(i * NX + l) * (NE + 1) + NE];
+          for (int i = 0; i < D; ++i) g += S[oL + i * LSZ + 1 + NX + (ii - NX)];
+        if (active) {
+          if (ii < NX) qh[T::oqb + ii] = g + s; else qh[T::orb + (ii - NX)] = g + s;
         }
-      if (active) {
-        if (ii < NX) { qh[T::oq + ii] = g; qh[T::oqb + ii] = gb; el[T::ogx + ii] = g_plain; }
-        else { qh[T::orr + (ii - NX)] = g; qh[T::orb + (ii - NX)] = gb; el[T::ogu + (ii - NX)] = g_plain; }
       }
     }
     // elimination block for Expand: T | t0 | gX
@@ -425,7 +452,12 @@ struct EvalQuad {
       phi += qshfl_xor(phi, m); c1 += qshfl_xor(c1, m);
       comp = dmax(comp, qshfl_xor(comp, m)); cinf = dmax(cinf, qshfl_xor(cinf, m));
     }
-    if (active && q == 0) { a.s_cinf[nb] = cinf; a.s_c1[nb] = c1; a.s_phi[nb] = phi; a.s_comp[nb] = comp; }
+    minpiv = fmin(minpiv, fmin(qshfl_xor(minpiv, 1), qshfl_xor(minpiv, 2)));
+    minpiv = fmin(minpiv, qshfl_xor(minpiv, 1));
+    if (active && q == 0) {
+      a.s_cinf[nb] = cinf; a.s_c1[nb] = c1; a.s_phi[nb] = phi; a.s_comp[nb] = comp;
+      a.nflag[sb] = (minpiv < 0.05) ? 1 : 0;  // degenerate static pivot: redo this node with partial pivoting
+    }
   }
 };
 
@@ -441,6 +473,7 @@ inline cudaError_t launch_eval_quad(const OcpArgs& a, cudaStream_t s) {
   const int grid = (int)((nodes + E::QUADS - 1) / E::QUADS);
   eval_quad_kernel<P><<<grid, 128, E::SMEM_BYTES, s>>>(a);
   launch_1d<OcpEvalTerminal<P>>(a, a.B, s);
+  launch_2d<OcpEvalFlagged<P>>(a, a.B, OcpT<P>::N, s);
   return cudaGetLastError();
 }
 

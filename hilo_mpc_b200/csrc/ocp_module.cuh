@@ -93,7 +93,7 @@ struct OcpModule {
     w += b * n1 * T::NX + b * n * T::NU + b * n * T::NC;                   // dx, du, dxc
     w += 7 * b * n1;                                                       // per-node scalars
     w += 2 * b * (size_t)n_alpha * n1;                                     // line-search table
-    w += b * ST_COUNT;                                                     // state
+    w += b * ST_COUNT + (b * n + 1) / 2 + 2;                               // state, node flags
     return w + 128;  // slack for the per-array 16-byte alignment padding
   }
 
@@ -124,6 +124,7 @@ struct OcpModule {
     a.s_ap = take(b * n1); a.s_ad = take(b * n1); a.s_dphi = take(b * n1);
     a.ls_phi = take(b * (size_t)c->n_alpha * n1); a.ls_c1 = take(b * (size_t)c->n_alpha * n1);
     a.st = take(b * ST_COUNT);
+    a.nflag = reinterpret_cast<int*>(take((b * n + 1) / 2 + 1));
     cudaStream_t s = (cudaStream_t)c->stream;
 
     static thread_local KernelTimer tm;
