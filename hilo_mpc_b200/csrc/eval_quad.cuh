@@ -42,35 +42,32 @@ struct EvalQuad {
   static constexpr bool NX4 = (NX % 4 == 0); // then the collocation point of a local row is a compile-time constant
   static constexpr int W = NC + NE + 1;      // columns of the plain system  [G_X | G_x G_u | c]
   static constexpr int WT = NC + 1;          // columns of the transposed system
+  static constexpr int NV = NX + NU + NC;    // bounded variables of a node: x_k | u_k | X_k
   static constexpr bool SUPPORTED = (P::METHOD == METHOD_COLLOCATION) && P::FIXED_X0 && !P::HAS_GADD && !P::HAS_ARR &&
                                     !P::OBJ_DISCRETE && (D <= 3) && (RPL * W <= 64) && (NC >= 4);
-  // per-quad scratch (doubles)
+  // per-quad scratch (doubles).  [oF | oPB | oT] are dead once the reduced Hessian partial sums exist and are reused
+  // as the quad-reduction area oRED.
   static constexpr int FSZ = NX + NX * NX + NX * NU;                             // f | fx | fu of one point
   static constexpr int LSZ = 1 + NX + NU + NX * NX + NU * NX + NU * NU;          // l | lx | lu | lxx | lux | luu (weighted)
-  static constexpr int oF = 0, oL = oF + D * FSZ, oPB = oL + D * LSZ, oT = oPB + 2 * W, oNU = oT + NC * (NE + 1),
-                       oGX = oNU + NC, oDGX = oGX + NC, oSGX = oDGX + NC, oXU = oSGX + NC,  // gx dgx sigx gu dgu sigu
-                       oEND = oXU + 3 * NX + 3 * NU,
-                       oRED = oEND;  // quad-reduction area: 4 lanes x (NE x (NE+1) partial Hessian/gradient + NE)
-  static constexpr int NRED = NE * (NE + 1) + NE;
-  static constexpr int SCR = ((oRED + 4 * NRED + 1) & ~1) + 3;  // odd multiple keeps neighbouring quads on different banks
+  static constexpr int NRED = NE * (NE + 1) + NE;    // partial Hessian/gradient [NE][NE+1] + multiplier-form gradient
+  static constexpr int A1 = D * FSZ + 2 * W + NC * (NE + 1), A2 = 4 * NRED;
+  static constexpr int oF = 0, oPB = oF + D * FSZ, oT = oPB + 2 * W, oRED = 0,
+                       oL = (A1 > A2 ? A1 : A2), oNU = oL + D * LSZ,
+                       oBG = oNU + NC, oBD = oBG + NV, oBS = oBD + NV,   // barrier gradient | dz | sigma of x|u|X
+                       oEND = oBS + NV;
+  static constexpr int oGX = oBG + NX + NU, oDGX = oBD + NX + NU, oSGX = oBS + NX + NU;
+  static constexpr int SCR = ((oEND + 1) & ~1) + 3;  // odd multiple keeps neighbouring quads on different banks
   static constexpr int QUADS = 32;                   // quads (nodes) per CTA, 128 threads
   static constexpr int SMEM_BYTES = QUADS * SCR * 8;
+  static constexpr bool EL_VEC2 = (NE % 2 == 0) && (T::oT % 2 == 0) && (T::TD % 2 == 0);
 
   static __device__ __forceinline__ double qshfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m, 4); }
   static __device__ __forceinline__ int qshfl_xor(int v, int m) { return __shfl_xor_sync(0xffffffffu, v, m, 4); }
 
-  // 1/x (either sign): hardware approximation + two Newton steps
-  static __device__ __forceinline__ double rcp(double x) {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    return fma(r, e, r);
-  }
-
   // Gauss-Jordan on rows R[RPL][NCOLS] (row lr of lane q is global row lr*4 + q) with the STATIC pivot order
   // "row c for column c": no search, no row selection; the owner lane and its local row are compile-time constants.
+  // The owner publishes its (unnormalised) pivot row, every lane forms its own multipliers with a Newton-refined
+  // reciprocal, and the rows are scaled by their inverse pivots once at the end.
   // The collocation matrix is dt*blkdiag(f_x) - C^T (x) I, whose unpivoted pivots are about (-3.2, -2.1, -9.0) per
   // state for the Radau-3 constants; the smallest pivot magnitude met is returned so that the caller can hand nodes
   // with a degenerate pivot (stiff dt*f_x) to the partially pivoted one-thread-per-node kernel.
@@ -78,29 +75,35 @@ struct EvalQuad {
   template <int NCOLS, int NPIV>
   static __device__ __forceinline__ double gauss_jordan(double (&R)[RPL][NCOLS], int q, double* pb) {
     double minpiv = 1e300;
+    double ipiv[RPL];
+#pragma unroll
+    for (int lr = 0; lr < RPL; ++lr) ipiv[lr] = 1.0;
 #pragma unroll
     for (int c = 0; c < NPIV; ++c) {
       const int po = c & 3, plr = c >> 2;   // owner lane / local row of the pivot row
       double* prow = pb + (c & 1) * NCOLS;   // double-buffered broadcast row
       if (q == po) {
-        const double piv = R[plr][c];
-        const double inv = rcp(piv);
-        prow[c] = fabs(piv);
 #pragma unroll
-        for (int j = c + 1; j < NCOLS; ++j) { R[plr][j] *= inv; prow[j] = R[plr][j]; }
+        for (int j = c; j < NCOLS; ++j) prow[j] = R[plr][j];
       }
       __syncwarp();
-      minpiv = fmin(minpiv, prow[c]);
+      const double piv = prow[c];
+      const double inv = rcp_nr(piv);
+      if (q == po) { ipiv[plr] = inv; minpiv = fmin(minpiv, fabs(piv)); }
 #pragma unroll
       for (int lr = 0; lr < RPL; ++lr) {
         const bool is_piv = (lr == plr) && (q == po);
-        const double f = is_piv ? 0.0 : R[lr][c];
+        const double f = is_piv ? 0.0 : R[lr][c] * inv;
 #pragma unroll
         for (int j = c + 1; j < NCOLS; ++j) R[lr][j] -= f * prow[j];
       }
     }
+#pragma unroll
+    for (int lr = 0; lr < RPL; ++lr)
+#pragma unroll
+      for (int j = NPIV; j < NCOLS; ++j) R[lr][j] *= ipiv[lr];
     __syncwarp();
-    return (minpiv == minpiv) ? minpiv : 0.0;
+    return minpiv;
   }
 
   static __device__ void run(const OcpArgs& a) {
@@ -129,17 +132,53 @@ struct EvalQuad {
     const double* xg = a.x + nb * NX;
     const double* xng = a.x + (nb + 1) * NX;
     const double* Xg = a.xc + sb * NC;
-    double x[NX], u[NU], Xq[NX];
+    const double* ug = a.u + sb * NU;
+    double u[NU], Xq[NX];
 #pragma unroll
-    for (int i = 0; i < NX; ++i) { x[i] = xg[i]; Xq[i] = Xg[(q < D ? q : 0) * NX + i]; }
+    for (int i = 0; i < NX; ++i) Xq[i] = Xg[(q < D ? q : 0) * NX + i];
 #pragma unroll
-    for (int i = 0; i < NU; ++i) u[i] = a.u[sb * NU + i];
+    for (int i = 0; i < NU; ++i) u[i] = ug[i];
 
     double phi = 0.0, comp = 0.0, c1 = 0.0, cinf = 0.0, minpiv = 1e300;
-    // ---------------------------------------------------------------- 1. derivatives at the collocation points
+    // ---------------------------------------------------------------- 1a. barrier terms, 4 variables at a time
+    {
+      BarrierSum bs;
+#pragma unroll
+      for (int it = 0; it < (NV + 3) / 4; ++it) {
+        const int e = it * 4 + q;
+        const bool ok = (it * 4 + 3 < NV) || (e < NV);
+        const double *vp, *lp, *up, *zlp, *zup;
+        bool use = ok;
+        if (e < NX) {
+          vp = xg + e; lp = a.xlb + e; up = a.xub + e; zlp = a.zlx + nb * NX + e; zup = a.zux + nb * NX + e;
+          use = use && x_free;
+        } else if (e < NX + NU) {
+          const int i = e - NX;
+          vp = ug + i; lp = a.ulb + i; up = a.uub + i; zlp = a.zlu + sb * NU + i; zup = a.zuu + sb * NU + i;
+        } else {
+          const int r = ok ? e - NX - NU : 0, j = r % NX;
+          vp = Xg + r; lp = a.xlb + j; up = a.xub + j; zlp = a.zlc + sb * NC + r; zup = a.zuc + sb * NC + r;
+        }
+        double g = 0.0, dg = 0.0, sg = 0.0;
+        if (use) {
+          const double v = *vp, lb = *lp, ub = *up, zl = *zlp, zu = *zup;
+          const BarrierTerm bt = barrier_term(v, lb, ub, zl, zu, mu);
+          g = bt.grad; dg = bt.dz; sg = bt.sigma;
+          bs.add(v, lb, ub);
+          if (has_lb(lb)) comp = dmax(comp, dabs((v - lb) * zl - mu));
+          if (has_ub(ub)) comp = dmax(comp, dabs((ub - v) * zu - mu));
+        }
+        if (ok) { S[oBG + e] = g; S[oBD + e] = dg; S[oBS + e] = sg; }
+      }
+      phi += bs.value(mu);
+    }
+    // ---------------------------------------------------------------- 1b. derivatives at the collocation points
     if (q < D) {
-      const int i = q + 1;
-      const double ti = t + dt * P::CTAU(i - 1);
+      double cb = 0.0, ctau = 0.0;
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+        if (q == i) { cb = P::CB(i + 1); ctau = P::CTAU(i); }
+      const double ti = t + dt * ctau;
       double* F = S + oF + q * FSZ;
       P::f_jac(Xq, u, sp, ti, dt, F, F + NX, F + NX + NX * NX);
       double* L = S + oL + q * LSZ;
@@ -167,7 +206,7 @@ struct EvalQuad {
 #pragma unroll
         for (int j = 0; j < NU * NU; ++j) luu[j] = 0.0;
       }
-      const double w = dt * P::CB(i);
+      const double w = dt * cb;
       phi += w * l;
       L[0] = w * l;
 #pragma unroll
@@ -181,48 +220,8 @@ struct EvalQuad {
 #pragma unroll
       for (int j = 0; j < NU * NU; ++j) L[1 + NX + NU + NX * NX + NU * NX + j] = w * luu[j];
     }
-    if (q == 3) {  // barrier terms of x_k, u_k  (layout at oXU: gx | dgx | sigx | gu | dgu | sigu)
-      double* XU = S + oXU;
-#pragma unroll
-      for (int i = 0; i < NX; ++i) {
-        double g = 0.0, dg = 0.0, sg = 0.0;
-        if (x_free) {
-          const double zl = a.zlx[nb * NX + i], zu = a.zux[nb * NX + i];
-          const BarrierTerm bt = barrier_term(x[i], a.xlb[i], a.xub[i], zl, zu, mu);
-          g = bt.grad; dg = bt.dz; sg = bt.sigma;
-          phi += barrier_value(x[i], a.xlb[i], a.xub[i], mu);
-          if (has_lb(a.xlb[i])) comp = dmax(comp, dabs((x[i] - a.xlb[i]) * zl - mu));
-          if (has_ub(a.xub[i])) comp = dmax(comp, dabs((a.xub[i] - x[i]) * zu - mu));
-        }
-        XU[i] = g; XU[NX + i] = dg; XU[2 * NX + i] = sg;
-      }
-#pragma unroll
-      for (int i = 0; i < NU; ++i) {
-        const double zl = a.zlu[sb * NU + i], zu = a.zuu[sb * NU + i];
-        const BarrierTerm bt = barrier_term(u[i], a.ulb[i], a.uub[i], zl, zu, mu);
-        phi += barrier_value(u[i], a.ulb[i], a.uub[i], mu);
-        if (has_lb(a.ulb[i])) comp = dmax(comp, dabs((u[i] - a.ulb[i]) * zl - mu));
-        if (has_ub(a.uub[i])) comp = dmax(comp, dabs((a.uub[i] - u[i]) * zu - mu));
-        XU[3 * NX + i] = bt.grad; XU[3 * NX + NU + i] = bt.dz; XU[3 * NX + 2 * NU + i] = bt.sigma;
-      }
-    }
-    // barrier terms of the collocation states, one entry per own row
-#pragma unroll
-    for (int lr = 0; lr < RPL; ++lr) {
-      const int r = lr * 4 + q;
-      if (r < NC) {
-        const int j = r % NX;
-        const double zl = a.zlc[sb * NC + r], zu = a.zuc[sb * NC + r];
-        const double Xr = Xg[r];
-        const BarrierTerm bt = barrier_term(Xr, a.xlb[j], a.xub[j], zl, zu, mu);
-        S[oGX + r] = bt.grad; S[oDGX + r] = bt.dz; S[oSGX + r] = bt.sigma;
-        phi += barrier_value(Xr, a.xlb[j], a.xub[j], mu);
-        if (has_lb(a.xlb[j])) comp = dmax(comp, dabs((Xr - a.xlb[j]) * zl - mu));
-        if (has_ub(a.xub[j])) comp = dmax(comp, dabs((a.xub[j] - Xr) * zu - mu));
-      }
-    }
     __syncwarp();
-    // gX (cost + barrier) for every collocation state: gXf[r] = w*lx_i[j] + barrier grad
+    // gX (cost + barrier) for every collocation state: gX[r] = w*lx_i[j] + barrier grad
 #pragma unroll
     for (int lr = 0; lr < RPL; ++lr) {
       const int r = lr * 4 + q;
@@ -256,10 +255,14 @@ struct EvalQuad {
         if (lr * 4 + q < NC) S[oNU + lr * 4 + q] = Rt[lr][NC];
       __syncwarp();
       if (q < D) {
+        double ctau = 0.0;
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+          if (q == i) ctau = P::CTAU(i);
         double nu[NX], hxx[NX * NX], hux[NU * NX], huu[NU * NU];
 #pragma unroll
         for (int rr = 0; rr < NX; ++rr) nu[rr] = dt * S[oNU + q * NX + rr];
-        P::f_hess(Xq, u, sp, t + dt * P::CTAU(q), dt, nu, hxx, hux, huu);
+        P::f_hess(Xq, u, sp, t + dt * ctau, dt, nu, hxx, hux, huu);
         double* L = S + oL + q * LSZ;
 #pragma unroll
         for (int j = 0; j < NX * NX; ++j) L[1 + NX + NU + j] += hxx[j];
@@ -272,46 +275,48 @@ struct EvalQuad {
     }
 
     // ---------------------------------------------------------------- 3. plain system  G_X dX + G_x dx + G_u du + c = 0
-    double R[RPL][W];
+    double Tr[RPL][NE + 1];   // own T rows (negated solution)
+    {
+      double R[RPL][W];
 #pragma unroll
-    for (int lr = 0; lr < RPL; ++lr) {
-      const int r = lr * 4 + q;  // row (i, rr)
-      const int ii = NX4 ? (lr * 4) / NX : r / NX, rr = NX4 ? ((lr * 4) % NX + q) : r % NX;  // ii = i - 1
-      const bool rv = r < NC;
+      for (int lr = 0; lr < RPL; ++lr) {
+        const int r = lr * 4 + q;  // row (i, rr)
+        const int ii = NX4 ? (lr * 4) / NX : r / NX, rr = NX4 ? ((lr * 4) % NX + q) : r % NX;  // ii = i - 1
+        const bool rv = r < NC;
 #pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        const int jp = c / NX, cc = c % NX;  // column (j, cc), jp = j - 1
-        double v = 0.0;
-        if (rv) {
-          if (jp == ii) v = dt * S[oF + ii * FSZ + NX + rr * NX + cc];
-          if (cc == rr) v -= P::CC((jp + 1) * (D + 1) + (ii + 1));
+        for (int c = 0; c < NC; ++c) {
+          const int jp = c / NX, cc = c % NX;  // column (j, cc), jp = j - 1
+          double v = 0.0;
+          if (rv) {
+            if (jp == ii) v = dt * S[oF + ii * FSZ + NX + rr * NX + cc];
+            if (cc == rr) v -= P::CC((jp + 1) * (D + 1) + (ii + 1));
+          }
+          R[lr][c] = v;
         }
-        R[lr][c] = v;
+#pragma unroll
+        for (int c = 0; c < NX; ++c) R[lr][NC + c] = (rv && c == rr) ? -P::CC(0 * (D + 1) + (ii + 1)) : 0.0;
+#pragma unroll
+        for (int c = 0; c < NU; ++c) R[lr][NC + NX + c] = rv ? dt * S[oF + ii * FSZ + NX + NX * NX + rr * NU + c] : 0.0;
+        double res = 0.0;
+        if (rv) {
+          double xp = P::CC(0 * (D + 1) + (ii + 1)) * xg[rr];
+#pragma unroll
+          for (int j = 1; j <= D; ++j) xp += P::CC(j * (D + 1) + (ii + 1)) * Xg[(j - 1) * NX + rr];
+          res = dt * S[oF + ii * FSZ + rr] - xp;
+          c1 += dabs(res); cinf = dmax(cinf, dabs(res));
+        }
+        R[lr][NC + NE] = res;
       }
+      minpiv = fmin(minpiv, gauss_jordan<W, NC>(R, q, S + oPB));
+      // own T rows stay in registers and are published to the scratch pad for the other lanes
 #pragma unroll
-      for (int c = 0; c < NX; ++c) R[lr][NC + c] = (rv && c == rr) ? -P::CC(0 * (D + 1) + (ii + 1)) : 0.0;
+      for (int lr = 0; lr < RPL; ++lr) {
+        const int r = lr * 4 + q;
 #pragma unroll
-      for (int c = 0; c < NU; ++c) R[lr][NC + NX + c] = rv ? dt * S[oF + ii * FSZ + NX + NX * NX + rr * NU + c] : 0.0;
-      double res = 0.0;
-      if (rv) {
-        double xp = P::CC(0 * (D + 1) + (ii + 1)) * xg[rr];
-#pragma unroll
-        for (int j = 1; j <= D; ++j) xp += P::CC(j * (D + 1) + (ii + 1)) * Xg[(j - 1) * NX + rr];
-        res = dt * S[oF + ii * FSZ + rr] - xp;
-        c1 += dabs(res); cinf = dmax(cinf, dabs(res));
-      }
-      R[lr][NC + NE] = res;
-    }
-    minpiv = fmin(minpiv, gauss_jordan<W, NC>(R, q, S + oPB));
-    // own T rows (negated solution) stay in registers and are published to the scratch pad for the other lanes
-    double Tr[RPL][NE + 1];
-#pragma unroll
-    for (int lr = 0; lr < RPL; ++lr) {
-      const int r = lr * 4 + q;
-#pragma unroll
-      for (int j = 0; j <= NE; ++j) {
-        Tr[lr][j] = (r < NC) ? -R[lr][NC + j] : 0.0;
-        if (r < NC) S[oT + r * (NE + 1) + j] = Tr[lr][j];
+        for (int j = 0; j <= NE; ++j) {
+          Tr[lr][j] = (r < NC) ? -R[lr][NC + j] : 0.0;
+          if (r < NC) S[oT + r * (NE + 1) + j] = Tr[lr][j];
+        }
       }
     }
     __syncwarp();
@@ -322,35 +327,59 @@ struct EvalQuad {
     double* el = a.el + sb * T::TD;
     const double* Tm = S + oT;
     // dynamics rows (lane q -> state rows q, q+4, ...)
-    for (int rr = q; rr < NX; rr += 4) {
-      double xf = P::CD(0) * xg[rr], bsum = 0.0;
 #pragma unroll
-      for (int i = 1; i <= D; ++i) { xf += P::CD(i) * Xg[(i - 1) * NX + rr]; bsum += P::CD(i) * Tm[((i - 1) * NX + rr) * (NE + 1) + NE]; }
-      const double res = xf - xng[rr];
-      c1 += dabs(res); cinf = dmax(cinf, dabs(res));
-      if (active) {
+    for (int it = 0; it < (NX + 3) / 4; ++it) {
+      const int rr = it * 4 + q;
+      if (rr < NX) {
+        double xf = P::CD(0) * xg[rr], bsum = 0.0;
 #pragma unroll
-        for (int c = 0; c < NX; ++c) {
-          double s = (rr == c) ? P::CD(0) : 0.0;
+        for (int i = 1; i <= D; ++i) { xf += P::CD(i) * Xg[(i - 1) * NX + rr]; bsum += P::CD(i) * Tm[((i - 1) * NX + rr) * (NE + 1) + NE]; }
+        const double res = xf - xng[rr];
+        c1 += dabs(res); cinf = dmax(cinf, dabs(res));
+        if (active) {
 #pragma unroll
-          for (int i = 1; i <= D; ++i) s += P::CD(i) * Tm[((i - 1) * NX + rr) * (NE + 1) + c];
-          qa[T::oA + rr * NX + c] = s;
+          for (int c = 0; c < NX; ++c) {
+            double s = (rr == c) ? P::CD(0) : 0.0;
+#pragma unroll
+            for (int i = 1; i <= D; ++i) s += P::CD(i) * Tm[((i - 1) * NX + rr) * (NE + 1) + c];
+            qa[T::oA + rr * NX + c] = s;
+          }
+#pragma unroll
+          for (int c = 0; c < NU; ++c) {
+            double s = 0.0;
+#pragma unroll
+            for (int i = 1; i <= D; ++i) s += P::CD(i) * Tm[((i - 1) * NX + rr) * (NE + 1) + NX + c];
+            qa[T::oB + rr * NU + c] = s;
+          }
+          qa[T::ob + rr] = bsum + res;
         }
+      }
+    }
+    // elimination block for Expand, own rows straight from the registers: T | t0 | gX
+    if (active) {
 #pragma unroll
-        for (int c = 0; c < NU; ++c) {
-          double s = 0.0;
+      for (int lr = 0; lr < RPL; ++lr) {
+        const int r = lr * 4 + q;
+        if (r < NC) {
+          if constexpr (EL_VEC2) {
+            double2* dst = reinterpret_cast<double2*>(el + T::oT + r * NE);
 #pragma unroll
-          for (int i = 1; i <= D; ++i) s += P::CD(i) * Tm[((i - 1) * NX + rr) * (NE + 1) + NX + c];
-          qa[T::oB + rr * NU + c] = s;
+            for (int j = 0; j < NE / 2; ++j) dst[j] = make_double2(Tr[lr][2 * j], Tr[lr][2 * j + 1]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < NE; ++j) el[T::oT + r * NE + j] = Tr[lr][j];
+          }
+          el[T::ot0 + r] = Tr[lr][NE];
+          el[T::ogX + r] = S[oGX + r];
         }
-        qa[T::ob + rr] = bsum + res;
       }
     }
     // Partial sums over the OWN rows r = (i, l), all operands in registers:
     //   Pq[ii][jj] += T[r][ii] * HT[r][jj]        HT[r][:] = (H_i + diag sigma)[l][:] T_i[:][:]  (+ gX[r] in column NE)
     //   Pq[NX+a][jj] += Hu_i[a][l] * T[r][jj]     (jj = 0..NE; column NE is the gradient)
-    //   Pq[ii][NX+a] += Hu_i[a][l] * T[r][ii]
+    //   Pq[NX+b][NX+a] += Hu_i[a][l] * T[r][NX+b]
     //   gb[ii]      += T[r][ii] * (gX + dz)[r]    multiplier-form gradient
+    // The block Pq[ii < NX][NX <= jj < NE] (S transposed) is never needed and not formed.
     double Pq[NE][NE + 1], gbp[NE];
 #pragma unroll
     for (int ii = 0; ii < NE; ++ii) {
@@ -365,9 +394,10 @@ struct EvalQuad {
         const int ii0 = NX4 ? (lr * 4) / NX : r / NX, l = NX4 ? ((lr * 4) % NX + q) : r % NX;
         const double* Hx = S + oL + ii0 * LSZ + 1 + NX + NU + l * NX;
         const double* Hu = S + oL + ii0 * LSZ + 1 + NX + NU + NX * NX;
+        const double gXr = S[oGX + r];
         double HTr[NE + 1];
 #pragma unroll
-        for (int c = 0; c <= NE; ++c) HTr[c] = (c == NE) ? S[oGX + r] : 0.0;
+        for (int c = 0; c <= NE; ++c) HTr[c] = (c == NE) ? gXr : 0.0;
 #pragma unroll
         for (int l2 = 0; l2 < NX; ++l2) {
           double hv = Hx[l2];
@@ -376,12 +406,13 @@ struct EvalQuad {
 #pragma unroll
           for (int c = 0; c <= NE; ++c) HTr[c] += hv * T2[c];
         }
-        const double gbx = S[oGX + r] + S[oDGX + r];
+        const double gbx = gXr + S[oDGX + r];
 #pragma unroll
         for (int ii = 0; ii < NE; ++ii) {
           gbp[ii] += Tr[lr][ii] * gbx;
 #pragma unroll
-          for (int jj = 0; jj <= NE; ++jj) Pq[ii][jj] += Tr[lr][ii] * HTr[jj];
+          for (int jj = 0; jj <= NE; ++jj)
+            if (!(ii < NX && jj >= NX && jj < NE)) Pq[ii][jj] += Tr[lr][ii] * HTr[jj];
         }
 #pragma unroll
         for (int aa = 0; aa < NU; ++aa) {
@@ -389,71 +420,74 @@ struct EvalQuad {
 #pragma unroll
           for (int jj = 0; jj <= NE; ++jj) Pq[NX + aa][jj] += hu * Tr[lr][jj];
 #pragma unroll
-          for (int ii = 0; ii < NE; ++ii) Pq[ii][NX + aa] += hu * Tr[lr][ii];
+          for (int bb = 0; bb < NU; ++bb) Pq[NX + bb][NX + aa] += hu * Tr[lr][NX + bb];
         }
       }
     }
-    // quad reduction through the scratch pad, then every lane finalises a share of the entries
+    __syncwarp();   // every lane is done with F / PB / T: the area becomes the reduction buffer
     {
       double* red = S + oRED + q * NRED;
 #pragma unroll
       for (int ii = 0; ii < NE; ++ii) {
 #pragma unroll
-        for (int jj = 0; jj <= NE; ++jj) red[ii * (NE + 1) + jj] = Pq[ii][jj];
+        for (int jj = 0; jj <= NE; ++jj)
+          if (!(ii < NX && jj >= NX && jj < NE)) red[ii * (NE + 1) + jj] = Pq[ii][jj];
         red[NE * (NE + 1) + ii] = gbp[ii];
       }
     }
     __syncwarp();
-    const double* XU = S + oXU;
-    for (int e = q; e < NRED; e += 4) {
-      const double s = S[oRED + e] + S[oRED + NRED + e] + S[oRED + 2 * NRED + e] + S[oRED + 3 * NRED + e];
-      if (e < NE * (NE + 1)) {
-        const int ii = e / (NE + 1), jj = e % (NE + 1);
-        if (jj < NE) {  // Hessian entry
-          double v = s;
-          if (ii >= NX && jj >= NX)
+    // every lane finalises whole rows (lane q -> rows q, q+4, ...): the column index is static
 #pragma unroll
-            for (int i = 0; i < D; ++i) v += S[oL + i * LSZ + 1 + NX + NU + NX * NX + NU * NX + (ii - NX) * NU + (jj - NX)];
-          if (ii == jj) v += (ii < NX) ? XU[2 * NX + ii] : XU[3 * NX + 2 * NU + (ii - NX)];
+    for (int it = 0; it < (NE + 3) / 4; ++it) {
+      const int ii = it * 4 + q;
+      if (ii < NE) {
+        const double* r0 = S + oRED + ii * (NE + 1);
+        const double* rg = S + oRED + NE * (NE + 1) + ii;
+        const double sg = rg[0] + rg[NRED] + rg[2 * NRED] + rg[3 * NRED];
+        const double sq = r0[NE] + r0[NRED + NE] + r0[2 * NRED + NE] + r0[3 * NRED + NE];
+        const bool xrow = NX4 ? (it * 4 < NX) : (ii < NX);
+        if (xrow) {
+          const double g = S[oBG + ii];
           if (active) {
-            if (ii < NX && jj < NX) qh[T::oQ + ii * NX + jj] = v;
-            else if (ii >= NX && jj < NX) qh[T::oS + (ii - NX) * NX + jj] = v;
-            else if (ii >= NX && jj >= NX) qh[T::oR + (ii - NX) * NU + (jj - NX)] = v;
-          }
-        } else {        // Newton-form gradient q / r
-          double g = (ii < NX) ? XU[ii] : XU[3 * NX + (ii - NX)];
-          if (ii >= NX)
 #pragma unroll
-            for (int i = 0; i < D; ++i) g += S[oL + i * LSZ + 1 + NX + (ii - NX)];
+            for (int jj = 0; jj < NX; ++jj) {
+              double v = r0[jj] + r0[NRED + jj] + r0[2 * NRED + jj] + r0[3 * NRED + jj];
+              if (jj == ii) v += S[oBS + ii];
+              qh[T::oQ + ii * NX + jj] = v;
+            }
+            qh[T::oq + ii] = g + sq; el[T::ogx + ii] = g;
+            qh[T::oqb + ii] = g + S[oBD + ii] + sg;
+          }
+        } else {
+          const int aa = ii - NX;
+          double g = S[oBG + ii];
+#pragma unroll
+          for (int i = 0; i < D; ++i) g += S[oL + i * LSZ + 1 + NX + aa];
           if (active) {
-            if (ii < NX) { qh[T::oq + ii] = g + s; el[T::ogx + ii] = g; }
-            else { qh[T::orr + (ii - NX)] = g + s; el[T::ogu + (ii - NX)] = g; }
-          }
-        }
-      } else {          // multiplier-form gradient qbar / rbar
-        const int ii = e - NE * (NE + 1);
-        double g = (ii < NX) ? (XU[ii] + XU[NX + ii]) : (XU[3 * NX + (ii - NX)] + XU[3 * NX + NU + (ii - NX)]);
-        if (ii >= NX)
 #pragma unroll
-          for (int i = 0; i < D; ++i) g += S[oL + i * LSZ + 1 + NX + (ii - NX)];
-        if (active) {
-          if (ii < NX) qh[T::oqb + ii] = g + s; else qh[T::orb + (ii - NX)] = g + s;
+            for (int jj = 0; jj < NX; ++jj)
+              qh[T::oS + aa * NX + jj] = r0[jj] + r0[NRED + jj] + r0[2 * NRED + jj] + r0[3 * NRED + jj];
+#pragma unroll
+            for (int bb = 0; bb < NU; ++bb) {
+              double v = r0[NX + bb] + r0[NRED + NX + bb] + r0[2 * NRED + NX + bb] + r0[3 * NRED + NX + bb];
+#pragma unroll
+              for (int i = 0; i < D; ++i) v += S[oL + i * LSZ + 1 + NX + NU + NX * NX + NU * NX + aa * NU + bb];
+              if (bb == aa) v += S[oBS + ii];
+              qh[T::oR + aa * NU + bb] = v;
+            }
+            qh[T::orr + aa] = g + sq; el[T::ogu + aa] = g;
+            qh[T::orb + aa] = g + S[oBD + ii] + sg;
+          }
         }
       }
-    }
-    // elimination block for Expand: T | t0 | gX
-    if (active) {
-      for (int e = q; e < NC * NE; e += 4) el[T::oT + e] = Tm[(e / NE) * (NE + 1) + (e % NE)];
-      for (int r = q; r < NC; r += 4) { el[T::ot0 + r] = Tm[r * (NE + 1) + NE]; el[T::ogX + r] = S[oGX + r]; }
     }
     // ---------------------------------------------------------------- 5. per-node scalars
 #pragma unroll
     for (int m = 1; m < 4; m <<= 1) {
       phi += qshfl_xor(phi, m); c1 += qshfl_xor(c1, m);
       comp = dmax(comp, qshfl_xor(comp, m)); cinf = dmax(cinf, qshfl_xor(cinf, m));
+      minpiv = fmin(minpiv, qshfl_xor(minpiv, m));
     }
-    minpiv = fmin(minpiv, fmin(qshfl_xor(minpiv, 1), qshfl_xor(minpiv, 2)));
-    minpiv = fmin(minpiv, qshfl_xor(minpiv, 1));
     if (active && q == 0) {
       a.s_cinf[nb] = cinf; a.s_c1[nb] = c1; a.s_phi[nb] = phi; a.s_comp[nb] = comp;
       a.nflag[sb] = (minpiv < 0.05) ? 1 : 0;  // degenerate static pivot: redo this node with partial pivoting
