@@ -29,7 +29,7 @@ if ROOT not in sys.path:
 N_HORIZON = 50
 BATCH_PER_GPU = 4096
 NX, NU = 4, 2
-KERNEL_NAMES = "init,eval,riccati,expand,prep,trial,decide,apply,commit,count".split(',')
+KERNEL_NAMES = "init,eval,riccati,expand,prep,trial,decide,apply,commit,count,step".split(',')
 DIST_SCALE = np.array([.02, .02, .5, .5])  # closed-loop disturbance added to the predicted next state
 
 
@@ -255,13 +255,22 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
+    outs = []
     for k in range(args.steps):
-        x_cur, out = step_device(args.warmup + k, x_cur, True)
-        iters_hist.append(out['iters'].max().item())
+        x_cur, out = step_device(args.warmup + k, x_cur, False)
+        outs.append(out['iters'].max())          # stays on the device: no host sync inside the timed region
     ev1.record()
     barrier()
     ms_total = ev0.elapsed_time(ev1)
     launches = getattr(eng, 'total_kernel_launches', 0) - launches0
+    iters_hist = [int(o.item()) for o in outs]
+    # per-kernel pass: the same closed loop continued for K more steps with a CUDA-event pair around every launch (on
+    # the launching stream, inside the C-ABI call).  Kept out of the `value` region because ~330 event records and
+    # elapsed-time reads per step cost about 3 ms of device idle time per step.
+    x_k = x_cur
+    for k in range(args.steps):
+        x_k, _ = step_device(args.warmup + k, x_k, True)
+    torch.cuda.synchronize()
     status_ok = float((out['status'] == 1).double().mean().item())
     iters_mean = float(out['iters'].double().mean().item())
     clocks = sampler.stop() if rank == 0 else None
@@ -272,21 +281,28 @@ def main():
     value = world * B / (ms_per_step * 1e-3)
 
     # ------------------------------------------------------------------ end-to-end arm through the public API (host buffers)
+    # The same closed loop as above restarted from the same initial states and disturbance sequence, so that both arms
+    # see the same solves (the loop settles towards the set point and later steps need fewer iterations).
     x_host = torch.empty(B, NX, dtype=torch.float64).pin_memory()
     u_host = torch.empty(B, NU, dtype=torch.float64).pin_memory()
-    x_host.copy_(x_cur.cpu())
-    noise_h = noise[n_total:2 * n_total + 1].cpu()
-    for k in range(2):
-        u = nmpc.optimize(x_host.to(dev, non_blocking=True))
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for k in range(args.steps):
+    x_host.copy_(x0.cpu())
+    noise_h = noise[:n_total].cpu()
+    eng.reset_guess()
+
+    def step_e2e(k):
         u = nmpc.optimize(x_host.to(dev, non_blocking=True))  # H2D of this step's measured states
         u_host.copy_(u, non_blocking=False)                    # D2H of the applied inputs
         x_pred, _, _ = nmpc.return_prediction()
         x_host.copy_(x_pred[:, 1, :NX])                        # plant model: predicted next state (+ disturbance)
         x_host.add_(noise_h[k])
+
+    for k in range(args.warmup):
+        step_e2e(k)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(args.steps):
+        step_e2e(args.warmup + k)
     e1.record()
     barrier()
     t_e = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -319,6 +335,8 @@ def main():
     achieved = alg[roof_name] / avg_s / 1e9
     roofline = {'kernel': roof_name, 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                 'frac': achieved / peak, 'traffic': None, 'peak_kind': peak_kind,
+                'timing': 'CUDA event pair around every launch on the launching stream; pass of K closed-loop steps '
+                          'right after the value region (events inside it would add ~3 ms/step of idle time)',
                 'algorithmic_bytes_per_launch': alg[roof_name]}
     ric = per_kernel.get('riccati')
     if ric:

@@ -4,6 +4,7 @@
 #include "ocp_kernels.cuh"
 #include "riccati.cuh"
 #include "eval_quad.cuh"
+#include "step_fused.cuh"
 #include "../../include/hilo_b200.h"
 
 namespace hb {
@@ -22,7 +23,7 @@ struct OcpCount {
 
 // Per-kernel device timing with CUDA events recorded on the launching stream (hb_ocp_call.kernel_ms != NULL).
 // Events are only read back at the points where the driver synchronises anyway (convergence polls).
-enum { K_INIT = 0, K_EVAL, K_RICCATI, K_EXPAND, K_PREP, K_TRIAL, K_DECIDE, K_APPLY, K_COMMIT, K_COUNT_ACTIVE, K_NUM };
+enum { K_INIT = 0, K_EVAL, K_RICCATI, K_EXPAND, K_PREP, K_TRIAL, K_DECIDE, K_APPLY, K_COMMIT, K_COUNT_ACTIVE, K_STEP, K_NUM };
 
 struct KernelTimer {
   bool on = false;
@@ -165,18 +166,32 @@ struct OcpModule {
       launch_1d<OcpRiccati<P>>(a, a.B, s);
 #endif
       tm.end();
-      tm.begin(K_EXPAND); launch_2d<OcpExpand<P>>(a, a.B, T::N + 1, s); tm.end();
-      tm.begin(K_PREP); launch_1d<OcpPrep<P>>(a, a.B, s); tm.end();
-      a.ls_phase = 0;
-      tm.begin(K_TRIAL); launch_3d<OcpTrial<P>>(a, a.B, T::N + 1, 1, s); tm.end();
-      tm.begin(K_DECIDE); launch_1d<OcpDecide<P>>(a, a.B, s); tm.end();
-      if (a.n_alpha > 1) {
-        a.ls_phase = 1;
-        tm.begin(K_TRIAL); launch_3d<OcpTrial<P>>(a, a.B, T::N + 1, a.n_alpha - 1, s); tm.end();
-        tm.begin(K_DECIDE); launch_1d<OcpDecide<P>>(a, a.B, s); tm.end();
+      bool fused = false;
+#if HB_DEVICE_BUILD
+      if constexpr (StepFused<P>::SUPPORTED) {
+        if (c->step_variant != 0) {
+          tm.begin(K_STEP);
+          cudaError_t e = launch_step_fused<P>(a, s);
+          tm.end();
+          if (e != cudaSuccess) return (int)e;
+          fused = true;
+        }
       }
-      tm.begin(K_APPLY); launch_2d<OcpApply<P>>(a, a.B, T::N + 1, s); tm.end();
-      tm.begin(K_COMMIT); launch_1d<OcpCommit<P>>(a, a.B, s); tm.end();
+#endif
+      if (!fused) {
+        tm.begin(K_EXPAND); launch_2d<OcpExpand<P>>(a, a.B, T::N + 1, s); tm.end();
+        tm.begin(K_PREP); launch_1d<OcpPrep<P>>(a, a.B, s); tm.end();
+        a.ls_phase = 0;
+        tm.begin(K_TRIAL); launch_3d<OcpTrial<P>>(a, a.B, T::N + 1, 1, s); tm.end();
+        tm.begin(K_DECIDE); launch_1d<OcpDecide<P>>(a, a.B, s); tm.end();
+        if (a.n_alpha > 1) {
+          a.ls_phase = 1;
+          tm.begin(K_TRIAL); launch_3d<OcpTrial<P>>(a, a.B, T::N + 1, a.n_alpha - 1, s); tm.end();
+          tm.begin(K_DECIDE); launch_1d<OcpDecide<P>>(a, a.B, s); tm.end();
+        }
+        tm.begin(K_APPLY); launch_2d<OcpApply<P>>(a, a.B, T::N + 1, s); tm.end();
+        tm.begin(K_COMMIT); launch_1d<OcpCommit<P>>(a, a.B, s); tm.end();
+      }
       ++launched;
       if ((it + 1) % check_every == 0 || it == c->max_iter) {
         int active = 0;

@@ -95,7 +95,7 @@ class OcpEngine:
               acc_tol: float = 1e-6, max_iter: int = 3000, n_alpha: int = 8, mu_init: float = .1,
               mu_min: Optional[float] = None, check_every: int = 4, stream=None, kernel_ms=None, kernel_count=None,
               riccati_variant: int = 1, warm_start: int = 0, mu_init_warm: float = 1e-4,
-              eval_variant: int = 1):
+              eval_variant: int = 1, step_variant: int = 1):
         """``x0``: CUDA tensor ``[B, nx]`` (scaled). Optional ``sp [B|1, N, nsp]``, ``tp``, ``uold``, ``ap`` tensors.
         Returns dict of device tensors: x [B,N+1,nx], u [B,N,nu], xc, lam, status, iters, stats."""
         torch = _lib.require_cuda()
@@ -137,7 +137,7 @@ class OcpEngine:
             kernel_count=None if kernel_count is None else kernel_count.ctypes.data_as(C.POINTER(C.c_longlong)),
             riccati_variant=riccati_variant,
             warm_start=int(bool(warm_start) and getattr(self, '_solved_once', False) and self._solved_batch == B),
-            mu_init_warm=mu_init_warm, eval_variant=eval_variant)
+            mu_init_warm=mu_init_warm, eval_variant=eval_variant, step_variant=step_variant)
         _lib.check(lib.hb_ocp_solve(self._handle, C.byref(call)), 'hb_ocp_solve')
         self.last_launched = launched.value
         self._solved_once, self._solved_batch = True, B

@@ -87,11 +87,13 @@ typedef struct hb_ocp_call {
   double mu_init_warm;
   int eval_variant;         /* 1: 4-lanes-per-node register-resident evaluation kernel where supported (default),
                                0: one-thread-per-node kernel                                                       */
+  int step_variant;         /* 1: expand / line search / apply of one iteration fused into one kernel, one CTA per
+                               instance (default), 0: separate kernels                                             */
 } hb_ocp_call;
 
 /* kernel indices of kernel_ms / kernel_count */
-#define HB_OCP_KERNELS 10
-#define HB_OCP_KERNEL_NAMES "init,eval,riccati,expand,prep,trial,decide,apply,commit,count"
+#define HB_OCP_KERNELS 11
+#define HB_OCP_KERNEL_NAMES "init,eval,riccati,expand,prep,trial,decide,apply,commit,count,step"
 
 typedef struct hb_ocp* hb_ocp_t;
 int hb_ocp_open(const char* module_path, hb_ocp_t* out);
