@@ -224,8 +224,14 @@ HB_HD double warm_z(double z, double mu) {
 
 // Largest alpha in (0, 1] with  s + alpha*ds >= (1 - tau) * s  for a positive quantity s.
 HB_HD double frac_to_boundary(double s, double ds, double tau, double amax) {
-  if (ds < 0.0) { const double a = -tau * s / ds; if (a < amax) amax = a; }
+  if (ds < 0.0) { const double a = -tau * s * rcp_nr(ds); if (a < amax) amax = a; }
   return amax;
+}
+
+// Newton step of a bound multiplier z whose slack s changes by ds:  dz = mu/s - z - (z/s) ds
+HB_HD double dual_step(double z, double s, double ds, double mu) {
+  const double is = rcp_nr(s);
+  return mu * is - z - z * is * ds;
 }
 
 }  // namespace hb

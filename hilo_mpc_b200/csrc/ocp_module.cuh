@@ -5,6 +5,7 @@
 #include "riccati.cuh"
 #include "eval_quad.cuh"
 #include "step_fused.cuh"
+#include "step_quad.cuh"
 #include "../../include/hilo_b200.h"
 
 namespace hb {
@@ -168,8 +169,17 @@ struct OcpModule {
       tm.end();
       bool fused = false;
 #if HB_DEVICE_BUILD
+      if constexpr (StepQuad<P>::SUPPORTED) {
+        if (c->step_variant >= 2) {
+          tm.begin(K_STEP);
+          cudaError_t e = launch_step_quad<P>(a, s);
+          tm.end();
+          if (e != cudaSuccess) return (int)e;
+          fused = true;
+        }
+      }
       if constexpr (StepFused<P>::SUPPORTED) {
-        if (c->step_variant != 0) {
+        if (c->step_variant != 0 && !fused) {
           tm.begin(K_STEP);
           cudaError_t e = launch_step_fused<P>(a, s);
           tm.end();

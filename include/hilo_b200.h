@@ -87,8 +87,9 @@ typedef struct hb_ocp_call {
   double mu_init_warm;
   int eval_variant;         /* 1: 4-lanes-per-node register-resident evaluation kernel where supported (default),
                                0: one-thread-per-node kernel                                                       */
-  int step_variant;         /* 1: expand / line search / apply of one iteration fused into one kernel, one CTA per
-                               instance (default), 0: separate kernels                                             */
+  int step_variant;         /* expand / line search / apply of one iteration: 2: one kernel, one CTA per instance,
+                               4 lanes per node, iterate register-resident (default where supported); 1: one kernel,
+                               one thread per node; 0: separate kernels                                            */
 } hb_ocp_call;
 
 /* kernel indices of kernel_ms / kernel_count */

@@ -153,15 +153,16 @@ def test_quad_eval_kernel_matches_thread_per_node_kernel(cuda_device):
         assert (res[0]['u'] - res[1]['u']).abs().max().item() < 1e-7
 
 
-def test_fused_step_kernel_matches_separate_kernels(cuda_device):
-    """Expand/Prep/Trial/Decide/Apply/Commit as one kernel (one CTA per instance) run the same device functions in the
-    same order as the separate launches: complete solves must agree bit for bit, cold and with rejected full steps
-    (the wide initial-state box makes the filter backtrack for part of the batch)."""
+def test_fused_step_kernels_match_separate_kernels(cuda_device):
+    """Expand/Prep/Trial/Decide/Apply/Commit as one kernel, one CTA per instance.  Variant 1 (one thread per node) runs
+    the same device functions in the same order as the separate launches: bit-identical solves.  Variant 2 (4 lanes per
+    node, register-resident iterate) sums in a different order: same iteration counts up to one, same solution to
+    rounding level.  The wide initial-state box makes the filter backtrack for part of the batch."""
     import torch
     from hilo_mpc_b200.examples import cstr_initial_states, cstr_nmpc
     x0 = torch.tensor(cstr_initial_states(1000, seed=5), device=cuda_device)
     res = []
-    for variant in (0, 1):
+    for variant in (0, 1, 2):
         nmpc = cstr_nmpc(N=50, solver_options={'b200.step_variant': variant})
         nmpc.optimize(x0)
         out = nmpc._last
@@ -170,3 +171,6 @@ def test_fused_step_kernel_matches_separate_kernels(cuda_device):
     assert torch.equal(res[0]['iters'], res[1]['iters'])
     assert torch.equal(res[0]['x'], res[1]['x'])
     assert torch.equal(res[0]['u'], res[1]['u'])
+    assert (res[0]['iters'] - res[2]['iters']).abs().max().item() <= 1
+    assert (res[0]['x'] - res[2]['x']).abs().max().item() < 1e-8
+    assert (res[0]['u'] - res[2]['u']).abs().max().item() < 1e-7
