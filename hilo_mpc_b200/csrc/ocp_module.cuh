@@ -10,15 +10,16 @@
 
 namespace hb {
 
-struct OcpCount {
+struct OcpCount {  // (b): poll[0] = instances still active, poll[1] = largest iteration count of the batch
   static HB_HD void run(const OcpArgs& a, int b) {
-    if (a.st[(long long)b * ST_COUNT + ST_ACTIVE] != 0.0) {
+    const int it = a.iters[b];
 #if HB_DEVICE_BUILD && defined(__CUDA_ARCH__)
-      atomicAdd(a.iters + a.B, 1);  // slot B of the iters array is the active counter
+    if (a.st[(long long)b * ST_COUNT + ST_ACTIVE] != 0.0) atomicAdd(a.poll, 1);
+    if (it > a.poll[1]) atomicMax(a.poll + 1, it);
 #else
-      a.iters[a.B] += 1;
+    if (a.st[(long long)b * ST_COUNT + ST_ACTIVE] != 0.0) a.poll[0] += 1;
+    if (it > a.poll[1]) a.poll[1] = it;
 #endif
-    }
   }
 };
 
@@ -95,7 +96,7 @@ struct OcpModule {
     w += b * n1 * T::NX + b * n * T::NU + b * n * T::NC;                   // dx, du, dxc
     w += 7 * b * n1;                                                       // per-node scalars
     w += 2 * b * (size_t)n_alpha * n1;                                     // line-search table
-    w += b * ST_COUNT + (b * n + 1) / 2 + 2;                               // state, node flags
+    w += b * ST_COUNT + (b * n + 1) / 2 + 2 + 2;                           // state, node flags, poll counters
     return w + 128;  // slack for the per-array 16-byte alignment padding
   }
 
@@ -127,13 +128,18 @@ struct OcpModule {
     a.ls_phi = take(b * (size_t)c->n_alpha * n1); a.ls_c1 = take(b * (size_t)c->n_alpha * n1);
     a.st = take(b * ST_COUNT);
     a.nflag = reinterpret_cast<int*>(take((b * n + 1) / 2 + 1));
+    a.poll = reinterpret_cast<int*>(take(2));
     cudaStream_t s = (cudaStream_t)c->stream;
 
     static thread_local KernelTimer tm;
     tm.on = c->kernel_ms != nullptr; tm.s = s; tm.ms = c->kernel_ms; tm.count = c->kernel_count; tm.launches = 0;
     tm.begin(K_INIT); launch_2d<OcpInit<P>>(a, a.B, T::N + 1, s); tm.end();
+    // Host polling schedule: every check_every iterations, or - with a hint from the previous solve of the same closed
+    // loop (first_check = iterations that one needed) - once after that many and then after every further iteration.
     const int check_every = c->check_every > 0 ? c->check_every : 4;
-    int launched = 0;
+    const int hint = (c->first_check > 0 && c->first_check <= 64) ? c->first_check : 0;
+    int next_check = hint > 0 ? hint : check_every;
+    int launched = 0, needed = 0, single_polls = 0;
     for (int it = 0; it <= c->max_iter; ++it) {
       tm.begin(K_EVAL);
 #if HB_DEVICE_BUILD
@@ -203,21 +209,24 @@ struct OcpModule {
         tm.begin(K_COMMIT); launch_1d<OcpCommit<P>>(a, a.B, s); tm.end();
       }
       ++launched;
-      if ((it + 1) % check_every == 0 || it == c->max_iter) {
-        int active = 0;
+      if (launched == next_check || it == c->max_iter) {
+        int poll[2] = {0, 0};
 #if HB_DEVICE_BUILD
-        cudaMemsetAsync(a.iters + a.B, 0, sizeof(int), s);
+        cudaMemsetAsync(a.poll, 0, 2 * sizeof(int), s);
         tm.begin(K_COUNT_ACTIVE); launch_1d<OcpCount>(a, a.B, s); tm.end();
-        cudaMemcpyAsync(&active, a.iters + a.B, sizeof(int), cudaMemcpyDeviceToHost, s);
+        cudaMemcpyAsync(poll, a.poll, 2 * sizeof(int), cudaMemcpyDeviceToHost, s);
         cudaError_t e = cudaStreamSynchronize(s);
         if (e != cudaSuccess) return (int)e;
         tm.flush(false);
 #else
-        a.iters[a.B] = 0;
+        a.poll[0] = 0; a.poll[1] = 0;
         launch_1d<OcpCount>(a, a.B, s);
-        active = a.iters[a.B];
+        poll[0] = a.poll[0]; poll[1] = a.poll[1];
 #endif
-        if (active == 0) break;
+        needed = poll[1] + 1;  // the iteration after the last step is the one that detects convergence
+        if (poll[0] == 0) break;
+        if (hint > 0 && single_polls < 3) { next_check = launched + 1; ++single_polls; }
+        else next_check = launched + check_every;
       }
     }
     if (c->stats != nullptr) {
@@ -228,6 +237,7 @@ struct OcpModule {
 #endif
     }
     if (c->n_iterations_launched != nullptr) *c->n_iterations_launched = launched;
+    if (c->n_iterations_needed != nullptr) *c->n_iterations_needed = needed;
     if (c->n_kernel_launches != nullptr) *c->n_kernel_launches = tm.launches;
 #if HB_DEVICE_BUILD
     cudaError_t e = cudaGetLastError();

@@ -95,7 +95,7 @@ class OcpEngine:
               acc_tol: float = 1e-6, max_iter: int = 3000, n_alpha: int = 8, mu_init: float = .1,
               mu_min: Optional[float] = None, check_every: int = 4, stream=None, kernel_ms=None, kernel_count=None,
               riccati_variant: int = 1, warm_start: int = 0, mu_init_warm: float = 1e-4,
-              eval_variant: int = 1, step_variant: int = 2):
+              eval_variant: int = 1, step_variant: int = 2, adaptive_poll: bool = True):
         """``x0``: CUDA tensor ``[B, nx]`` (scaled). Optional ``sp [B|1, N, nsp]``, ``tp``, ``uold``, ``ap`` tensors.
         Returns dict of device tensors: x [B,N+1,nx], u [B,N,nu], xc, lam, status, iters, stats."""
         torch = _lib.require_cuda()
@@ -121,6 +121,8 @@ class OcpEngine:
         uov, uos = opt(uold, d.nuold)
         apv, aps = opt(ap, d.nap)
         launched = C.c_int(0)
+        needed = C.c_int(0)
+        warm = int(bool(warm_start) and getattr(self, '_solved_once', False) and self._solved_batch == B)
         n_launch = C.c_longlong(0)
         st = torch.cuda.current_stream(self._device) if stream is None else stream
         call = _lib.OcpCall(
@@ -136,10 +138,12 @@ class OcpEngine:
             kernel_ms=None if kernel_ms is None else kernel_ms.ctypes.data_as(_lib._DP),
             kernel_count=None if kernel_count is None else kernel_count.ctypes.data_as(C.POINTER(C.c_longlong)),
             riccati_variant=riccati_variant,
-            warm_start=int(bool(warm_start) and getattr(self, '_solved_once', False) and self._solved_batch == B),
+            warm_start=warm, first_check=(getattr(self, 'last_needed', 0) if (warm and adaptive_poll) else 0),
+            n_iterations_needed=C.pointer(needed),
             mu_init_warm=mu_init_warm, eval_variant=eval_variant, step_variant=step_variant)
         _lib.check(lib.hb_ocp_solve(self._handle, C.byref(call)), 'hb_ocp_solve')
         self.last_launched = launched.value
+        self.last_needed = needed.value
         self._solved_once, self._solved_batch = True, B
         self.last_kernel_launches = n_launch.value
         self.total_kernel_launches = getattr(self, 'total_kernel_launches', 0) + n_launch.value

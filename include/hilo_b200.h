@@ -87,6 +87,9 @@ typedef struct hb_ocp_call {
   double mu_init_warm;
   int eval_variant;         /* 1: 4-lanes-per-node register-resident evaluation kernel where supported (default),
                                0: one-thread-per-node kernel                                                       */
+  int first_check;          /* > 0: first host poll after this many iterations, then after every further one (pass
+                               *n_iterations_needed of the previous solve of the same closed loop); 0: every check_every */
+  int* n_iterations_needed; /* host out or NULL: largest per-instance iteration count + 1                          */
   int step_variant;         /* expand / line search / apply of one iteration: 2: one kernel, one CTA per instance,
                                4 lanes per node, iterate register-resident (default where supported); 1: one kernel,
                                one thread per node; 0: separate kernels                                            */

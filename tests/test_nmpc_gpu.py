@@ -119,8 +119,12 @@ def test_warm_start_mode_reaches_the_same_solution_in_fewer_iterations(cuda_devi
     noise = (torch.rand(4, 512, 4, generator=gen, device=cuda_device, dtype=torch.float64) * 2 - 1) * \
         torch.tensor([.02, .02, .5, .5], dtype=torch.float64, device=cuda_device)
     runs = {}
-    for warm in (0, 1):
-        nmpc = cstr_nmpc(N=50, solver_options={'b200.warm_start': warm, 'ipopt.tol': 1e-9})
+    # warm = 0: IPOPT-default restart; 1e-4: library default of the warm-start mode; 1e-8: the setting bench.py uses
+    for warm, mu0 in ((0, None), (1, 1e-4), (1, 1e-8)):
+        opts = {'b200.warm_start': warm, 'ipopt.tol': 1e-9}
+        if mu0 is not None:
+            opts['b200.warm_start_mu'] = mu0
+        nmpc = cstr_nmpc(N=50, solver_options=opts)
         x, us, its = x0.clone(), [], []
         for k in range(4):
             us.append(nmpc.optimize(x).clone())
@@ -128,10 +132,13 @@ def test_warm_start_mode_reaches_the_same_solution_in_fewer_iterations(cuda_devi
             its.append(nmpc._last['iters'].double().mean().item())
             xp, _, _ = nmpc.return_prediction()
             x = xp[:, 1, :4] + noise[k]
-        runs[warm] = (us, its)
-    for ua, ub in zip(runs[0][0], runs[1][0]):
-        assert (ua - ub).abs().max().item() < 1e-4 * ua.abs().max().item()
-    assert np.mean(runs[1][1][1:]) < np.mean(runs[0][1][1:])
+        runs[(warm, mu0)] = (us, its)
+    cold = runs[(0, None)]
+    for key in ((1, 1e-4), (1, 1e-8)):
+        for ua, ub in zip(cold[0], runs[key][0]):
+            assert (ua - ub).abs().max().item() < 1e-4 * ua.abs().max().item()
+        assert np.mean(runs[key][1][1:]) < np.mean(cold[1][1:])
+    assert np.mean(runs[(1, 1e-8)][1][1:]) < np.mean(runs[(1, 1e-4)][1][1:])
 
 
 def test_quad_eval_kernel_matches_thread_per_node_kernel(cuda_device):
