@@ -45,15 +45,20 @@ struct EvalQuad {
   static constexpr int NV = NX + NU + NC;    // bounded variables of a node: x_k | u_k | X_k
   static constexpr bool SUPPORTED = (P::METHOD == METHOD_COLLOCATION) && P::FIXED_X0 && !P::HAS_GADD && !P::HAS_ARR &&
                                     !P::OBJ_DISCRETE && (D <= 3) && (RPL * W <= 64) && (NC >= 4);
-  // per-quad scratch (doubles).  [oF | oPB | oT] are dead once the reduced Hessian partial sums exist and are reused
-  // as the quad-reduction area oRED.
+  // per-quad scratch (doubles), sized for 3 CTAs per SM.  Lifetimes:  F (model derivatives) until the plain system is
+  // assembled, then the same words hold T (its solution);  PB (pivot row) during the two eliminations, the collocation
+  // multipliers NU in between;  L (weighted cost derivatives + constraint curvature) until the partial sums of the
+  // reduced Hessian exist - from then on [F/T | PB | L] is the quad-reduction area RED and only the sums over the
+  // collocation points of lu / luu (SUM) are still needed.
   static constexpr int FSZ = NX + NX * NX + NX * NU;                             // f | fx | fu of one point
   static constexpr int LSZ = 1 + NX + NU + NX * NX + NU * NX + NU * NU;          // l | lx | lu | lxx | lux | luu (weighted)
   static constexpr int NRED = NE * (NE + 1) + NE;    // partial Hessian/gradient [NE][NE+1] + multiplier-form gradient
-  static constexpr int A1 = D * FSZ + 2 * W + NC * (NE + 1), A2 = 4 * NRED;
-  static constexpr int oF = 0, oPB = oF + D * FSZ, oT = oPB + 2 * W, oRED = 0,
-                       oL = (A1 > A2 ? A1 : A2), oNU = oL + D * LSZ,
-                       oBG = oNU + NC, oBD = oBG + NV, oBS = oBD + NV,   // barrier gradient | dz | sigma of x|u|X
+  static constexpr int FT = (D * FSZ > NC * (NE + 1)) ? D * FSZ : NC * (NE + 1);
+  static constexpr int PBN = (2 * W > NC) ? 2 * W : NC;
+  static constexpr int A1 = FT + PBN + D * LSZ, A2 = 4 * NRED;
+  static constexpr int oF = 0, oT = 0, oPB = FT, oNU = oPB, oL = oPB + PBN, oRED = 0,
+                       oSUM = (A1 > A2 ? A1 : A2),                       // sum_i lu_i [NU] | sum_i luu_i [NU*NU]
+                       oBG = oSUM + NU + NU * NU, oBD = oBG + NV, oBS = oBD + NV,   // barrier gradient | dz | sigma of x|u|X
                        oEND = oBS + NV;
   static constexpr int oGX = oBG + NX + NU, oDGX = oBD + NX + NU, oSGX = oBS + NX + NU;
   static constexpr int SCR = ((oEND + 1) & ~1) + 3;  // odd multiple keeps neighbouring quads on different banks
@@ -274,6 +279,18 @@ struct EvalQuad {
       __syncwarp();
     }
 
+    // sums over the collocation points of the input gradient / input Hessian of the cost (the L area is recycled later)
+#pragma unroll
+    for (int it = 0; it < (NU + NU * NU + 3) / 4; ++it) {
+      const int e = it * 4 + q;
+      if (e < NU + NU * NU) {
+        const int off = (e < NU) ? (1 + NX + e) : (1 + NX + NU + NX * NX + NU * NX + (e - NU));
+        double sacc = 0.0;
+#pragma unroll
+        for (int i = 0; i < D; ++i) sacc += S[oL + i * LSZ + off];
+        S[oSUM + e] = sacc;
+      }
+    }
     // ---------------------------------------------------------------- 3. plain system  G_X dX + G_x dx + G_u du + c = 0
     double Tr[RPL][NE + 1];   // own T rows (negated solution)
     {
@@ -424,7 +441,7 @@ struct EvalQuad {
         }
       }
     }
-    __syncwarp();   // every lane is done with F / PB / T: the area becomes the reduction buffer
+    __syncwarp();   // every lane is done with F / T / PB / L: the area becomes the reduction buffer
     {
       double* red = S + oRED + q * NRED;
 #pragma unroll
@@ -460,9 +477,7 @@ struct EvalQuad {
           }
         } else {
           const int aa = ii - NX;
-          double g = S[oBG + ii];
-#pragma unroll
-          for (int i = 0; i < D; ++i) g += S[oL + i * LSZ + 1 + NX + aa];
+          const double g = S[oBG + ii] + S[oSUM + aa];
           if (active) {
 #pragma unroll
             for (int jj = 0; jj < NX; ++jj)
@@ -470,8 +485,7 @@ struct EvalQuad {
 #pragma unroll
             for (int bb = 0; bb < NU; ++bb) {
               double v = r0[NX + bb] + r0[NRED + NX + bb] + r0[2 * NRED + NX + bb] + r0[3 * NRED + NX + bb];
-#pragma unroll
-              for (int i = 0; i < D; ++i) v += S[oL + i * LSZ + 1 + NX + NU + NX * NX + NU * NX + aa * NU + bb];
+              v += S[oSUM + NU + aa * NU + bb];
               if (bb == aa) v += S[oBS + ii];
               qh[T::oR + aa * NU + bb] = v;
             }
@@ -496,7 +510,7 @@ struct EvalQuad {
 };
 
 template <class P>
-__global__ void __launch_bounds__(128) eval_quad_kernel(OcpArgs a) { EvalQuad<P>::run(a); }
+__global__ void __launch_bounds__(128, 3) eval_quad_kernel(OcpArgs a) { EvalQuad<P>::run(a); }
 
 template <class P>
 inline cudaError_t launch_eval_quad(const OcpArgs& a, cudaStream_t s) {
