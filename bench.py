@@ -247,7 +247,9 @@ def main():
     ap.add_argument('--hessian', default='exact', choices=['exact', 'gauss-newton'])
     ap.add_argument('--warm-start', type=int, default=1, help='1: reuse multipliers + small initial barrier parameter '
                                                               'between closed-loop steps; 0: IPOPT-default restart')
-    ap.add_argument('--warm-mu', type=float, default=1e-4)
+    ap.add_argument('--warm-mu', type=float, default=1e-8,
+                    help='initial barrier parameter of warm-started solves (library default 1e-4; 1e-8 = one decade '
+                         'above the final one, tol/10: all instances of this closed loop still converge to tol)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     if args.impl == 'reference':

@@ -199,7 +199,9 @@ def _dep_hash() -> str:
 def build_module(src: str, name: str, hostsim: bool = False, verbose: bool = False,
                  extra_flags: Sequence[str] = ()) -> str:
     os.makedirs(GEN_DIR, exist_ok=True)
-    digest = hashlib.sha256((src + _dep_hash() + ('host' if hostsim else 'sm100a')).encode()).hexdigest()[:16]
+    # HB_NVCC_DEFINES='-DHB_STEPQ_MINB=3 ...': tuning experiments build separate, separately hashed modules
+    tune = os.environ.get('HB_NVCC_DEFINES', '').split()
+    digest = hashlib.sha256((src + _dep_hash() + ('host' if hostsim else 'sm100a') + ' '.join(tune)).encode()).hexdigest()[:16]
     safe = ''.join(c if c.isalnum() else '_' for c in name)
     base = os.path.join(GEN_DIR, f'{safe}_{digest}')
     so = base + ('_host.so' if hostsim else '.so')
@@ -212,7 +214,7 @@ def build_module(src: str, name: str, hostsim: bool = False, verbose: bool = Fal
     if hostsim:
         cmd = ['g++', '-O1', '-std=c++17', '-shared', '-fPIC', '-DHB_HOSTSIM', '-x', 'c++', '-I', CSRC, cu, '-o', tmp]
     else:
-        cmd = [nvcc_path()] + NVCC_FLAGS + list(extra_flags) + ['-I', CSRC, cu, '-o', tmp]
+        cmd = [nvcc_path()] + NVCC_FLAGS + list(extra_flags) + tune + ['-I', CSRC, cu, '-o', tmp]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"Building generated module failed:\n{' '.join(cmd)}\n{res.stdout}\n{res.stderr}")

@@ -30,7 +30,8 @@ struct StepQuad {
   static constexpr bool SUPPORTED = (P::METHOD == METHOD_COLLOCATION) && !P::OBJ_DISCRETE && !P::HAS_GADD && (D <= 3) &&
                                     (THREADS <= 1024);
   // shared memory (doubles): trial copy of the instance | warp partials | control block
-  static constexpr int oTRIAL = 0, oRED = oTRIAL + (N + 1) * NV, oCTRL = oRED + 8 * 32, SMEM = oCTRL + 8;
+  static constexpr int oTRIAL = 0, oRED = oTRIAL + (N + 1) * NV, oCTRL = oRED + 8 * 32, oST = oCTRL + 8,
+                       SMEM = oST + ST_COUNT;
   enum { C_FLAG = 0, C_ALPHA, C_AD, C_MU };   // control block entries
   enum { F_STOP = 0, F_EVAL = 1, F_APPLY = 2 };
 
@@ -53,9 +54,13 @@ struct StepQuad {
   static __device__ void run(const OcpArgs& a) {
     __shared__ __align__(16) double smem[SMEM];
     const int b = blockIdx.x, tid = threadIdx.x, k = tid >> 2, q = tid & 3, warp = tid >> 5, lane = tid & 31;
-    double* st = a.st + (long long)b * ST_COUNT;
-    if (st[ST_ACTIVE] == 0.0) return;   // uniform over the CTA
-    const double mu = st[ST_MU];
+    double* stg = a.st + (long long)b * ST_COUNT;
+    if (stg[ST_ACTIVE] == 0.0) return;   // uniform over the CTA
+    // the per-instance solver state is edited by thread 0 between the phases: work on a shared-memory copy (one
+    // coalesced load, no global round trips on the serial path) and write it back at the end
+    double* st = smem + oST;
+    if (tid < ST_COUNT) st[tid] = stg[tid];
+    const double mu = stg[ST_MU];
     const double tau = dmax(0.99, 1.0 - mu);
     const bool node = k <= N, inter = k < N;
     const long long nb = (long long)b * (N + 1) + (node ? k : N), sb = (long long)b * N + (inter ? k : N - 1);
@@ -113,9 +118,15 @@ struct StepQuad {
         lb[it] = a.xlb[j]; ub[it] = a.xub[j]; zl[it] = a.zlc[sb * NC + r]; zu[it] = a.zuc[sb * NC + r];
         kind[it] = 2;
         double s = el[T::ot0 + r];
-        const double* Tr = el + T::oT + r * NE;
+        if constexpr ((NE % 2 == 0) && (T::oT % 2 == 0) && (T::TD % 2 == 0)) {
+          const double2* Tr = reinterpret_cast<const double2*>(el + T::oT + r * NE);
 #pragma unroll
-        for (int c = 0; c < NE; ++c) s += Tr[c] * dxu[c];
+          for (int c = 0; c < NE / 2; ++c) { const double2 tv = Tr[c]; s += tv.x * dxu[2 * c] + tv.y * dxu[2 * c + 1]; }
+        } else {
+          const double* Tr = el + T::oT + r * NE;
+#pragma unroll
+          for (int c = 0; c < NE; ++c) s += Tr[c] * dxu[c];
+        }
         d[it] = s;
         dphi += el[T::ogX + r] * s;
       }
@@ -172,7 +183,10 @@ struct StepQuad {
     double* S = smem + oTRIAL + (node ? k : 0) * NV;
     for (int ai = 0;; ++ai) {
       const int flag = (int)ctrl[C_FLAG];
-      if (flag == F_STOP) return;
+      if (flag == F_STOP) {
+        if (tid < ST_COUNT) stg[tid] = st[tid];
+        return;
+      }
       if (flag == F_APPLY) break;
       const double alpha = ctrl[C_ALPHA];
       // own variables at the trial point
@@ -295,12 +309,16 @@ struct StepQuad {
         }
       }
     }
-    if (tid == 0) st[ST_MU] = st[ST_NACC];   // commit the barrier parameter chosen by the line search
+    // write the state back; the barrier parameter chosen by the line search is committed on the way
+    if (tid < ST_COUNT) stg[tid] = (tid == ST_MU) ? st[ST_NACC] : st[tid];
   }
 };
 
+#ifndef HB_STEPQ_MINB
+#define HB_STEPQ_MINB 2   // CTAs per SM the register allocation aims at
+#endif
 template <class P>
-__global__ void __launch_bounds__(StepQuad<P>::THREADS, 2) step_quad_kernel(const OcpArgs a) { StepQuad<P>::run(a); }
+__global__ void __launch_bounds__(StepQuad<P>::THREADS, HB_STEPQ_MINB) step_quad_kernel(const OcpArgs a) { StepQuad<P>::run(a); }
 
 template <class P>
 inline cudaError_t launch_step_quad(const OcpArgs& a, cudaStream_t s) {
