@@ -3,6 +3,7 @@
 #pragma once
 #include "ocp_kernels.cuh"
 #include "riccati.cuh"
+#include "riccati2.cuh"
 #include "eval_quad.cuh"
 #include "step_fused.cuh"
 #include "step_quad.cuh"
@@ -159,7 +160,16 @@ struct OcpModule {
       tm.end();
       tm.begin(K_RICCATI);
 #if HB_DEVICE_BUILD
-      if constexpr (RiccatiTma<P>::SUPPORTED) {
+      bool ric_done = false;
+      if constexpr (RiccatiTma2<P>::SUPPORTED) {
+        if (c->riccati_variant >= 2) {
+          cudaError_t e = launch_riccati_tma2<P>(a, s);
+          if (e != cudaSuccess) return (int)e;
+          ric_done = true;
+        }
+      }
+      if (ric_done) {
+      } else if constexpr (RiccatiTma<P>::SUPPORTED) {
         if (c->riccati_variant != 0) {
           cudaError_t e = launch_riccati_tma<P>(a, s);
           if (e != cudaSuccess) return (int)e;

@@ -94,7 +94,7 @@ class OcpEngine:
     def solve(self, x0, dt: float, time0: float = 0., sp=None, tp=None, uold=None, ap=None, tol: float = 1e-8,
               acc_tol: float = 1e-6, max_iter: int = 3000, n_alpha: int = 8, mu_init: float = .1,
               mu_min: Optional[float] = None, check_every: int = 4, stream=None, kernel_ms=None, kernel_count=None,
-              riccati_variant: int = 1, warm_start: int = 0, mu_init_warm: float = 1e-4,
+              riccati_variant: int = 2, warm_start: int = 0, mu_init_warm: float = 1e-4,
               eval_variant: int = 1, step_variant: int = 2, adaptive_poll: bool = True):
         """``x0``: CUDA tensor ``[B, nx]`` (scaled). Optional ``sp [B|1, N, nsp]``, ``tp``, ``uold``, ``ap`` tensors.
         Returns dict of device tensors: x [B,N+1,nx], u [B,N,nu], xc, lam, status, iters, stats."""

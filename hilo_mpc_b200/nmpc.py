@@ -194,7 +194,7 @@ class DynamicOptimization:
                     mu_init=float(o.get('ipopt.mu_init', .1)),
                     n_alpha=int(o.get('b200.line_search_candidates', 8)),
                     check_every=int(o.get('b200.check_every', 4)),
-                    riccati_variant=int(o.get('b200.riccati_variant', 1)),
+                    riccati_variant=int(o.get('b200.riccati_variant', 2)),
                     warm_start=int(o.get('b200.warm_start', 0)),
                     mu_init_warm=float(o.get('b200.warm_start_mu', 1e-4)),
                     eval_variant=int(o.get('b200.eval_variant', 1)),

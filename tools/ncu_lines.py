@@ -26,10 +26,15 @@ for r in rows:
     if hdr is None:
         continue
     if r[0] != '':
-        agg.append((kern, cur, int(r[0]), r[1].strip()[:100], int(r[ix['# Samples']]), int(r[ix['Instructions Executed']])))
+        def num(v):
+            try:
+                return int(v)
+            except ValueError:
+                return 0
+        agg.append((kern, cur, int(r[0]), r[1].strip()[:100], num(r[ix['# Samples']]), num(r[ix['Instructions Executed']])))
         for h, i in ix.items():
             if h.startswith('stall_') and 'Not Issued' not in h:
-                stall[(kern, h)] += int(r[i])
+                stall[(kern, h)] += num(r[i])
 kernels = sorted({a[0] for a in agg})
 for kn in kernels:
     sel = [a for a in agg if a[0] == kn]
