@@ -200,6 +200,40 @@ def _cpu_worker(arg):
     return ok
 
 
+def gp_predict_line(dev, n: int = 512, d: int = 6, m: int = 65536, reps: int = 5):
+    """Second BASELINE metric: GP predict microseconds per query point (SE kernel, n=512 training points, d=6 features,
+    BASELINE config 3 sizes), posterior mean + variance and mean only, through ``GaussianProcess.predict`` with device
+    tensors.  The variance is one (n x n) x (n x m) fp64 product on the DMMA pipe; flops = n^2 m (+ Gram n m (3d+4))."""
+    import torch
+    from hilo_mpc_b200.gp import GaussianProcess, Kernel
+    rng = np.random.default_rng(1)
+    X = rng.uniform(-1., 1., size=(d, n))
+    y = np.sin(X.sum(0, keepdims=True)) + 1e-2 * rng.standard_normal((1, n))
+    gp = GaussianProcess([f'x{i}' for i in range(d)], 'y', kernel=Kernel.squared_exponential(length_scales=.8),
+                         noise_variance=1e-4)
+    gp.set_training_data(X, y)
+    t0 = time.perf_counter()
+    gp.setup()
+    torch.cuda.synchronize()
+    fit_ms = (time.perf_counter() - t0) * 1e3
+    Xq = torch.tensor(rng.uniform(-1., 1., size=(d, m)), dtype=torch.float64, device=dev)
+    out = {'n_train': n, 'features': d, 'queries': m, 'fit_ms_incl_alloc': fit_ms}
+    for key, mean_only in (('mean_var', False), ('mean_only', True)):
+        for _ in range(2):
+            gp.predict(Xq, mean_only=mean_only)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            gp.predict(Xq, mean_only=mean_only)
+        e1.record()
+        torch.cuda.synchronize()
+        us_pt = e0.elapsed_time(e1) * 1e3 / (reps * m)
+        flops_pt = n * (3 * d + 4) + 2 * n + (0 if mean_only else 2 * n * n)
+        out[key] = {'us_per_pt': us_pt, 'gflops': flops_pt / us_pt * 1e-3}
+    out['fp64_peak_note'] = 'B200 nominal fp64 (vector = tensor) 37-40 TFLOP/s; no measured fp64 peak in MEASURED_PEAKS.json'
+    return out
+
+
 def run_reference(args):
     """``--impl reference``: CPU arm, rank 0 only."""
     rank = int(os.environ.get('RANK', '0'))
@@ -240,6 +274,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=BATCH_PER_GPU, help='instances per GPU')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-gp', action='store_true', help='skip the GP-predict side metric')
     ap.add_argument('--debug-steps', action='store_true')
     ap.add_argument('--prewarm-ms', type=float, default=600.)
     ap.add_argument('--clock-sampler', default='nvml', choices=['nvml', 'smi', 'none'])
@@ -419,6 +454,21 @@ def main():
                                      'frac': bytes_riccati / (ric['avg_us'] * 1e-6) / 1e9 / peak,
                                      'avg_us': ric['avg_us']}
 
+    # measured DRAM traffic per launch (ncu --set full, profiles/ncu_traffic.json; refreshed with every kernel change)
+    traffic_path = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+    if os.path.exists(traffic_path):
+        with open(traffic_path) as f:
+            tr = json.load(f)
+        if roof_name in tr:
+            roofline['traffic'] = tr[roof_name]['dram_bytes_per_launch']
+            roofline['traffic_source'] = tr[roof_name].get('source')
+        if 'riccati' in tr and 'riccati_sweep' in roofline:
+            roofline['riccati_sweep']['traffic'] = tr['riccati']['dram_bytes_per_launch']
+
+    extras = {}
+    if not args.no_gp:
+        extras['gp_predict'] = gp_predict_line(dev)
+
     cpu_baseline = None
     if not args.no_cpu_baseline:
         v, el = cpu_port_sample(args.cpu_sample, 1)
@@ -442,7 +492,7 @@ def main():
         'e2e': {'value': e2e_value, 'unit': 'steps/s', 'h2d_bytes_per_step': B * NX * 8,
                 'd2h_bytes_per_step': B * NU * 8 + B * (N_HORIZON + 1) * 0 + B * NX * 8},
         'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'kernels': per_kernel,
-        'cpu_baseline': cpu_baseline,
+        'cpu_baseline': cpu_baseline, 'extras': extras,
     }
     print(json.dumps(line))
     if world > 1:
