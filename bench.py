@@ -304,6 +304,8 @@ def main():
     dev = torch.device('cuda', local_rank)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
+            os.environ['NCCL_DEBUG'] = 'WARN'   # the version banner goes to stdout, which carries exactly one JSON line
         dist.init_process_group('nccl', device_id=dev)
 
     B = args.batch
