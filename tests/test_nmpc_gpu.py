@@ -75,6 +75,62 @@ def test_full_size_properties(cuda_device):
     np.testing.assert_allclose(u_single.cpu().numpy(), u0[1234:1235].cpu().numpy(), rtol=0, atol=1e-9)
 
 
+def test_full_size_independent_kkt_certificate(cuda_device):
+    """BASELINE config 2 size, bench settings (warm-started closed loop, mu0 = 1e-8): for sampled instances of the
+    4096-batch the returned point is checked with the ORACLE's functions, not the solver's own statistics - constraint
+    residual of the flat NLP (mpc.py:1133-1787 transcription) <= 1e-8, bounds respected, and first-order optimality: a
+    multiplier vector exists (least squares over the constraint multipliers, bound multipliers >= 0 on active bounds)
+    that makes the Lagrangian gradient vanish to 1e-6.  Also: permuting the batch permutes the result bit for bit."""
+    import torch
+    from scipy.sparse.linalg import lsqr
+    from hilo_mpc_b200.examples import cstr_initial_states, cstr_nmpc
+    B = 4096
+    nmpc = cstr_nmpc(N=50, solver_options={'b200.warm_start': 1, 'b200.warm_start_mu': 1e-8})
+    x0 = cstr_initial_states(B, seed=0)
+    rng = np.random.default_rng(5)
+    x = torch.tensor(x0, device=cuda_device)
+    for k in range(3):   # third closed-loop step: warm-started solve like in bench.py
+        nmpc.optimize(x)
+        assert (nmpc.solver_status_code == 1).all()
+        xp, _, _ = nmpc.return_prediction()
+        x_solved = x.clone()
+        x = xp[:, 1, :4] + torch.tensor(rng.uniform(-1, 1, size=(B, 4)) * np.array([.02, .02, .5, .5]), device=cuda_device)
+    out = {k: nmpc._last[k].cpu().numpy() for k in ('x', 'u', 'xc')}
+    xs = np.asarray(nmpc._xs_full)
+    nlp = _oracle(nmpc)
+    spec = nmpc.spec
+    cb = nlp.callback(0., np.full(spec.N, nmpc.sampling_interval), np.zeros((spec.N, spec.nsp)), np.zeros(spec.ntp),
+                      np.zeros(spec.nuold))
+    for b in rng.choice(B, size=12, replace=False):
+        lb, ub, _ = nlp.bounds_and_guess(x_solved[b].cpu().numpy() / xs)
+        v = np.zeros(nlp.n_v)
+        for k in range(spec.N + 1):
+            v[nlp.x_ind[k]] = out['x'][b, k]
+        for k in range(spec.N):
+            v[nlp.u_ind[k]] = out['u'][b, k]
+            v[nlp.c_ind[k]] = out['xc'][b, k]
+        f, gf, g, J, _ = cb(v, None)
+        assert np.abs(g).max() < 1e-8, f'instance {b}: constraint residual {np.abs(g).max():.2e}'
+        assert (v >= lb - 1e-12).all() and (v <= ub + 1e-12).all()
+        # stationarity on the variables that are strictly inside their bounds; on (nearly) active bounds the sign of the
+        # remaining gradient component must be the one a non-negative bound multiplier can cancel
+        # (mu = 1e-9 at the solution: a bound at distance s carries the multiplier mu/s, below 1e-6 for s > 1e-3)
+        free = (v - lb > 1e-3) & (ub - v > 1e-3)
+        lam = lsqr(J.T.tocsr()[free], -gf[free], atol=1e-14, btol=1e-14, iter_lim=20000)[0]
+        r = gf + J.T @ lam
+        assert np.abs(r[free]).max() < 1e-6, f'instance {b}: stationarity residual {np.abs(r[free]).max():.2e}'
+        at_lb, at_ub = (v - lb <= 1e-3) & (ub > lb), (ub - v <= 1e-3) & (ub > lb)
+        assert (r[at_lb] > -1e-6).all() and (r[at_ub] < 1e-6).all()
+    # batch-permutation equivariance (no cross-instance coupling anywhere in the kernels)
+    perm = torch.tensor(rng.permutation(B), device=cuda_device)
+    a1 = cstr_nmpc(N=50)
+    a2 = cstr_nmpc(N=50)
+    xt = torch.tensor(x0, device=cuda_device)
+    u1 = a1.optimize(xt)
+    u2 = a2.optimize(xt[perm])
+    assert torch.equal(u1[perm], u2)
+
+
 def test_full_size_one_instance_vs_oracle(cuda_device):
     import torch
     from hilo_mpc_b200.examples import cstr_initial_states, cstr_nmpc
