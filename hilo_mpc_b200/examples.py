@@ -32,6 +32,47 @@ def cstr_nmpc(N: int = 50, dt: float = 0.005, integration_method: str = 'colloca
     return nmpc
 
 
+def cstr_side_reaction_gp(n_train: int = 24, seed: int = 1):
+    """Config 3, the learned component: a GP (SE kernel with ARD length scales, fixed hyper-parameters, constant prior
+    mean) of the side-reaction rate ``k_3(T_R) c_A^2`` over the feature box ``c_A in [0.6, 2], T_R in [110, 140]``,
+    trained on ``n_train`` uniformly drawn points with N(0, 1e-4) noise and fitted on the GPU (``hb_gp_fit``)."""
+    from .gp import GaussianProcess, Kernel
+    from .library import cstr_side_reaction
+    rng = np.random.default_rng(seed)
+    X = np.vstack([rng.uniform(.6, 2., n_train), rng.uniform(110., 140., n_train)])
+    y = cstr_side_reaction(X[0], X[1]) + 1e-2 * rng.standard_normal(n_train)
+    gp = GaussianProcess(['c_A', 'T_R'], 'r_3', kernel=Kernel.squared_exponential(signal_variance=25., ard=True,
+                                                                                    length_scales=[.7, 15.]),
+                         noise_variance=1e-4, mean=float(y.mean()))
+    gp.set_training_data(X, y.reshape(1, -1))
+    gp.setup()
+    return gp
+
+
+def cstr_gp_nmpc(gp, N: int = 10, dt: float = 0.005, solver_options=None) -> NMPC:
+    """Config 3 (GP-output-feedback NMPC): the CSTR of config 2 with the side-reaction rate replaced by the posterior
+    mean of ``gp`` (symbolic query, the way the reference embeds learned components: dynamic_model.py:3040-3080)."""
+    from . import symbolic as sx
+
+    def side_reaction(cA, TR):
+        mean, _ = gp.predict(sx.as_vector([cA, TR]))
+        return mean[0]
+    model = cstr_model(dt, side_reaction=side_reaction, name=f'cstr_gp{gp.X_train.shape[1]}')
+    x_ss, u_ss = cstr_steady_state()
+    nmpc = NMPC(model)
+    nmpc.horizon = N
+    nmpc.quad_stage_cost.add_states(names=['c_A', 'c_B', 'T_R', 'T_K'], ref=list(x_ss), weights=CSTR_Q)
+    nmpc.quad_stage_cost.add_inputs(names=['F', 'Q_dot'], ref=list(u_ss), weights=CSTR_R)
+    nmpc.quad_terminal_cost.add_states(names=['c_A', 'c_B', 'T_R', 'T_K'], ref=list(x_ss), weights=CSTR_Q)
+    nmpc.set_box_constraints(**CSTR_BOUNDS)
+    nmpc.set_scaling(**CSTR_SCALING)
+    nmpc.set_initial_guess(x_guess=x_ss, u_guess=u_ss)
+    if solver_options:
+        nmpc.set_solver_opts(solver_options)
+    nmpc.setup()
+    return nmpc
+
+
 def cstr_initial_states(B: int, seed: int = 0) -> np.ndarray:
     """``x0 = x_ss + diag([.2,.2,5,5]) U(-1,1)`` with ``np.random.default_rng(seed)`` (cfg 2)."""
     x_ss, _ = cstr_steady_state()

@@ -17,30 +17,37 @@ CSTR = dict(k10=1.287e12, k20=1.287e12, k30=9.043e9, E1=9758.3, E2=9758.3, E3=85
             cA0=5.1)
 
 
-def cstr_rhs(x, u, c=CSTR, exp=None):
+def cstr_rhs(x, u, c=CSTR, exp=None, side_reaction=None):
     """Right-hand side for symbolic (``exp=sx.exp``) or NumPy (``exp=np.exp``) arguments; states
-    ``[c_A, c_B, T_R, T_K]``, inputs ``[F, Q_dot]``."""
+    ``[c_A, c_B, T_R, T_K]``, inputs ``[F, Q_dot]``.  ``side_reaction(c_A, T_R)``, if given, replaces the rate term
+    ``k_3(T_R) c_A^2`` (BASELINE config 3: that term learned by a Gaussian process)."""
     exp = exp or sx.exp
     cA, cB, TR, TK = x[0], x[1], x[2], x[3]
     F, Qd = u[0], u[1]
     k1 = c['k10'] * exp(-c['E1'] / (TR + 273.15))
     k2 = c['k20'] * exp(-c['E2'] / (TR + 273.15))
     k3 = c['k30'] * exp(-c['E3'] / (TR + 273.15))
-    dcA = F * (c['cA0'] - cA) - k1 * cA - k3 * cA * cA
+    r3 = k3 * cA * cA if side_reaction is None else side_reaction(cA, TR)
+    dcA = F * (c['cA0'] - cA) - k1 * cA - r3
     dcB = -F * cB + k1 * cA - k2 * cB
     dTR = F * (c['T_in'] - TR) + c['k_w'] * c['A_R'] / (c['rho'] * c['cp'] * c['V_R']) * (TK - TR) \
-        - (k1 * cA * c['dH_AB'] + k2 * cB * c['dH_BC'] + k3 * cA * cA * c['dH_AD']) / (c['rho'] * c['cp'])
+        - (k1 * cA * c['dH_AB'] + k2 * cB * c['dH_BC'] + r3 * c['dH_AD']) / (c['rho'] * c['cp'])
     dTK = (Qd + c['k_w'] * c['A_R'] * (TR - TK)) / (c['m_K'] * c['cpK'])
     return [dcA, dcB, dTR, dTK]
 
 
-def cstr_model(dt: float = 0.005) -> Model:
-    model = Model(name='cstr_klatt_engell', time_unit='h')
+def cstr_side_reaction(cA, TR, c=CSTR, exp=np.exp):
+    """The true rate term ``k_3(T_R) c_A^2`` (training target of the GP of config 3)."""
+    return c['k30'] * exp(-c['E3'] / (TR + 273.15)) * cA * cA
+
+
+def cstr_model(dt: float = 0.005, side_reaction=None, name: str = 'cstr_klatt_engell') -> Model:
+    model = Model(name=name, time_unit='h')
     x = model.set_dynamical_states(['c_A', 'c_B', 'T_R', 'T_K'])
     u = model.set_inputs(['F', 'Q_dot'])
     model.set_measurements(['y_cB', 'y_TR'])
     model.set_measurement_equations([x[1], x[2]])
-    model.set_dynamical_equations(cstr_rhs(x, u))
+    model.set_dynamical_equations(cstr_rhs(x, u, side_reaction=side_reaction))
     model.setup(dt=dt)
     return model
 

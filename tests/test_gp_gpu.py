@@ -49,3 +49,37 @@ def test_gp_fit_and_predict_match_oracle(cuda_device, n, d):
     ms, _ = gp.predict(xs)
     F = sx.Function('m', [('x', xs)], [('m', ms)])
     np.testing.assert_allclose(F(Xq[:, :5])[0], mo[:5], rtol=1e-7, atol=1e-8)
+
+
+def test_gp_inside_nmpc_matches_oracle(cuda_device):
+    """BASELINE config 3 (GP-output-feedback NMPC) at a size the oracle finishes in seconds: the CSTR's side-reaction rate
+    is replaced by the posterior mean of a GP fitted on the GPU (`hb_gp_fit`), embedded symbolically like the reference
+    does (dynamic_model.py:3040-3080), compiled into the node kernels, and the batched solve is compared with the oracle
+    on the same NLP.  The learned model must also be a good surrogate: first moves within 2 % of the true-model NMPC."""
+    import torch
+    from hilo_mpc_b200.examples import cstr_gp_nmpc, cstr_initial_states, cstr_nmpc, cstr_side_reaction_gp
+    from hilo_mpc_b200.library import cstr_side_reaction
+    from oracle.nmpc import FlatNlp
+    gp = cstr_side_reaction_gp(n_train=24)
+    rng = np.random.default_rng(0)
+    Xq = np.vstack([rng.uniform(.8, 1.8, 200), rng.uniform(115., 135., 200)])
+    mean, var = gp.predict(Xq)
+    truth = cstr_side_reaction(Xq[0], Xq[1])
+    assert np.abs(mean[0] - truth).max() < 0.05 * np.abs(truth).max()
+    assert (var > 0).all()
+    nmpc = cstr_gp_nmpc(gp, N=10)
+    x0 = cstr_initial_states(16, seed=3)
+    u0 = nmpc.optimize(torch.tensor(x0, device=cuda_device))
+    assert (nmpc.solver_status_code == 1).all()
+    x_pred, u_pred, _ = nmpc.return_prediction()
+    xs, us = np.asarray(nmpc._xs_full), np.asarray(nmpc._us_full)
+    nlp = FlatNlp(nmpc.spec, exact_hessian=True)
+    for b in (0, 9):
+        res, xo, uo = nlp.solve(x0[b] / xs, dt=nmpc.sampling_interval, finish_barrier=True)
+        assert res.status == 1
+        np.testing.assert_allclose(x_pred[b].cpu().numpy() / xs, xo.T, atol=2e-6)
+        np.testing.assert_allclose(u_pred[b].cpu().numpy() / us, uo.T, atol=2e-5)
+    true_nmpc = cstr_nmpc(N=10)
+    u_true = true_nmpc.optimize(torch.tensor(x0, device=cuda_device))
+    rel = ((u0 - u_true).abs() / torch.tensor(us, device=cuda_device)).max().item()
+    assert rel < 0.02 * (u_true.abs() / torch.tensor(us, device=cuda_device)).max().item() + 0.02
