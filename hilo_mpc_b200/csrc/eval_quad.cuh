@@ -54,14 +54,16 @@ struct EvalQuad {
   static constexpr int LSZ = 1 + NX + NU + NX * NX + NU * NX + NU * NU;          // l | lx | lu | lxx | lux | luu (weighted)
   static constexpr int NRED = NE * (NE + 1) + NE;    // partial Hessian/gradient [NE][NE+1] + multiplier-form gradient
   static constexpr int FT = (D * FSZ > NC * (NE + 1)) ? D * FSZ : NC * (NE + 1);
-  static constexpr int PBN = (2 * W > NC) ? 2 * W : NC;
+  static constexpr int PBN = (2 * ((W + 1) & ~1) > NC) ? 2 * ((W + 1) & ~1) : NC;
   static constexpr int A1 = FT + PBN + D * LSZ, A2 = 4 * NRED;
   static constexpr int oF = 0, oT = 0, oPB = FT, oNU = oPB, oL = oPB + PBN, oRED = 0,
                        oSUM = (A1 > A2 ? A1 : A2),                       // sum_i lu_i [NU] | sum_i luu_i [NU*NU]
                        oBG = oSUM + NU + NU * NU, oBD = oBG + NV, oBS = oBD + NV,   // barrier gradient | dz | sigma of x|u|X
                        oEND = oBS + NV;
   static constexpr int oGX = oBG + NX + NU, oDGX = oBD + NX + NU, oSGX = oBS + NX + NU;
-  static constexpr int SCR = ((oEND + 1) & ~1) + 3;  // odd multiple keeps neighbouring quads on different banks
+  // stride = 2 (mod 16) doubles: 16-byte aligned, and the 8 quads of a warp start 4 banks apart (conflict-free 64- and
+  // 128-bit accesses to the same offset)
+  static constexpr int SCR = ((oEND + 13) / 16) * 16 + 2;
   static constexpr int QUADS = 32;                   // quads (nodes) per CTA, 128 threads
   static constexpr int SMEM_BYTES = QUADS * SCR * 8;
   static constexpr bool EL_VEC2 = (NE % 2 == 0) && (T::oT % 2 == 0) && (T::TD % 2 == 0);
@@ -74,41 +76,51 @@ struct EvalQuad {
   // The owner publishes its (unnormalised) pivot row, every lane forms its own multipliers with a Newton-refined
   // reciprocal, and the rows are scaled by their inverse pivots once at the end.
   // The collocation matrix is dt*blkdiag(f_x) - C^T (x) I, whose unpivoted pivots are about (-3.2, -2.1, -9.0) per
-  // state for the Radau-3 constants; the smallest pivot magnitude met is returned so that the caller can hand nodes
-  // with a degenerate pivot (stiff dt*f_x) to the partially pivoted one-thread-per-node kernel.
+  // state for the Radau-3 constants; the largest |1 / pivot| met is returned so that the caller can hand nodes with
+  // a degenerate pivot (stiff dt*f_x) to the partially pivoted one-thread-per-node kernel.
   // On return row r holds, in columns >= NPIV, the solution of variable r.
   template <int NCOLS, int NPIV>
   static __device__ __forceinline__ double gauss_jordan(double (&R)[RPL][NCOLS], int q, double* pb) {
-    double minpiv = 1e300;
+    constexpr int PS = (NCOLS + 1) & ~1;   // even stride: the pivot row travels in 128-bit words
     double ipiv[RPL];
 #pragma unroll
     for (int lr = 0; lr < RPL; ++lr) ipiv[lr] = 1.0;
 #pragma unroll
     for (int c = 0; c < NPIV; ++c) {
       const int po = c & 3, plr = c >> 2;   // owner lane / local row of the pivot row
-      double* prow = pb + (c & 1) * NCOLS;   // double-buffered broadcast row
+      const int j0 = c & ~1;                 // first (even) column of the broadcast; column j0 < c is dead weight
+      double* prow = pb + (c & 1) * PS;      // double-buffered broadcast row
       if (q == po) {
 #pragma unroll
-        for (int j = c; j < NCOLS; ++j) prow[j] = R[plr][j];
+        for (int j = j0; j < NCOLS; j += 2)
+          *reinterpret_cast<double2*>(prow + j) = make_double2(R[plr][j], (j + 1 < NCOLS) ? R[plr][j + 1] : 0.0);
       }
       __syncwarp();
-      const double piv = prow[c];
-      const double inv = rcp_nr(piv);
-      if (q == po) { ipiv[plr] = inv; minpiv = fmin(minpiv, fabs(piv)); }
+      double pr[PS];
+#pragma unroll
+      for (int j = j0; j < NCOLS; j += 2) {
+        const double2 t2 = *reinterpret_cast<const double2*>(prow + j);
+        pr[j] = t2.x; pr[j + 1] = t2.y;
+      }
+      const double inv = rcp_nr(pr[c]);
+      ipiv[plr] = (q == po) ? inv : ipiv[plr];
 #pragma unroll
       for (int lr = 0; lr < RPL; ++lr) {
         const bool is_piv = (lr == plr) && (q == po);
         const double f = is_piv ? 0.0 : R[lr][c] * inv;
 #pragma unroll
-        for (int j = c + 1; j < NCOLS; ++j) R[lr][j] -= f * prow[j];
+        for (int j = c + 1; j < NCOLS; ++j) R[lr][j] -= f * pr[j];
       }
     }
+    double maxinv = 0.0;   // largest |1 / pivot| of the own rows
 #pragma unroll
-    for (int lr = 0; lr < RPL; ++lr)
+    for (int lr = 0; lr < RPL; ++lr) {
+      maxinv = fmax(maxinv, fabs(ipiv[lr]));
 #pragma unroll
       for (int j = NPIV; j < NCOLS; ++j) R[lr][j] *= ipiv[lr];
+    }
     __syncwarp();
-    return minpiv;
+    return maxinv;
   }
 
   static __device__ void run(const OcpArgs& a) {
@@ -144,7 +156,7 @@ struct EvalQuad {
 #pragma unroll
     for (int i = 0; i < NU; ++i) u[i] = ug[i];
 
-    double phi = 0.0, comp = 0.0, c1 = 0.0, cinf = 0.0, minpiv = 1e300;
+    double phi = 0.0, comp = 0.0, c1 = 0.0, cinf = 0.0, maxinv = 0.0;
     // ---------------------------------------------------------------- 1a. barrier terms, 4 variables at a time
     {
       BarrierSum bs;
@@ -254,7 +266,7 @@ struct EvalQuad {
         }
         Rt[lr][NC] = (r < NC) ? -(S[oGX + r] + S[oDGX + r] + P::CD(ip + 1) * lam1[cc]) : 0.0;
       }
-      minpiv = fmin(minpiv, gauss_jordan<WT, NC>(Rt, q, S + oPB));
+      maxinv = fmax(maxinv, gauss_jordan<WT, NC>(Rt, q, S + oPB));
 #pragma unroll
       for (int lr = 0; lr < RPL; ++lr)
         if (lr * 4 + q < NC) S[oNU + lr * 4 + q] = Rt[lr][NC];
@@ -324,7 +336,7 @@ struct EvalQuad {
         }
         R[lr][NC + NE] = res;
       }
-      minpiv = fmin(minpiv, gauss_jordan<W, NC>(R, q, S + oPB));
+      maxinv = fmax(maxinv, gauss_jordan<W, NC>(R, q, S + oPB));
       // own T rows stay in registers and are published to the scratch pad for the other lanes
 #pragma unroll
       for (int lr = 0; lr < RPL; ++lr) {
@@ -500,11 +512,11 @@ struct EvalQuad {
     for (int m = 1; m < 4; m <<= 1) {
       phi += qshfl_xor(phi, m); c1 += qshfl_xor(c1, m);
       comp = dmax(comp, qshfl_xor(comp, m)); cinf = dmax(cinf, qshfl_xor(cinf, m));
-      minpiv = fmin(minpiv, qshfl_xor(minpiv, m));
+      maxinv = fmax(maxinv, qshfl_xor(maxinv, m));
     }
     if (active && q == 0) {
       a.s_cinf[nb] = cinf; a.s_c1[nb] = c1; a.s_phi[nb] = phi; a.s_comp[nb] = comp;
-      a.nflag[sb] = (minpiv < 0.05) ? 1 : 0;  // degenerate static pivot: redo this node with partial pivoting
+      a.nflag[sb] = (maxinv > 20.0 || !(maxinv == maxinv)) ? 1 : 0;  // degenerate static pivot (|pivot| < 0.05): redo with partial pivoting
     }
   }
 };
