@@ -212,7 +212,8 @@ def build_module(src: str, name: str, hostsim: bool = False, verbose: bool = Fal
         f.write(src)
     tmp = so + f'.tmp{os.getpid()}'
     if hostsim:
-        cmd = ['g++', '-O1', '-std=c++17', '-shared', '-fPIC', '-DHB_HOSTSIM', '-x', 'c++', '-I', CSRC, cu, '-o', tmp]
+        cmd = ['g++', '-O1', '-std=c++17', '-shared', '-fPIC', '-pthread', '-DHB_HOSTSIM', '-x', 'c++', '-I', CSRC, cu,
+               '-o', tmp]
     else:
         cmd = [nvcc_path()] + NVCC_FLAGS + list(extra_flags) + tune + ['-I', CSRC, cu, '-o', tmp]
     res = subprocess.run(cmd, capture_output=True, text=True)

@@ -351,8 +351,8 @@ struct EvalQuad {
     __syncwarp();
 
     // ---------------------------------------------------------------- 4. reduced stage data
-    double* qa = a.qa + sb * T::NAp;
-    double* qh = a.qh + sb * T::NHp;
+    double* qa = a.qa + ((long long)b * T::N + k) * T::NAp;
+    double* qh = a.qh + ((long long)b * T::N + k) * T::NHp;
     double* el = a.el + sb * T::TD;
     const double* Tm = S + oT;
     // dynamics rows (lane q -> state rows q, q+4, ...)
@@ -371,19 +371,20 @@ struct EvalQuad {
             double s = (rr == c) ? P::CD(0) : 0.0;
 #pragma unroll
             for (int i = 1; i <= D; ++i) s += P::CD(i) * Tm[((i - 1) * NX + rr) * (NE + 1) + c];
-            qa[T::oA + rr * NX + c] = s;
+            qa[T::iA(rr, c)] = s;
           }
 #pragma unroll
           for (int c = 0; c < NU; ++c) {
             double s = 0.0;
 #pragma unroll
             for (int i = 1; i <= D; ++i) s += P::CD(i) * Tm[((i - 1) * NX + rr) * (NE + 1) + NX + c];
-            qa[T::oB + rr * NU + c] = s;
+            qa[T::iB(rr, c)] = s;
           }
-          qa[T::ob + rr] = bsum + res;
+          qa[T::ib(rr)] = bsum + res;
         }
       }
     }
+    if (active) T::fill_pads(qa, qh, q, 4);   // operand-order layout: zero column of M, pads of small problems
     // elimination block for Expand, own rows straight from the registers: T | t0 | gX
     if (active) {
 #pragma unroll
@@ -482,27 +483,30 @@ struct EvalQuad {
             for (int jj = 0; jj < NX; ++jj) {
               double v = r0[jj] + r0[NRED + jj] + r0[2 * NRED + jj] + r0[3 * NRED + jj];
               if (jj == ii) v += S[oBS + ii];
-              qh[T::oQ + ii * NX + jj] = v;
+              qh[T::iQ(ii, jj)] = v;
             }
-            qh[T::oq + ii] = g + sq; el[T::ogx + ii] = g;
-            qh[T::oqb + ii] = g + S[oBD + ii] + sg;
+            qh[T::iq(ii)] = g + sq; el[T::ogx + ii] = g;
+            qh[T::iqb(ii)] = g + S[oBD + ii] + sg;
           }
         } else {
           const int aa = ii - NX;
           const double g = S[oBG + ii] + S[oSUM + aa];
           if (active) {
 #pragma unroll
-            for (int jj = 0; jj < NX; ++jj)
-              qh[T::oS + aa * NX + jj] = r0[jj] + r0[NRED + jj] + r0[2 * NRED + jj] + r0[3 * NRED + jj];
+            for (int jj = 0; jj < NX; ++jj) {
+              const double v = r0[jj] + r0[NRED + jj] + r0[2 * NRED + jj] + r0[3 * NRED + jj];
+              qh[T::iS(aa, jj)] = v;
+              if constexpr (T::FRAG) qh[T::iSt(aa, jj)] = v;
+            }
 #pragma unroll
             for (int bb = 0; bb < NU; ++bb) {
               double v = r0[NX + bb] + r0[NRED + NX + bb] + r0[2 * NRED + NX + bb] + r0[3 * NRED + NX + bb];
               v += S[oSUM + NU + aa * NU + bb];
               if (bb == aa) v += S[oBS + ii];
-              qh[T::oR + aa * NU + bb] = v;
+              qh[T::iR(aa, bb)] = v;
             }
-            qh[T::orr + aa] = g + sq; el[T::ogu + aa] = g;
-            qh[T::orb + aa] = g + S[oBD + ii] + sg;
+            qh[T::ir(aa)] = g + sq; el[T::ogu + aa] = g;
+            qh[T::irb(aa)] = g + S[oBD + ii] + sg;
           }
         }
       }

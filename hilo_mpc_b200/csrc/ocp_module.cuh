@@ -2,8 +2,8 @@
 // The core library (hilo_b200.cu) dlopens the module and forwards hb_ocp_* calls to these hbm_* symbols.
 #pragma once
 #include "ocp_kernels.cuh"
-#include "riccati.cuh"
 #include "riccati2.cuh"
+#include "riccati6.cuh"
 #include "eval_quad.cuh"
 #include "step_fused.cuh"
 #include "step_quad.cuh"
@@ -84,7 +84,7 @@ struct OcpModule {
 
   static void dims(hb_ocp_dims* d) {
     d->nx = T::NX; d->nu = T::NU; d->N = T::N; d->nc = T::NC; d->nsp = T::NSP; d->ntp = T::NTP;
-    d->nuold = T::NUOLD; d->nap = T::NAP; d->stage_doubles = T::SD; d->elim_doubles = T::TD;
+    d->nuold = T::NUOLD; d->nap = T::NAP; d->stage_doubles = T::NA + T::NH; d->elim_doubles = T::TD;
     d->method = P::METHOD; d->fixed_x0 = P::FIXED_X0 ? 1 : 0; d->n_state = ST_COUNT;
   }
 
@@ -98,7 +98,7 @@ struct OcpModule {
     w += 7 * b * n1;                                                       // per-node scalars
     w += 2 * b * (size_t)n_alpha * n1;                                     // line-search table
     w += b * ST_COUNT + (b * n + 1) / 2 + 2 + 2;                           // state, node flags, poll counters
-    return w + 128;  // slack for the per-array 16-byte alignment padding
+    return w + 32 * 16 + 16;  // slack: every array starts on a 128-byte line (30 arrays), so does the first one
   }
 
   static int solve(const hb_ocp_call* c) {
@@ -118,7 +118,8 @@ struct OcpModule {
     a.status = c->status; a.iters = c->iters;
     const size_t b = (size_t)c->B, n1 = T::N + 1, n = T::N;
     double* w = c->work;
-    auto take = [&](size_t cnt) { double* p = w; w += (cnt + 1) & ~(size_t)1; return p; };  // keep 16-byte alignment
+    w += ((128 - (reinterpret_cast<uintptr_t>(w) & 127)) & 127) / 8;   // 128-byte lines: vector loads, L2 line prefetches
+    auto take = [&](size_t cnt) { double* p = w; w += (cnt + 15) & ~(size_t)15; return p; };
     a.zlx = take(b * n1 * T::NX); a.zux = take(b * n1 * T::NX);
     a.zlu = take(b * n * T::NU); a.zuu = take(b * n * T::NU);
     a.zlc = take(b * n * T::NC); a.zuc = take(b * n * T::NC);
@@ -159,29 +160,36 @@ struct OcpModule {
 #endif
       tm.end();
       tm.begin(K_RICCATI);
-#if HB_DEVICE_BUILD
+      // riccati_variant: 0 = one thread per instance (any size; the reference version of the sweep),
+      // >= 2 = the fastest sweep the problem admits: warp-per-instance tensor-pipe sweep (riccati6.cuh) for the
+      // operand-order layout (nx <= 4, nu <= 2, x0 fixed), the cp.async ring with 8 lanes per instance (riccati2.cuh)
+      // for the compact layout; 6 / 8 / 9 select the register-ring depth 4 / 5 / 3 of riccati6 instead of 2 (tuning runs)
       bool ric_done = false;
+      if (c->riccati_variant >= 2) {
+        int rc6 = -100;
+        auto try6 = [&](auto tag) {
+          using R = decltype(tag);
+          if constexpr (R::SUPPORTED) rc6 = launch_riccati6<R>(a, s);
+        };
+        switch (c->riccati_variant) {
+          case 6: try6(Riccati6<P, 4>{}); break;
+          case 8: try6(Riccati6<P, 5>{}); break;
+          case 9: try6(Riccati6<P, 3>{}); break;
+          default: try6(Riccati6<P, 2>{}); break;
+        }
+        if (rc6 > 0) return rc6;
+        ric_done = rc6 == 0;
+      }
+#if HB_DEVICE_BUILD
       if constexpr (RiccatiTma2<P>::SUPPORTED) {
-        if (c->riccati_variant >= 2) {
+        if (c->riccati_variant >= 2 && !ric_done) {
           cudaError_t e = launch_riccati_tma2<P>(a, s);
           if (e != cudaSuccess) return (int)e;
           ric_done = true;
         }
       }
-      if (ric_done) {
-      } else if constexpr (RiccatiTma<P>::SUPPORTED) {
-        if (c->riccati_variant != 0) {
-          cudaError_t e = launch_riccati_tma<P>(a, s);
-          if (e != cudaSuccess) return (int)e;
-        } else {
-          launch_1d<OcpRiccati<P>>(a, a.B, s);
-        }
-      } else {
-        launch_1d<OcpRiccati<P>>(a, a.B, s);
-      }
-#else
-      launch_1d<OcpRiccati<P>>(a, a.B, s);
 #endif
+      if (!ric_done) launch_1d<OcpRiccati<P>>(a, a.B, s);
       tm.end();
       bool fused = false;
 #if HB_DEVICE_BUILD

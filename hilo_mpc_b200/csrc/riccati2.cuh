@@ -1,7 +1,7 @@
 // Riccati sweep, sm_100a version 2.
 //
 // The whole batch is resident in one wave with ~2 warps per scheduler, so the kernel is bound by (1) how fast stage
-// blocks reach shared memory and (2) the dependent-latency chain of one stage.  Version 1 (riccati.cuh) loses on both:
+// blocks reach shared memory and (2) the dependent-latency chain of one stage.  Version 1 (one cp.async.bulk per block, removed) lost on both:
 //   (1) one cp.async.bulk per 224/320-byte block is a poor fit for the TMA unit - 64 tiny requests per SM and stage
 //       round are processed at ~30 cycles each, i.e. ~1900 cycles per round whatever the arithmetic does (ncu:
 //       profiles/ncu_riccati2_r1_summary.csv), and every per-instance mbarrier wait is G-way divergent;
@@ -19,10 +19,22 @@
 // Layout and traffic are those of version 1: LPI lanes per instance, lane g < NE owns column g, lane NE the gradient
 // column; gains stay in shared memory.
 #pragma once
-#include "riccati.cuh"
+#include "ocp_kernels.cuh"
 
 #if HB_DEVICE_BUILD
 namespace hb {
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+// 1/x for x > 0: hardware approximation refined by two Newton steps (full fp64 accuracy, no slow-path branch)
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
 
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
@@ -49,7 +61,7 @@ struct RiccatiTma2 {
   static constexpr int SMEM_BYTES = CW * G * STRIDE * 8;
   static constexpr int CHA = T::NAp / 2, CHH = T::NHp / 2;   // 16-byte chunks of the dynamics / Hessian part of a stage
   static constexpr bool SUPPORTED = (NE + 1 <= 32) && (NX <= 6) && (NU >= 1) && (NU <= 2) && (CW * G <= 32) &&
-                                    (SMEM_BYTES <= 110 * 1024) && (N >= NBUF);
+                                    (SMEM_BYTES <= 110 * 1024) && (N >= NBUF) && !T::FRAG;
 
   static __device__ __forceinline__ double gshfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src, LPI); }
   template <int M>

@@ -48,7 +48,7 @@ class HostOcp:
         self.lib.hbm_ocp_dims(C.byref(self.dims))
 
     def solve(self, x0, x, u, xc, xlb, xub, ulb, uub, dt, time0=0., sp=None, tp=None, uold=None, ap=None, tol=1e-8,
-              max_iter=200, n_alpha=8, mu_init=.1):
+              max_iter=200, n_alpha=8, mu_init=.1, riccati_variant=0):
         d = self.dims
         B = x.shape[0]
         f8 = lambda a, shape: np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(shape))
@@ -84,7 +84,7 @@ class HostOcp:
                        xlb=_dp(b[0]), xub=_dp(b[1]), ulb=_dp(b[2]), uub=_dp(b[3]), x=_dp(x), u=_dp(u), xc=_dp(xc),
                        lam=_dp(lam), status=status.ctypes.data_as(_IP), iters=iters.ctypes.data_as(_IP),
                        stats=_dp(stats), work=_dp(work), work_doubles=nwork, stream=None,
-                       n_iterations_launched=C.pointer(launched))
+                       n_iterations_launched=C.pointer(launched), riccati_variant=riccati_variant)
         rc = self.lib.hbm_ocp_solve(C.byref(call))
         if rc != 0:
             raise RuntimeError(f"hbm_ocp_solve returned {rc}")
