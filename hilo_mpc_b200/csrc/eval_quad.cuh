@@ -52,7 +52,10 @@ struct EvalQuad {
   // collocation points of lu / luu (SUM) are still needed.
   static constexpr int FSZ = NX + NX * NX + NX * NU;                             // f | fx | fu of one point
   static constexpr int LSZ = 1 + NX + NU + NX * NX + NU * NX + NU * NU;          // l | lx | lu | lxx | lux | luu (weighted)
-  static constexpr int NRED = NE * (NE + 1) + NE;    // partial Hessian/gradient [NE][NE+1] + multiplier-form gradient
+  // partial Hessian/gradient [NE][NE+1] + multiplier-form gradient of one lane; ODD stride between the lanes' copies:
+  // the quads of a warp sit on the even 8-byte bank pairs (SCR below), two lanes of a quad share a half-warp (lane
+  // mapping in run()), so the second lane must land on the odd ones
+  static constexpr int NRED = (NE * (NE + 1) + NE) | 1;
   static constexpr int FT = (D * FSZ > NC * (NE + 1)) ? D * FSZ : NC * (NE + 1);
   static constexpr int PBN = (2 * ((W + 1) & ~1) > NC) ? 2 * ((W + 1) & ~1) : NC;
   static constexpr int A1 = FT + PBN + D * LSZ, A2 = 4 * NRED;
@@ -68,8 +71,9 @@ struct EvalQuad {
   static constexpr int SMEM_BYTES = QUADS * SCR * 8;
   static constexpr bool EL_VEC2 = (NE % 2 == 0) && (T::oT % 2 == 0) && (T::TD % 2 == 0);
 
-  static __device__ __forceinline__ double qshfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m, 4); }
-  static __device__ __forceinline__ int qshfl_xor(int v, int m) { return __shfl_xor_sync(0xffffffffu, v, m, 4); }
+  // lanes q, q^m of the same quad (lane = q * 8 + quad-in-warp, see run())
+  static __device__ __forceinline__ double qshfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m << 3); }
+  static __device__ __forceinline__ int qshfl_xor(int v, int m) { return __shfl_xor_sync(0xffffffffu, v, m << 3); }
 
   // Gauss-Jordan on rows R[RPL][NCOLS] (row lr of lane q is global row lr*4 + q) with the STATIC pivot order
   // "row c for column c": no search, no row selection; the owner lane and its local row are compile-time constants.
@@ -125,7 +129,10 @@ struct EvalQuad {
 
   static __device__ void run(const OcpArgs& a) {
     extern __shared__ __align__(16) double smem[];
-    const int quad = threadIdx.x >> 2, q = threadIdx.x & 3;
+    // lane = q * 8 + quad-in-warp: the lanes with the same role q of the 8 quads of a warp are adjacent.  The pivot-row
+    // store of the elimination (one lane per quad, 128 bits) then comes from ONE quarter-warp = one shared-memory
+    // wavefront instead of four, and two (not four) lanes of a quad meet in a half-warp for the 64-bit accesses.
+    const int quad = ((threadIdx.x >> 5) << 3) | (threadIdx.x & 7), q = (threadIdx.x >> 3) & 3;
     const long long node = (long long)blockIdx.x * QUADS + quad;
     const long long total = (long long)a.B * N;
     const bool valid = node < total;
