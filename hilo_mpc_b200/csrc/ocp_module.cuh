@@ -135,7 +135,7 @@ struct OcpModule {
 
     static thread_local KernelTimer tm;
     tm.on = c->kernel_ms != nullptr; tm.s = s; tm.ms = c->kernel_ms; tm.count = c->kernel_count; tm.launches = 0;
-    tm.begin(K_INIT); launch_2d<OcpInit<P>>(a, a.B, T::N + 1, s); tm.end();
+    tm.begin(K_INIT); launch_2d<OcpInit<P>>(a, a.B, OcpInit<P>::ETOT, s); tm.end();
     // Host polling schedule: every check_every iterations, or - with a hint from the previous solve of the same closed
     // loop (first_check = iterations that one needed) - once after that many and then after every further iteration.
     const int check_every = c->check_every > 0 ? c->check_every : 4;
