@@ -68,6 +68,33 @@ struct StepQuad {
     double* red = smem + oRED;
     double* ctrl = smem + oCTRL;
 
+    // ------------------------------------------------------------------ early exit of a converged instance
+    // One launch in four (3-4 iterations per solve) only has to find out that its instance is done: the errors of the
+    // current point are known from the evaluation and the sweep, so the test comes before the 900 bytes per node
+    // of step data are touched.  Same decision and same stored state as the regular path below (ls_prelude).
+    {
+      double c1 = 0.0, phi = 0.0, cinf = 0.0, comp = 0.0;
+      if (node && q == 0) { c1 = a.s_c1[nb]; phi = a.s_phi[nb]; cinf = a.s_cinf[nb]; comp = a.s_comp[nb]; }
+      c1 = warp_sum(c1); phi = warp_sum(phi); cinf = warp_max(cinf); comp = warp_max(comp);
+      if (lane == 0) { red[3 * 32 + warp] = c1; red[4 * 32 + warp] = phi; red[5 * 32 + warp] = cinf; red[6 * 32 + warp] = comp; }
+      __syncthreads();
+      if (tid == 0) {
+        double rc1 = 0.0, rphi = 0.0, rcinf = 0.0, rcomp = 0.0;
+        for (int w = 0; w < WARPS; ++w) {
+          rc1 += red[96 + w]; rphi += red[128 + w]; rcinf = dmax(rcinf, red[160 + w]); rcomp = dmax(rcomp, red[192 + w]);
+        }
+        const double err = dmax(dmax(st[ST_EDUAL], rcinf), rcomp);
+        const bool done = (mu <= a.mu_min * (1.0 + 1e-12)) && (err <= a.tol);
+        if (done) { prep_store(st, 1.0, 1.0, 0.0, rc1, rphi, rcinf, rcomp); ls_prelude(a, st, b, mu, err); }
+        ctrl[C_FLAG] = done ? (double)F_STOP : (double)F_EVAL;
+      }
+      __syncthreads();
+      if ((int)ctrl[C_FLAG] == F_STOP) {
+        if (tid < ST_COUNT) stg[tid] = st[tid];
+        return;
+      }
+      __syncthreads();   // ctrl / red are rewritten below
+    }
     // ------------------------------------------------------------------ load the own variables
     // slot it holds variable e = 4 it + q of the node:  e < NX: x_k[e] | e < NX+NU: u_k[e-NX] | else X_k[e-NX-NU]
     double v[NVIT], d[NVIT], lb[NVIT], ub[NVIT], zl[NVIT], zu[NVIT];
