@@ -80,8 +80,10 @@ typedef struct hb_ocp_call {
   long long* n_kernel_launches; /* host out or NULL: kernels launched by this call                                 */
   double* kernel_ms;        /* host in/out [HB_OCP_KERNELS] or NULL: accumulates device ms per kernel (CUDA events) */
   long long* kernel_count;  /* host in/out [HB_OCP_KERNELS] or NULL: accumulates launches per kernel              */
-  int riccati_variant;      /* 2: TMA-staged sweep with producer warp and single-exchange stages (default where
-                               supported), 1: first TMA-staged version, 0: one-thread-per-instance sweep           */
+  int riccati_variant;      /* 0: one-thread-per-instance sweep (any size; the reference version of the sweep),
+                               >= 2: fastest sweep the problem admits (default): warp-per-instance sweep on the fp64
+                               tensor pipe for nx <= 4, nu <= 2, x0 fixed; cp.async ring with 8 lanes per instance
+                               otherwise; 6 / 8 / 9: register-ring depth 4 / 5 / 3 of the former (tuning runs)      */
   int warm_start;           /* 0: IPOPT-default start (push 1e-2 into the bounds, z = 1, mu = mu_init);
                                1: x/u/xc AND the bound multipliers kept in `work` by the previous call are reused,
                                   tiny push, mu = mu_init_warm (needs the same `work` buffer and batch as before)    */
