@@ -10,10 +10,11 @@ from .lmpc import LMPC
 from .mhe import MHE, MovingHorizonEstimator
 from .gp import GP, GaussianProcess, Kernel
 from .ann import ANN, Layer
+from .control_loop import SimpleControlLoop
 from .estimators import EKF, KF, PF, UKF, ExtendedKalmanFilter, KalmanFilter, ParticleFilter, UnscentedKalmanFilter
 
 pi = 3.141592653589793
 
 __all__ = ['Model', 'NMPC', 'LMPC', 'MHE', 'MovingHorizonEstimator', 'GP', 'GaussianProcess', 'Kernel', 'ANN', 'Layer',
            'KF', 'EKF', 'UKF', 'PF', 'KalmanFilter', 'ExtendedKalmanFilter', 'UnscentedKalmanFilter',
-           'ParticleFilter', 'symbolic', 'ca']
+           'ParticleFilter', 'SimpleControlLoop', 'symbolic', 'ca']

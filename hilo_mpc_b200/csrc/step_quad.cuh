@@ -95,6 +95,17 @@ struct StepQuad {
       }
       __syncthreads();   // ctrl / red are rewritten below
     }
+#ifndef HB_STEPQ_PREFETCH
+#define HB_STEPQ_PREFETCH 1
+#endif
+    // the 816-byte elimination block of the node (written two kernels ago, mostly in HBM by now): its seven 128-byte
+    // lines are requested up front by the four lanes of the node, so that the dependent loads below find them on chip
+    if (HB_STEPQ_PREFETCH && inter) {
+      const char* eb = reinterpret_cast<const char*>(el);
+      constexpr int ELB = T::TD * 8;
+      if (q * 256 < ELB) asm volatile("prefetch.global.L2 [%0];" ::"l"(eb + q * 256));
+      if (q * 256 + 128 < ELB) asm volatile("prefetch.global.L2 [%0];" ::"l"(eb + q * 256 + 128));
+    }
     // ------------------------------------------------------------------ load the own variables
     // slot it holds variable e = 4 it + q of the node:  e < NX: x_k[e] | e < NX+NU: u_k[e-NX] | else X_k[e-NX-NU]
     double v[NVIT], d[NVIT], lb[NVIT], ub[NVIT], zl[NVIT], zu[NVIT];
