@@ -6,7 +6,9 @@ Mirrors ``hilo_mpc/modules/machine_learning/gp/gp.py`` (``GaussianProcess`` :112
 ``hb_gp_fit`` / ``hb_gp_predict`` kernels (Gram, blocked Cholesky with fp64 tensor-core trailing updates, ``L^-1 K*`` on
 the tensor pipe); symbolic queries (``predict(x_sym)``, which is how the reference embeds a GP into a ``Model``,
 ``dynamic_model.py:3040-3080``) return the posterior mean/variance as expressions of the fitted numbers.
-Hyper-parameter training (``fit_model``) is a "next" row and not implemented.
+Hyper-parameter training (``fit_model``, gp.py:660-697): the negative log marginal likelihood and its
+analytic gradient are evaluated on the device (``hb_gp_fit`` for the factorisation, the trace terms as device matrix
+products), the quasi-Newton iteration over the handful of log-hyper-parameters runs on the host.
 """
 from __future__ import annotations
 
@@ -154,9 +156,72 @@ class GaussianProcess:
                          alpha_host=alpha.cpu().numpy(), dev=dev)
         self._is_setup = True
 
-    def fit_model(self, *args, **kwargs):
-        raise NotImplementedError("Hyper-parameter training is not part of the B200 hot path yet (SURVEY.md §8f-3); set "
-                                  "the hyper-parameters and call setup()")
+    @property
+    def hyperparameters(self):
+        """``[noise_variance, length_scales, signal_variance]`` as objects with ``name`` / ``value`` (the order of the
+        reference's list, gp.py:215-240; tests/test_GPs.py:846-849 reads ``[p.value for p in gp.hyperparameters]``)."""
+        from types import SimpleNamespace as NS
+        ls = self.kernel.length_scales
+        return [NS(name='GP.noise_variance', value=self.noise_variance),
+                NS(name='SE.length_scales', value=float(ls[0]) if ls.size == 1 else ls.copy()),
+                NS(name='SE.signal_variance', value=self.kernel.signal_variance)]
+
+    def _nlml_and_grad(self, theta, free, base):
+        """Negative LML and its gradient w.r.t. the free log-hyper-parameters: factorisation by ``hb_gp_fit`` (setup),
+        ``dNLML/dtheta_j = 1/2 tr((K^-1 - alpha alpha^T) dK/dtheta_j)`` as device matrix products."""
+        torch = _lib.require_cuda()
+        full = base.copy()
+        full[free] = theta
+        d = self._X.shape[0]
+        nl = self.kernel.length_scales.size
+        if free[0]:                                      # fixed values are not passed through log/exp
+            self.noise_variance = float(np.exp(full[0]))
+        if free[1:1 + nl].any():
+            self.kernel.length_scales = np.where(free[1:1 + nl], np.exp(full[1:1 + nl]), self.kernel.length_scales)
+        if free[1 + nl]:
+            self.kernel.signal_variance = float(np.exp(full[1 + nl]))
+        try:
+            self.setup()
+        except RuntimeError:   # not positive definite at this trial point: reject the step
+            return 1e300, np.zeros_like(theta)
+        fit = self._fit
+        X, Linv, alpha = fit['X'], fit['Linv'], fit['alpha']
+        W = Linv.T @ Linv - torch.outer(alpha, alpha)
+        ls = self.kernel.length_scale_vector(d)
+        D2 = ((X[:, :, None] - X[:, None, :]) / fit['ls'][:, None, None]) ** 2      # (d, n, n)
+        WK = W * (self.kernel.signal_variance * torch.exp(-.5 * D2.sum(0)))
+        g = np.empty(full.size)
+        g[0] = .5 * self.noise_variance * float(torch.trace(W).item())
+        if nl == 1:
+            g[1] = .5 * float((WK * D2.sum(0)).sum().item())
+        else:
+            g[1:1 + nl] = .5 * (WK[None] * D2).sum(dim=(1, 2)).cpu().numpy()
+        g[1 + nl] = .5 * float(WK.sum().item())
+        del ls
+        return -fit['lml'], g[free]
+
+    def fit_model(self, fixed: Sequence[str] = (), maxiter: int = 500) -> None:
+        """Optimise the hyper-parameters by minimising the negative log marginal likelihood (gp.py:660-697), starting from
+        the current values.  ``fixed``: names out of ``'noise_variance'``, ``'length_scales'``, ``'signal_variance'`` that
+        keep their values (the reference's ``prior = 'Delta'`` / ``'fixed'`` bounds)."""
+        if not self._is_setup:
+            raise RuntimeError("The GP has not been set up yet. Please run the setup() method before fitting.")
+        import scipy.optimize as sopt
+        nl = self.kernel.length_scales.size
+        base = np.concatenate([[np.log(self.noise_variance)], np.log(self.kernel.length_scales),
+                               [np.log(self.kernel.signal_variance)]])
+        names = ['noise_variance'] + ['length_scales'] * nl + ['signal_variance']
+        unknown = [f for f in fixed if f not in names]
+        if unknown:
+            raise ValueError(f"Unknown hyper-parameter name(s) {unknown}")
+        free = np.array([n not in fixed for n in names])
+        if not free.any():
+            return
+        res = sopt.minimize(self._nlml_and_grad, base[free], args=(free, base), jac=True, method='L-BFGS-B',
+                            options=dict(maxiter=maxiter, ftol=1e-15, gtol=1e-10))
+        self._nlml_and_grad(res.x, free, base)   # leaves the fitted hyper-parameters and the factorisation in place
+        self._optimization_stats = dict(success=bool(res.success) or res.status == 2, message=str(res.message),
+                                        iterations=int(res.nit), nlml=float(res.fun))
 
     def log_marginal_likelihood(self) -> float:
         if not self._is_setup:

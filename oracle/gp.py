@@ -46,3 +46,65 @@ class GpOracle:
         if not noise_free:
             var = var + self.hyp['noise_variance']  # gp.py:709-712
         return mu, var
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Hyper-parameter training (gp.py:660-697: minimise the negative log marginal likelihood over the logs of the
+# hyper-parameters; inference.py:211-217).  Pinned by the gpml values of tests/test_GPs.py:846-849 (SE kernel, 20 points
+# from the LCG generator of tests/test_GPs.py:1173-1199, restated below as a data generator).
+def lcg_randn(seed, shape):
+    """Normal variates of the reference's test-data generator (tests/test_GPs.py:1173-1199): Lehmer LCG + Box-Muller."""
+    n = int(np.prod(shape))
+    N = int(np.ceil(n / 2) * 2)
+    a, m = 7 ** 5, 2 ** 31 - 1
+    q, r = np.fix(m / a), np.remainder(m, a)
+    u = np.zeros(N + 1)
+    u[0] = np.fix(seed * 2 ** 31)
+    for k in range(1, N + 1):
+        u[k] = a * np.remainder(u[k - 1], q) - r * np.fix(u[k - 1] / q)
+        if u[k] < 0.:
+            u[k] += m
+    u = u[1:N + 1] / (2 ** 31)
+    N2 = N // 2
+    w = np.sqrt(-2 * np.log(u[:N2]))
+    x = np.concatenate([w * np.cos(2 * np.pi * u[N2:N]), w * np.sin(2 * np.pi * u[N2:N])])
+    return np.reshape(x[:n], shape)
+
+
+def nlml_and_grad(theta, X, y, mean=0., ard=False):
+    """Negative LML and its gradient w.r.t. theta = [log noise_variance, log length_scale(s), log signal_variance]:
+    dNLML/dtheta_j = 1/2 tr((K^-1 - alpha alpha^T) dK/dtheta_j) (Rasmussen & Williams eq. 5.9)."""
+    X = np.atleast_2d(np.asarray(X, dtype=float))
+    y = np.asarray(y, dtype=float).reshape(-1)
+    d, n = X.shape
+    nl = d if ard else 1
+    sn2, ls, sf2 = np.exp(theta[0]), np.exp(theta[1:1 + nl]), np.exp(theta[1 + nl])
+    lsv = np.broadcast_to(ls, (d,))
+    D2 = ((X[:, :, None] - X[:, None, :]) / lsv[:, None, None]) ** 2        # (d, n, n)
+    Kse = sf2 * np.exp(-.5 * D2.sum(0))
+    L = np.linalg.cholesky(Kse + sn2 * np.eye(n))
+    alpha = sla.cho_solve((L, True), y - mean)
+    nlml = .5 * (y - mean) @ alpha + np.log(np.diag(L)).sum() + n / 2 * np.log(2 * np.pi)
+    W = sla.cho_solve((L, True), np.eye(n)) - np.outer(alpha, alpha)
+    g = np.empty_like(theta)
+    g[0] = .5 * sn2 * np.trace(W)
+    if ard:
+        for k in range(d):
+            g[1 + k] = .5 * (W * Kse * D2[k]).sum()
+    else:
+        g[1] = .5 * (W * Kse * D2.sum(0)).sum()
+    g[1 + nl] = .5 * (W * Kse).sum()
+    return float(nlml), g
+
+
+def fit_hyperparameters(X, y, noise_variance=1., length_scales=1., signal_variance=1., mean=0., ard=False):
+    """Returns (noise_variance, length_scales, signal_variance) at the minimiser of the negative LML (L-BFGS on the logs,
+    started from the given values)."""
+    import scipy.optimize as sopt
+    d = np.atleast_2d(X).shape[0]
+    ls0 = np.broadcast_to(np.asarray(length_scales, dtype=float).reshape(-1), (d if ard else 1,))
+    th0 = np.concatenate([[np.log(noise_variance)], np.log(ls0), [np.log(signal_variance)]])
+    res = sopt.minimize(nlml_and_grad, th0, args=(X, y, mean, ard), jac=True, method='L-BFGS-B',
+                        options=dict(maxiter=500, ftol=1e-15, gtol=1e-10))
+    th = res.x
+    return float(np.exp(th[0])), np.exp(th[1:-1]), float(np.exp(th[-1])), res

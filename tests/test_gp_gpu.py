@@ -83,3 +83,33 @@ def test_gp_inside_nmpc_matches_oracle(cuda_device):
     u_true = true_nmpc.optimize(torch.tensor(x0, device=cuda_device))
     rel = ((u0 - u_true).abs() / torch.tensor(us, device=cuda_device)).max().item()
     assert rel < 0.02 * (u_true.abs() / torch.tensor(us, device=cuda_device)).max().item() + 0.02
+
+
+def test_gp_fit_model_reproduces_gpml_golden(cuda_device):
+    """Hyper-parameter training: tests/test_GPs.py:833-849 - 20 points from the reference's LCG
+    generator, default SE kernel and start values, fitted [noise_variance, length_scale, signal_variance] must equal the
+    gpml toolbox values to rtol 1e-5; the same through the oracle, and a fixed hyper-parameter stays put."""
+    from hilo_mpc_b200.gp import GP
+    from oracle.gp import fit_hyperparameters, lcg_randn
+    x = lcg_randn(.8, (20, 1))
+    y = np.sin(3 * x) + .1 * lcg_randn(.9, (20, 1))
+    gp = GP(['x'], ['y'])
+    gp.set_training_data(x.T, y.T)
+    gp.setup()
+    lml0 = gp.log_marginal_likelihood()
+    gp.fit_model()
+    vals = [p.value for p in gp.hyperparameters]
+    np.testing.assert_allclose(vals, [.0085251, .5298217, .8114553], rtol=1e-5)
+    sn2, ls, sf2, res = fit_hyperparameters(x.T, y.T)
+    np.testing.assert_allclose(vals, [sn2, ls[0], sf2], rtol=1e-6)
+    assert gp.log_marginal_likelihood() > lml0
+    np.testing.assert_allclose(gp.log_marginal_likelihood(), -res.fun, rtol=1e-10)
+    # predictions use the fitted values
+    mean, var = gp.predict(np.linspace(-3, 3, 61).reshape(1, -1))
+    assert np.isfinite(mean).all() and (var > 0).all()
+    gp2 = GP(['x'], ['y'], noise_variance=.1 ** 2)
+    gp2.set_training_data(x.T, y.T)
+    gp2.setup()
+    gp2.fit_model(fixed=('noise_variance',))
+    assert gp2.noise_variance == .1 ** 2
+    assert gp2.log_marginal_likelihood() <= gp.log_marginal_likelihood() + 1e-9

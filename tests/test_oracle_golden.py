@@ -94,3 +94,11 @@ def test_pf_resampling_matches_numpy_choice():
         np.random.seed(1234)
         u = np.random.random_sample(n)
         np.testing.assert_array_equal(est.pf_resample_indices(q, u), ref)
+
+
+def test_gp_fitted_hyperparameters_golden():  # tests/test_GPs.py:833-849: gpml values for the SE kernel, rtol 1e-5
+    from oracle.gp import fit_hyperparameters, lcg_randn
+    x = lcg_randn(.8, (20, 1))
+    y = np.sin(3 * x) + .1 * lcg_randn(.9, (20, 1))
+    sn2, ls, sf2, _ = fit_hyperparameters(x.T, y.T)
+    np.testing.assert_allclose([sn2, ls[0], sf2], [.0085251, .5298217, .8114553], rtol=1e-5)
