@@ -134,10 +134,10 @@ struct EvalQuad {
     // wavefront instead of four, and two (not four) lanes of a quad meet in a half-warp for the 64-bit accesses.
     const int quad = ((threadIdx.x >> 5) << 3) | (threadIdx.x & 7), q = (threadIdx.x >> 3) & 3;
     const long long node = (long long)blockIdx.x * QUADS + quad;
-    const long long total = (long long)a.B * N;
+    const long long total = (long long)a.n_instances() * N;   // late iterations run over the list of active instances
     const bool valid = node < total;
     const long long nn = valid ? node : (total - 1);
-    const int b = (int)(nn / N), k = (int)(nn % N);
+    const int b = a.instance((int)(nn / N)), k = (int)(nn % N);
     const double* st = a.st + (long long)b * ST_COUNT;
     const bool active = valid && st[ST_ACTIVE] != 0.0;
     // a whole warp (8 nodes) leaves together; partially active warps compute everything and mask the stores
@@ -540,7 +540,7 @@ inline cudaError_t launch_eval_quad(const OcpArgs& a, cudaStream_t s) {
   using E = EvalQuad<P>;
   cudaError_t e = cudaFuncSetAttribute(eval_quad_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, E::SMEM_BYTES);
   if (e != cudaSuccess) return e;
-  const long long nodes = (long long)a.B * OcpT<P>::N;
+  const long long nodes = (long long)a.n_instances() * OcpT<P>::N;
   const int grid = (int)((nodes + E::QUADS - 1) / E::QUADS);
   eval_quad_kernel<P><<<grid, 128, E::SMEM_BYTES, s>>>(a);
   launch_1d<OcpEvalTerminal<P>>(a, a.B, s);

@@ -11,14 +11,15 @@
 
 namespace hb {
 
-struct OcpCount {  // (b): poll[0] = instances still active, poll[1] = largest iteration count of the batch
+struct OcpCount {  // (b): poll[0] = instances still active (their indices appended to alist, in any order), poll[1] =
+                   // largest iteration count of the batch
   static HB_HD void run(const OcpArgs& a, int b) {
     const int it = a.iters[b];
 #if HB_DEVICE_BUILD && defined(__CUDA_ARCH__)
-    if (a.st[(long long)b * ST_COUNT + ST_ACTIVE] != 0.0) atomicAdd(a.poll, 1);
+    if (a.st[(long long)b * ST_COUNT + ST_ACTIVE] != 0.0) a.alist[atomicAdd(a.poll, 1)] = b;
     if (it > a.poll[1]) atomicMax(a.poll + 1, it);
 #else
-    if (a.st[(long long)b * ST_COUNT + ST_ACTIVE] != 0.0) a.poll[0] += 1;
+    if (a.st[(long long)b * ST_COUNT + ST_ACTIVE] != 0.0) { a.alist[a.poll[0]] = b; a.poll[0] += 1; }
     if (it > a.poll[1]) a.poll[1] = it;
 #endif
   }
@@ -97,7 +98,7 @@ struct OcpModule {
     w += b * n1 * T::NX + b * n * T::NU + b * n * T::NC;                   // dx, du, dxc
     w += 7 * b * n1;                                                       // per-node scalars
     w += 2 * b * (size_t)n_alpha * n1;                                     // line-search table
-    w += b * ST_COUNT + (b * n + 1) / 2 + 2 + 2;                           // state, node flags, poll counters
+    w += b * ST_COUNT + (b * n + 1) / 2 + 2 + 2 + (b + 1) / 2 + 1;         // state, node flags, poll counters, active list
     return w + 32 * 16 + 16;  // slack: every array starts on a 128-byte line (30 arrays), so does the first one
   }
 
@@ -131,6 +132,8 @@ struct OcpModule {
     a.st = take(b * ST_COUNT);
     a.nflag = reinterpret_cast<int*>(take((b * n + 1) / 2 + 1));
     a.poll = reinterpret_cast<int*>(take(2));
+    a.alist = reinterpret_cast<int*>(take((b + 1) / 2 + 1));
+    a.n_list = 0;
     cudaStream_t s = (cudaStream_t)c->stream;
 
     static thread_local KernelTimer tm;
@@ -138,9 +141,12 @@ struct OcpModule {
     tm.begin(K_INIT); launch_2d<OcpInit<P>>(a, a.B, OcpInit<P>::ETOT, s); tm.end();
     // Host polling schedule: every check_every iterations, or - with a hint from the previous solve of the same closed
     // loop (first_check = iterations that one needed) - once after that many and then after every further iteration.
+    // With compaction the first poll comes one iteration earlier: the last iterations of a solve belong to a few
+    // stragglers (8 % of the instances in the BASELINE loop), and a launch over the whole batch costs half of a full one
+    // however few are active, whereas a launch over the list costs about the latency of one CTA.
     const int check_every = c->check_every > 0 ? c->check_every : 4;
     const int hint = (c->first_check > 0 && c->first_check <= 64) ? c->first_check : 0;
-    int next_check = hint > 0 ? hint : check_every;
+    int next_check = hint > 0 ? ((c->no_compaction == 0 && hint > 2) ? hint - 1 : hint) : check_every;
     int launched = 0, needed = 0, single_polls = 0;
     for (int it = 0; it <= c->max_iter; ++it) {
       tm.begin(K_EVAL);
@@ -243,6 +249,8 @@ struct OcpModule {
 #endif
         needed = poll[1] + 1;  // the iteration after the last step is the one that detects convergence
         if (poll[0] == 0) break;
+        // stragglers: run the following iterations over the list of active instances the count kernel just wrote
+        a.n_list = (c->no_compaction == 0 && 2 * poll[0] <= a.B) ? poll[0] : 0;
         if (hint > 0 && single_polls < 3) { next_check = launched + 1; ++single_polls; }
         else next_check = launched + check_every;
       }

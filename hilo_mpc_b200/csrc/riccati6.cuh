@@ -252,8 +252,9 @@ struct Riccati6 {
     double* smem = wp::dyn_smem();
     const int warp = wp::tid() >> 5, lane = wp::tid() & 31;
     const int gid = lane >> 2, tig = lane & 3, g4 = gid & 3;
-    const int b = wp::bid() * CW + warp;
-    if (b >= a.B) return;                               // warp-uniform
+    const int bi = wp::bid() * CW + warp;
+    if (bi >= a.n_instances()) return;                  // warp-uniform
+    const int b = a.instance(bi);                       // late iterations run over the list of active instances
     double* st = a.st + (long long)b * ST_COUNT;
     if (st[ST_ACTIVE] == 0.0) return;
 
@@ -373,7 +374,7 @@ __global__ void __launch_bounds__(R::THREADS, 7) riccati6_kernel(OcpArgs a) { R:
 
 template <class R>
 inline int launch_riccati6(const OcpArgs& a, cudaStream_t s) {
-  const int grid = (a.B + R::CW - 1) / R::CW;
+  const int grid = (a.n_instances() + R::CW - 1) / R::CW;
 #if HB_DEVICE_BUILD
   cudaError_t e = cudaFuncSetAttribute(riccati6_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, R::SMEM_BYTES);
   if (e != cudaSuccess) return (int)e;

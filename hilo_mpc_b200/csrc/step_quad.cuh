@@ -53,7 +53,7 @@ struct StepQuad {
 
   static __device__ void run(const OcpArgs& a) {
     __shared__ __align__(16) double smem[SMEM];
-    const int b = blockIdx.x, tid = threadIdx.x, k = tid >> 2, q = tid & 3, warp = tid >> 5, lane = tid & 31;
+    const int b = a.instance(blockIdx.x), tid = threadIdx.x, k = tid >> 2, q = tid & 3, warp = tid >> 5, lane = tid & 31;
     double* stg = a.st + (long long)b * ST_COUNT;
     if (stg[ST_ACTIVE] == 0.0) return;   // uniform over the CTA
     // the per-instance solver state is edited by thread 0 between the phases: work on a shared-memory copy (one
@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(StepQuad<P>::THREADS, HB_STEPQ_MINB) step_quad
 
 template <class P>
 inline cudaError_t launch_step_quad(const OcpArgs& a, cudaStream_t s) {
-  step_quad_kernel<P><<<a.B, StepQuad<P>::THREADS, 0, s>>>(a);
+  step_quad_kernel<P><<<a.n_instances(), StepQuad<P>::THREADS, 0, s>>>(a);
   return cudaGetLastError();
 }
 

@@ -199,6 +199,7 @@ class DynamicOptimization:
                     mu_init_warm=float(o.get('b200.warm_start_mu', 1e-4)),
                     eval_variant=int(o.get('b200.eval_variant', 1)),
                     step_variant=int(o.get('b200.step_variant', 2)),
+                    compaction=bool(int(o.get('b200.compaction', 1))),
                     adaptive_poll=bool(o.get('b200.adaptive_poll', True)))
 
     def is_setup(self) -> bool:

@@ -96,6 +96,8 @@ typedef struct hb_ocp_call {
   int step_variant;         /* expand / line search / apply of one iteration: 2: one kernel, one CTA per instance,
                                4 lanes per node, iterate register-resident (default where supported); 1: one kernel,
                                one thread per node; 0: separate kernels                                            */
+  int no_compaction;        /* 0 (default): once a poll finds at most half of the batch active, the node / sweep / step
+                               kernels run over the list of those instances; 1: always over the whole batch        */
 } hb_ocp_call;
 
 /* kernel indices of kernel_ms / kernel_count */
