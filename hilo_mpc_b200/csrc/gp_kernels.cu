@@ -18,9 +18,12 @@
 namespace {
 
 // ------------------------------------------------------------------------------------------------ covariance
-// C[i][j] = sf2 * exp(-0.5 * sum_k ((A[k][i] - B[k][j]) / ls[k])^2) (+ noise on the diagonal when A == B)
-__global__ void se_cov_kernel(int d, int na, int nb, const double* __restrict__ A, const double* __restrict__ Bm,
-                              const double* __restrict__ ls, double sf2, double noise, double* __restrict__ C, int ldc) {
+// C[i][j] = sf2 * g(r) with r^2 = sum_k ((A[k][i] - B[k][j]) / ls[k])^2 (+ noise on the diagonal when A == B);
+// kind 0: squared exponential g = exp(-r^2/2) (kernel.py:650-734); Matern family (kernel.py:783-826, d = sqrt(2 nu) r):
+// 1: exponential (nu = 1/2) g = exp(-r), 2: Matern 3/2 g = (1 + d) exp(-d), 3: Matern 5/2 g = (1 + d + d^2/3) exp(-d)
+__global__ void se_cov_kernel(int kind, int d, int na, int nb, const double* __restrict__ A,
+                              const double* __restrict__ Bm, const double* __restrict__ ls, double sf2, double noise,
+                              double* __restrict__ C, int ldc) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const int i = blockIdx.y;
   if (j >= nb) return;
@@ -29,7 +32,15 @@ __global__ void se_cov_kernel(int d, int na, int nb, const double* __restrict__ 
     const double r = (A[(size_t)k * na + i] - Bm[(size_t)k * nb + j]) / ls[k];
     d2 += r * r;
   }
-  double v = sf2 * exp(-0.5 * d2);
+  double v;
+  if (kind == 0) {
+    v = sf2 * exp(-0.5 * d2);
+  } else {
+    const double r = sqrt(d2);
+    if (kind == 1) v = sf2 * exp(-r);
+    else if (kind == 2) { const double t = 1.7320508075688772 * r; v = sf2 * (1.0 + t) * exp(-t); }
+    else { const double t = 2.23606797749979 * r; v = sf2 * (1.0 + t + t * t * (1.0 / 3.0)) * exp(-t); }
+  }
   if (noise != 0.0 && i == j) v += noise;
   C[(size_t)i * ldc + j] = v;
 }
@@ -239,12 +250,20 @@ size_t hb_gp_fit_work_doubles(int n) { return (size_t)n * 2 + 8; }
 int hb_gp_fit(int n, int d, const double* X, const double* y, const double* length_scales, double signal_variance,
               double noise_variance, double prior_mean, double* L, double* Linv, double* alpha, double* lml,
               double* work, int* info, void* stream) {
+  return hb_gp_fit_kernel(0, n, d, X, y, length_scales, signal_variance, noise_variance, prior_mean, L, Linv, alpha,
+                          lml, work, info, stream);
+}
+
+int hb_gp_fit_kernel(int kind, int n, int d, const double* X, const double* y, const double* length_scales,
+                     double signal_variance, double noise_variance, double prior_mean, double* L, double* Linv,
+                     double* alpha, double* lml, double* work, int* info, void* stream) {
+  if (kind < 0 || kind > 3) return -1;
   if (n <= 0 || d <= 0 || !X || !y || !length_scales || !L || !Linv || !alpha || !lml || !work || !info) return -1;
   cudaStream_t s = (cudaStream_t)stream;
   cudaMemsetAsync(info, 0, sizeof(int), s);
   {
     dim3 grid((n + 127) / 128, n);
-    se_cov_kernel<<<grid, 128, 0, s>>>(d, n, n, X, X, length_scales, signal_variance, noise_variance, L, n);
+    se_cov_kernel<<<grid, 128, 0, s>>>(kind, d, n, n, X, X, length_scales, signal_variance, noise_variance, L, n);
   }
   for (int j0 = 0; j0 < n; j0 += NB) {
     const int nb = (n - j0 < NB) ? (n - j0) : NB;
@@ -278,13 +297,21 @@ size_t hb_gp_predict_work_doubles(int n, int M) { return (size_t)2 * n * M + 8; 
 int hb_gp_predict(int n, int d, int M, const double* X, const double* Xq, const double* length_scales,
                   double signal_variance, double noise_variance, double prior_mean, const double* Linv,
                   const double* alpha, double* mean, double* var, double* work, void* stream) {
+  return hb_gp_predict_kernel(0, n, d, M, X, Xq, length_scales, signal_variance, noise_variance, prior_mean, Linv,
+                              alpha, mean, var, work, stream);
+}
+
+int hb_gp_predict_kernel(int kind, int n, int d, int M, const double* X, const double* Xq, const double* length_scales,
+                         double signal_variance, double noise_variance, double prior_mean, const double* Linv,
+                         const double* alpha, double* mean, double* var, double* work, void* stream) {
+  if (kind < 0 || kind > 3) return -1;
   if (n <= 0 || d <= 0 || M <= 0 || !X || !Xq || !length_scales || !alpha || !mean || !work) return -1;
   if (var != nullptr && Linv == nullptr) return -1;
   cudaStream_t s = (cudaStream_t)stream;
   double* Ks = work;                  // [n][M] cross covariance
   double* V = work + (size_t)n * M;   // [n][M] L^-1 K*
   dim3 grid((M + 127) / 128, n);
-  se_cov_kernel<<<grid, 128, 0, s>>>(d, n, M, X, Xq, length_scales, signal_variance, 0.0, Ks, M);
+  se_cov_kernel<<<grid, 128, 0, s>>>(kind, d, n, M, X, Xq, length_scales, signal_variance, 0.0, Ks, M);
   if (var != nullptr) dgemm_dmma(n, M, n, 1.0, Linv, n, Ks, M, 0, 0.0, V, M, 0, 1, s);
   predict_reduce_kernel<<<(M + 127) / 128, 128, 0, s>>>(n, M, Ks, var ? V : nullptr, alpha, prior_mean,
                                                         signal_variance, noise_variance, mean, var);

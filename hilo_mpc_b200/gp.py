@@ -1,4 +1,5 @@
-"""Gaussian-process regression with the reference's API (squared-exponential kernel, exact inference) on the GPU.
+"""Gaussian-process regression with the reference's API (squared-exponential and Matern kernels, exact inference) on the
+GPU.
 
 Mirrors ``hilo_mpc/modules/machine_learning/gp/gp.py`` (``GaussianProcess`` :112, ``set_training_data`` :378, ``setup``
 :522, ``predict`` :699, ``log_marginal_likelihood`` :653, ``noise_variance`` :302) and ``kernel.py``
@@ -22,8 +23,13 @@ from . import _lib
 from . import symbolic as sx
 
 
-class SquaredExponentialKernel:
+class StationaryKernel:
+    """Covariance functions of ``r^2 = sum_k ((x_k - x'_k) / l_k)^2`` (kernel.py:488-563): squared exponential
+    (:704-734) and the Matern family with half-integer ``nu`` (:737-917).  ``kind`` is the index the device kernels use
+    (``hb_gp_fit_kernel``); ``g_h`` returns the value ``g(r)`` and the factor ``h(r)`` of the length-scale derivative
+    ``dK/dlog l_k = sigma_f^2 h(r) D2_k`` (both for NumPy arrays and device tensors)."""
     acronym = 'SE'
+    kind = 0
 
     def __init__(self, active_dims=None, signal_variance=1., length_scales=1., ard=False, bounds=None):
         self.active_dims = None if active_dims is None else list(active_dims)
@@ -39,15 +45,48 @@ class SquaredExponentialKernel:
             raise ValueError("Length scales vector dimension does not equal input space dimension.")
         return ls.copy()
 
+    def g_h(self, r2, xp=np):
+        sq = xp.sqrt
+        if self.kind == 0:
+            g = xp.exp(-.5 * r2)
+            return g, g
+        r = sq(r2)
+        if self.kind == 1:
+            g = xp.exp(-r)
+            return g, xp.where(r > 0., g / xp.where(r > 0., r, xp.ones_like(r)), xp.zeros_like(r))
+        if self.kind == 2:
+            d = 3. ** .5 * r
+            e = xp.exp(-d)
+            return (1. + d) * e, 3. * e
+        d = 5. ** .5 * r
+        e = xp.exp(-d)
+        return (1. + d + d * d / 3.) * e, 5. / 3. * (1. + d) * e
+
     def __call__(self, X, X_bar=None):
-        """Numeric covariance matrix (kernel.py:97-140) — small host-side helper used by tests / set-up code."""
+        """Numeric covariance matrix (kernel.py:97-140) - small host-side helper used by tests / set-up code."""
         X = np.atleast_2d(np.asarray(X, dtype=float))
         Xb = X if X_bar is None else np.atleast_2d(np.asarray(X_bar, dtype=float))
         if X.shape[0] != Xb.shape[0]:
             raise AssertionError("X and X_bar do not have the same input space dimensions")
         ls = self.length_scale_vector(X.shape[0])
         d2 = (((X[:, :, None] - Xb[:, None, :]) / ls[:, None, None]) ** 2).sum(0)
-        return self.signal_variance * np.exp(-.5 * d2)
+        return self.signal_variance * self.g_h(d2)[0]
+
+
+class SquaredExponentialKernel(StationaryKernel):
+    acronym, kind = 'SE', 0
+
+
+class ExponentialKernel(StationaryKernel):      # kernel.py:829-856 (Matern with p = 0)
+    acronym, kind = 'E', 1
+
+
+class Matern32Kernel(StationaryKernel):         # kernel.py:859-886
+    acronym, kind = 'M32', 2
+
+
+class Matern52Kernel(StationaryKernel):         # kernel.py:889-916
+    acronym, kind = 'M52', 3
 
 
 class Kernel:
@@ -56,14 +95,26 @@ class Kernel:
         return SquaredExponentialKernel(active_dims, signal_variance, length_scales, ard, bounds)
 
     @staticmethod
+    def exponential(active_dims=None, signal_variance=1., length_scales=1., ard=False, bounds=None):
+        return ExponentialKernel(active_dims, signal_variance, length_scales, ard, bounds)
+
+    @staticmethod
+    def matern_32(active_dims=None, signal_variance=1., length_scales=1., ard=False, bounds=None):
+        return Matern32Kernel(active_dims, signal_variance, length_scales, ard, bounds)
+
+    @staticmethod
+    def matern_52(active_dims=None, signal_variance=1., length_scales=1., ard=False, bounds=None):
+        return Matern52Kernel(active_dims, signal_variance, length_scales, ard, bounds)
+
+    @staticmethod
     def _unsupported(name):
         def factory(*args, **kwargs):
             raise NotImplementedError(f"Kernel '{name}' is not supported by the B200 engine yet (SURVEY.md §2 row 7: "
-                                      f"only the squared-exponential kernel is on the hot path)")
+                                      f"only the squared-exponential and Matern kernels are on the hot path)")
         return factory
 
 
-for _name in ('matern_32', 'matern_52', 'exponential', 'rational_quadratic', 'periodic', 'linear', 'polynomial',
+for _name in ('rational_quadratic', 'periodic', 'linear', 'polynomial',
               'constant', 'neural_network', 'gamma_exponential', 'piecewise_polynomial', 'dot_product'):
     setattr(Kernel, _name, staticmethod(Kernel._unsupported(_name)))
 
@@ -77,8 +128,8 @@ class GaussianProcess:
             raise ValueError("Training a GP on multiple labels is not supported. Please use 'GPArray'.")  # gp.py:133-135
         self.labels = labels
         self.kernel = kernel if kernel is not None else Kernel.squared_exponential()
-        if not isinstance(self.kernel, SquaredExponentialKernel):
-            raise NotImplementedError("Only the squared-exponential kernel is supported by the B200 engine")
+        if not isinstance(self.kernel, StationaryKernel):
+            raise NotImplementedError("Only the squared-exponential and Matern kernels are supported by the B200 engine")
         self.prior_mean = 0. if mean is None else float(mean)
         self.noise_variance = float(noise_variance)
         self.id, self.name = id, name or 'GP'
@@ -144,11 +195,11 @@ class GaussianProcess:
         lib.hb_gp_fit_work_doubles.restype = C.c_size_t
         work = torch.empty(lib.hb_gp_fit_work_doubles(n), **f8)
         vp, i, dd = C.c_void_p, C.c_int, C.c_double
-        lib.hb_gp_fit.argtypes = [i, i, vp, vp, vp, dd, dd, dd, vp, vp, vp, vp, vp, vp, vp]
-        rc = lib.hb_gp_fit(n, d, Xt.data_ptr(), yt.data_ptr(), lst.data_ptr(), self.kernel.signal_variance,
+        lib.hb_gp_fit_kernel.argtypes = [i, i, i, vp, vp, vp, dd, dd, dd, vp, vp, vp, vp, vp, vp, vp]
+        rc = lib.hb_gp_fit_kernel(self.kernel.kind, n, d, Xt.data_ptr(), yt.data_ptr(), lst.data_ptr(), self.kernel.signal_variance,
                            self.noise_variance, self.prior_mean, L.data_ptr(), Linv.data_ptr(), alpha.data_ptr(),
                            lml.data_ptr(), work.data_ptr(), info.data_ptr(), torch.cuda.current_stream().cuda_stream)
-        _lib.check(rc, 'hb_gp_fit')
+        _lib.check(rc, 'hb_gp_fit_kernel')
         if int(info.item()) != 0:
             raise RuntimeError(f"Covariance matrix is not positive definite (pivot {int(info.item()) - 1}); increase "
                                f"the noise variance")
@@ -163,8 +214,8 @@ class GaussianProcess:
         from types import SimpleNamespace as NS
         ls = self.kernel.length_scales
         return [NS(name='GP.noise_variance', value=self.noise_variance),
-                NS(name='SE.length_scales', value=float(ls[0]) if ls.size == 1 else ls.copy()),
-                NS(name='SE.signal_variance', value=self.kernel.signal_variance)]
+                NS(name=f'{self.kernel.acronym}.length_scales', value=float(ls[0]) if ls.size == 1 else ls.copy()),
+                NS(name=f'{self.kernel.acronym}.signal_variance', value=self.kernel.signal_variance)]
 
     def _nlml_and_grad(self, theta, free, base):
         """Negative LML and its gradient w.r.t. the free log-hyper-parameters: factorisation by ``hb_gp_fit`` (setup),
@@ -189,13 +240,15 @@ class GaussianProcess:
         W = Linv.T @ Linv - torch.outer(alpha, alpha)
         ls = self.kernel.length_scale_vector(d)
         D2 = ((X[:, :, None] - X[:, None, :]) / fit['ls'][:, None, None]) ** 2      # (d, n, n)
-        WK = W * (self.kernel.signal_variance * torch.exp(-.5 * D2.sum(0)))
+        gk, hk = self.kernel.g_h(D2.sum(0), xp=torch)
+        WK = W * (self.kernel.signal_variance * gk)
+        WH = W * (self.kernel.signal_variance * hk)
         g = np.empty(full.size)
         g[0] = .5 * self.noise_variance * float(torch.trace(W).item())
         if nl == 1:
-            g[1] = .5 * float((WK * D2.sum(0)).sum().item())
+            g[1] = .5 * float((WH * D2.sum(0)).sum().item())
         else:
-            g[1:1 + nl] = .5 * (WK[None] * D2).sum(dim=(1, 2)).cpu().numpy()
+            g[1:1 + nl] = .5 * (WH[None] * D2).sum(dim=(1, 2)).cpu().numpy()
         g[1 + nl] = .5 * float(WK.sum().item())
         del ls
         return -fit['lml'], g[free]
@@ -255,18 +308,21 @@ class GaussianProcess:
         lib.hb_gp_predict_work_doubles.argtypes = [C.c_int, C.c_int]
         work = torch.empty(lib.hb_gp_predict_work_doubles(n, M), **f8)
         vp, i, dd = C.c_void_p, C.c_int, C.c_double
-        lib.hb_gp_predict.argtypes = [i, i, i, vp, vp, vp, dd, dd, dd, vp, vp, vp, vp, vp, vp]
-        rc = lib.hb_gp_predict(n, d, M, fit['X'].data_ptr(), Xq.data_ptr(), fit['ls'].data_ptr(),
+        lib.hb_gp_predict_kernel.argtypes = [i, i, i, i, vp, vp, vp, dd, dd, dd, vp, vp, vp, vp, vp, vp]
+        rc = lib.hb_gp_predict_kernel(self.kernel.kind, n, d, M, fit['X'].data_ptr(), Xq.data_ptr(), fit['ls'].data_ptr(),
                                self.kernel.signal_variance, 0. if noise_free else self.noise_variance, self.prior_mean,
                                fit['Linv'].data_ptr(), fit['alpha'].data_ptr(), mean.data_ptr(),
                                None if var is None else var.data_ptr(), work.data_ptr(),
                                torch.cuda.current_stream().cuda_stream)
-        _lib.check(rc, 'hb_gp_predict')
+        _lib.check(rc, 'hb_gp_predict_kernel')
         if is_tensor:
             return mean.reshape(1, M), (None if var is None else var.reshape(1, M))
         return mean.cpu().numpy().reshape(1, M), (None if var is None else var.cpu().numpy().reshape(1, M))
 
     def _predict_symbolic(self, xq, noise_free):
+        if self.kernel.kind != 0:
+            raise NotImplementedError("Symbolic queries (embedding into a Model) are implemented for the "
+                                      "squared-exponential kernel only")
         d, n = self._X.shape
         if len(xq) != d:
             raise ValueError(f"Dimension of the query point does not match the number of features: {len(xq)} vs {d}")

@@ -179,6 +179,15 @@ size_t hb_gp_predict_work_doubles(int n, int M);
 int hb_gp_predict(int n, int d, int M, const double* X, const double* Xq, const double* length_scales,
                   double signal_variance, double noise_variance, double prior_mean, const double* Linv,
                   const double* alpha, double* mean, double* var, double* work, void* stream);
+/* The same with another stationary covariance function of r^2 = sum_k ((x_k - x'_k) / l_k)^2: kind 0 = squared
+ * exponential, 1 = exponential, 2 = Matern 3/2, 3 = Matern 5/2 (MaternKernel.get_covariance_function with p = 0, 1, 2,
+ * kernel.py:783-826; classes :829-917).                                                                            */
+int hb_gp_fit_kernel(int kind, int n, int d, const double* X, const double* y, const double* length_scales,
+                     double signal_variance, double noise_variance, double prior_mean, double* L, double* Linv,
+                     double* alpha, double* lml, double* work, int* info, void* stream);
+int hb_gp_predict_kernel(int kind, int n, int d, int M, const double* X, const double* Xq, const double* length_scales,
+                         double signal_variance, double noise_variance, double prior_mean, const double* Linv,
+                         const double* alpha, double* mean, double* var, double* work, void* stream);
 
 #ifdef __cplusplus
 }

@@ -12,6 +12,42 @@ import numpy as np
 import scipy.linalg as sla
 
 
+# Stationary kernels as functions of r^2 = sum_k ((x_k - x'_k) / l_k)^2 (kernel.py:538-555): value g(r) and the factor
+# h(r) of the length-scale derivative, dK/dlog l_k = sigma_f^2 h(r) D2_k with D2_k = ((x_k - x'_k) / l_k)^2.
+#   'SE'  (kernel.py:650-734)    g = exp(-r^2/2)                                 h = g
+#   'E'   (kernel.py:783-826, p=0, nu=1/2)  g = exp(-r)                          h = exp(-r) / r
+#   'M32' (p=1, nu=3/2, d = sqrt(3) r)      g = (1 + d) exp(-d)                  h = 3 exp(-d)
+#   'M52' (p=2, nu=5/2, d = sqrt(5) r)      g = (1 + d + d^2/3) exp(-d)          h = 5/3 (1 + d) exp(-d)
+KINDS = ('SE', 'E', 'M32', 'M52')
+
+
+def stationary_g_h(r2, kind):
+    r = np.sqrt(np.maximum(r2, 0.))
+    if kind == 'SE':
+        g = np.exp(-.5 * r2)
+        return g, g
+    if kind == 'E':
+        g = np.exp(-r)
+        with np.errstate(divide='ignore', invalid='ignore'):
+            h = np.where(r > 0., g / np.where(r > 0., r, 1.), 0.)
+        return g, h
+    if kind == 'M32':
+        d = np.sqrt(3.) * r
+        return (1. + d) * np.exp(-d), 3. * np.exp(-d)
+    if kind == 'M52':
+        d = np.sqrt(5.) * r
+        return (1. + d + d * d / 3.) * np.exp(-d), 5. / 3. * (1. + d) * np.exp(-d)
+    raise ValueError(kind)
+
+
+def stationary_kernel(X, X_bar=None, signal_variance=1., length_scales=1., kind='SE'):
+    X = np.atleast_2d(np.asarray(X, dtype=float))
+    X_bar = X if X_bar is None else np.atleast_2d(np.asarray(X_bar, dtype=float))
+    ls = np.broadcast_to(np.asarray(length_scales, dtype=float).reshape(-1), (X.shape[0],))
+    r2 = (((X[:, :, None] - X_bar[:, None, :]) / ls[:, None, None]) ** 2).sum(0)
+    return signal_variance * stationary_g_h(r2, kind)[0]
+
+
 def se_kernel(X, X_bar=None, signal_variance=1., length_scales=1.):
     X = np.atleast_2d(np.asarray(X, dtype=float))
     X_bar = X if X_bar is None else np.atleast_2d(np.asarray(X_bar, dtype=float))
@@ -23,13 +59,14 @@ def se_kernel(X, X_bar=None, signal_variance=1., length_scales=1.):
 
 
 class GpOracle:
-    def __init__(self, X, y, noise_variance=1., signal_variance=1., length_scales=1., mean=0.):
+    def __init__(self, X, y, noise_variance=1., signal_variance=1., length_scales=1., mean=0., kind='SE'):
         self.X = np.atleast_2d(np.asarray(X, dtype=float))
         self.y = np.asarray(y, dtype=float).reshape(-1)
         self.hyp = dict(noise_variance=noise_variance, signal_variance=signal_variance, length_scales=length_scales)
         self.mean = mean
+        self.kind = kind
         n = self.X.shape[1]
-        K = se_kernel(self.X, None, signal_variance, length_scales)
+        K = stationary_kernel(self.X, None, signal_variance, length_scales, kind)
         self.L = np.linalg.cholesky(noise_variance * np.eye(n) + K)
         self.alpha = sla.cho_solve((self.L, True), self.y - mean)
 
@@ -39,7 +76,7 @@ class GpOracle:
 
     def predict(self, Xq, noise_free=False):
         Xq = np.atleast_2d(np.asarray(Xq, dtype=float))
-        Ks = se_kernel(self.X, Xq, self.hyp['signal_variance'], self.hyp['length_scales'])
+        Ks = stationary_kernel(self.X, Xq, self.hyp['signal_variance'], self.hyp['length_scales'], self.kind)
         mu = self.mean + Ks.T @ self.alpha
         v = sla.solve_triangular(self.L, Ks, lower=True)
         var = self.hyp['signal_variance'] - (v * v).sum(0)
@@ -71,7 +108,7 @@ def lcg_randn(seed, shape):
     return np.reshape(x[:n], shape)
 
 
-def nlml_and_grad(theta, X, y, mean=0., ard=False):
+def nlml_and_grad(theta, X, y, mean=0., ard=False, kind='SE'):
     """Negative LML and its gradient w.r.t. theta = [log noise_variance, log length_scale(s), log signal_variance]:
     dNLML/dtheta_j = 1/2 tr((K^-1 - alpha alpha^T) dK/dtheta_j) (Rasmussen & Williams eq. 5.9)."""
     X = np.atleast_2d(np.asarray(X, dtype=float))
@@ -81,7 +118,8 @@ def nlml_and_grad(theta, X, y, mean=0., ard=False):
     sn2, ls, sf2 = np.exp(theta[0]), np.exp(theta[1:1 + nl]), np.exp(theta[1 + nl])
     lsv = np.broadcast_to(ls, (d,))
     D2 = ((X[:, :, None] - X[:, None, :]) / lsv[:, None, None]) ** 2        # (d, n, n)
-    Kse = sf2 * np.exp(-.5 * D2.sum(0))
+    gk, hk = stationary_g_h(D2.sum(0), kind)
+    Kse, Kh = sf2 * gk, sf2 * hk
     L = np.linalg.cholesky(Kse + sn2 * np.eye(n))
     alpha = sla.cho_solve((L, True), y - mean)
     nlml = .5 * (y - mean) @ alpha + np.log(np.diag(L)).sum() + n / 2 * np.log(2 * np.pi)
@@ -90,21 +128,21 @@ def nlml_and_grad(theta, X, y, mean=0., ard=False):
     g[0] = .5 * sn2 * np.trace(W)
     if ard:
         for k in range(d):
-            g[1 + k] = .5 * (W * Kse * D2[k]).sum()
+            g[1 + k] = .5 * (W * Kh * D2[k]).sum()
     else:
-        g[1] = .5 * (W * Kse * D2.sum(0)).sum()
+        g[1] = .5 * (W * Kh * D2.sum(0)).sum()
     g[1 + nl] = .5 * (W * Kse).sum()
     return float(nlml), g
 
 
-def fit_hyperparameters(X, y, noise_variance=1., length_scales=1., signal_variance=1., mean=0., ard=False):
+def fit_hyperparameters(X, y, noise_variance=1., length_scales=1., signal_variance=1., mean=0., ard=False, kind='SE'):
     """Returns (noise_variance, length_scales, signal_variance) at the minimiser of the negative LML (L-BFGS on the logs,
     started from the given values)."""
     import scipy.optimize as sopt
     d = np.atleast_2d(X).shape[0]
     ls0 = np.broadcast_to(np.asarray(length_scales, dtype=float).reshape(-1), (d if ard else 1,))
     th0 = np.concatenate([[np.log(noise_variance)], np.log(ls0), [np.log(signal_variance)]])
-    res = sopt.minimize(nlml_and_grad, th0, args=(X, y, mean, ard), jac=True, method='L-BFGS-B',
+    res = sopt.minimize(nlml_and_grad, th0, args=(X, y, mean, ard, kind), jac=True, method='L-BFGS-B',
                         options=dict(maxiter=500, ftol=1e-15, gtol=1e-10))
     th = res.x
     return float(np.exp(th[0])), np.exp(th[1:-1]), float(np.exp(th[-1])), res

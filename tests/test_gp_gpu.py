@@ -113,3 +113,54 @@ def test_gp_fit_model_reproduces_gpml_golden(cuda_device):
     gp2.fit_model(fixed=('noise_variance',))
     assert gp2.noise_variance == .1 ** 2
     assert gp2.log_marginal_likelihood() <= gp.log_marginal_likelihood() + 1e-9
+
+
+@pytest.mark.parametrize('name,gold', [('matern_32', [.0088262, .8329355, .9398366]),
+                                       ('matern_52', [.0086694, .7180206, .9571137])])
+def test_gp_matern_kernels_reproduce_goldens(cuda_device, name, gold):
+    """Matern kernels on the device: Gram goldens of tests/test_kernels.py (through the fit's Cholesky factor), fitted
+    hyper-parameters = gpml values of tests/test_GPs.py:862-867 (rtol 1e-5), predictions = oracle."""
+    from hilo_mpc_b200.gp import GP, Kernel
+    from oracle.gp import GpOracle, lcg_randn, stationary_kernel
+    kind = {'matern_32': 'M32', 'matern_52': 'M52'}[name]
+    # Gram: L L^T - noise I must equal the reference's covariance matrix
+    x5 = np.array([[1., 2., 3., 4., 5.]])
+    g5 = GP(['x'], ['y'], kernel=getattr(Kernel, name)(), noise_variance=.5)
+    g5.set_training_data(x5, np.zeros((1, 5)))
+    g5.setup()
+    L = g5._fit['L'].cpu().numpy()
+    np.testing.assert_allclose(L @ L.T - .5 * np.eye(5), stationary_kernel(x5, kind=kind), atol=1e-14)
+    np.testing.assert_allclose(getattr(Kernel, name)()(x5), stationary_kernel(x5, kind=kind), atol=1e-15)
+    if kind == 'M32':
+        np.testing.assert_allclose((L @ L.T)[0, 1:], [.48335772, .13973135, .03431324, .007767734], rtol=2e-7)
+    # training
+    x = lcg_randn(.8, (20, 1))
+    y = np.sin(3 * x) + .1 * lcg_randn(.9, (20, 1))
+    gp = GP(['x'], ['y'], kernel=getattr(Kernel, name)())
+    gp.set_training_data(x.T, y.T)
+    gp.setup()
+    gp.fit_model()
+    vals = [p.value for p in gp.hyperparameters]
+    np.testing.assert_allclose(vals, gold, rtol=1e-5)
+    # prediction against the oracle at the fitted values
+    xq = np.linspace(-3, 3, 61).reshape(1, -1)
+    mean, var = gp.predict(xq)
+    orc = GpOracle(x.T, y.T, noise_variance=vals[0], length_scales=vals[1], signal_variance=vals[2], kind=kind)
+    mo, vo = orc.predict(xq)
+    np.testing.assert_allclose(mean[0], mo, atol=1e-9)
+    np.testing.assert_allclose(var[0], vo, atol=1e-9)
+
+
+def test_gp_exponential_kernel_training(cuda_device):
+    """tests/test_GPs.py:854-860: the noise variance collapses (< 1e-5), [length_scale, signal_variance] are pinned."""
+    from hilo_mpc_b200.gp import GP, Kernel
+    from oracle.gp import lcg_randn
+    x = lcg_randn(.8, (20, 1))
+    y = np.sin(3 * x) + .1 * lcg_randn(.9, (20, 1))
+    gp = GP(['x'], ['y'], kernel=Kernel.exponential())
+    gp.set_training_data(x.T, y.T)
+    gp.setup()
+    gp.fit_model()
+    vals = [p.value for p in gp.hyperparameters]
+    assert vals[0] < 1e-5
+    np.testing.assert_allclose(vals[1:], [.9769135, .5935212], rtol=1e-5)

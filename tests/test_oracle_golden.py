@@ -1,5 +1,6 @@
 """Pins the oracle restatements on the golden numbers held by the reference's own tests."""
 import numpy as np
+import pytest
 
 from oracle import estimators as est
 from oracle.gp import GpOracle, se_kernel
@@ -102,3 +103,32 @@ def test_gp_fitted_hyperparameters_golden():  # tests/test_GPs.py:833-849: gpml 
     y = np.sin(3 * x) + .1 * lcg_randn(.9, (20, 1))
     sn2, ls, sf2, _ = fit_hyperparameters(x.T, y.T)
     np.testing.assert_allclose([sn2, ls[0], sf2], [.0085251, .5298217, .8114553], rtol=1e-5)
+
+
+def test_matern_gram_golden():  # tests/test_kernels.py:1232-1247 (M32), :1826-1845 (M52), :856-875 (E)
+    from oracle.gp import stationary_kernel
+    x = np.array([[1., 2., 3., 4., 5.]])
+    np.testing.assert_allclose(stationary_kernel(x, kind='M32')[0], [1., .48335772, .13973135, .03431324, .007767734],
+                               rtol=2e-7)
+    np.testing.assert_allclose(stationary_kernel(x, x / 2., kind='M52')[0],
+                               [.82864914, 1., .82864914, .52399411, .28316327], rtol=2e-7)
+    np.testing.assert_allclose(stationary_kernel(x, x / 2., kind='E')[0],
+                               [.60653066, 1., .60653066, .36787944, .22313016], rtol=2e-7)
+
+
+@pytest.mark.parametrize('kind,gold', [('M32', [.0088262, .8329355, .9398366]), ('M52', [.0086694, .7180206, .9571137])])
+def test_gp_fitted_hyperparameters_matern_golden(kind, gold):  # tests/test_GPs.py:862-867: gpml values, rtol 1e-5
+    from oracle.gp import fit_hyperparameters, lcg_randn
+    x = lcg_randn(.8, (20, 1))
+    y = np.sin(3 * x) + .1 * lcg_randn(.9, (20, 1))
+    sn2, ls, sf2, _ = fit_hyperparameters(x.T, y.T, kind=kind)
+    np.testing.assert_allclose([sn2, ls[0], sf2], gold, rtol=1e-5)
+
+
+def test_gp_fitted_hyperparameters_exponential_golden():  # tests/test_GPs.py:854-860: noise -> 0, [l, sf2] pinned
+    from oracle.gp import fit_hyperparameters, lcg_randn
+    x = lcg_randn(.8, (20, 1))
+    y = np.sin(3 * x) + .1 * lcg_randn(.9, (20, 1))
+    sn2, ls, sf2, _ = fit_hyperparameters(x.T, y.T, kind='E')
+    assert sn2 < 1e-5
+    np.testing.assert_allclose([ls[0], sf2], [.9769135, .5935212], rtol=1e-5)
