@@ -12,23 +12,20 @@
 //                    reduced Hessian entries, a share of the output copy.
 // Supported: collocation, NMPC-type problems (x_0 pinned, continuous objective, no additive input, no arrival cost)
 // with deg <= 4 and rows_per_lane * columns <= 64 doubles; everything else uses OcpEval.  Terminal nodes are evaluated
-// by OcpEvalTerminal (one thread per instance).
+// by OcpEvalTail (one thread per node, same launch as the re-evaluation of flagged nodes).
 #pragma once
 #include "ocp_kernels.cuh"
 
 namespace hb {
 
 // terminal node only (the k == N branch of OcpEval), launched over instances
+// What the quad kernel leaves to the one-thread-per-node body, as ONE launch over (instance, k = 0..N): the terminal node
+// (k = N), and the nodes whose statically pivoted elimination met a degenerate pivot (recomputed with partial pivoting)
 template <class P>
-struct OcpEvalTerminal {
-  static HB_HD void run(const OcpArgs& a, int b) { OcpEval<P>::run(a, b, OcpT<P>::N); }
-};
-
-// nodes whose statically pivoted elimination met a degenerate pivot are recomputed with partial pivoting
-template <class P>
-struct OcpEvalFlagged {
-  static HB_HD void run(const OcpArgs& a, int b, int k) {
-    if (a.nflag[(long long)b * OcpT<P>::N + k] != 0) OcpEval<P>::run(a, b, k);
+struct OcpEvalTail {
+  static HB_HD void run(const OcpArgs& a, int i, int k) {
+    const int b = a.instance(i);
+    if (k == OcpT<P>::N || a.nflag[(long long)b * OcpT<P>::N + k] != 0) OcpEval<P>::run(a, b, k);
   }
 };
 
@@ -543,8 +540,7 @@ inline cudaError_t launch_eval_quad(const OcpArgs& a, cudaStream_t s) {
   const long long nodes = (long long)a.n_instances() * OcpT<P>::N;
   const int grid = (int)((nodes + E::QUADS - 1) / E::QUADS);
   eval_quad_kernel<P><<<grid, 128, E::SMEM_BYTES, s>>>(a);
-  launch_1d<OcpEvalTerminal<P>>(a, a.B, s);
-  launch_2d<OcpEvalFlagged<P>>(a, a.B, OcpT<P>::N, s);
+  launch_2d<OcpEvalTail<P>>(a, a.n_instances(), OcpT<P>::N + 1, s);
   return cudaGetLastError();
 }
 
