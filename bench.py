@@ -281,6 +281,7 @@ def main():
     ap.add_argument('--cpu-sample', type=int, default=16)
     ap.add_argument('--hessian', default='exact', choices=['exact', 'gauss-newton'])
     ap.add_argument('--riccati-variant', type=int, default=None, help='override b200.riccati_variant (tuning runs)')
+    ap.add_argument('--no-compaction', action='store_true', help='b200.compaction=0: every launch over the whole batch')
     ap.add_argument('--warm-start', type=int, default=1, help='1: reuse multipliers + small initial barrier parameter '
                                                               'between closed-loop steps; 0: IPOPT-default restart')
     ap.add_argument('--warm-mu', type=float, default=1e-8,
@@ -313,6 +314,8 @@ def main():
     opts = {'b200.hessian': args.hessian, 'b200.warm_start': args.warm_start, 'b200.warm_start_mu': args.warm_mu}
     if args.riccati_variant is not None:
         opts['b200.riccati_variant'] = args.riccati_variant
+    if args.no_compaction:
+        opts['b200.compaction'] = 0
     nmpc = cstr_nmpc(N=N_HORIZON, solver_options=opts)
     eng = nmpc.engine
     xs = torch.tensor(nmpc._xs_full, dtype=torch.float64, device=dev)
