@@ -310,8 +310,11 @@ class ParticleFilter(_Estimator):
     def __init__(self, model, id=None, name=None, plot_backend=None, variant=None, roughening=False,
                  prior_editing=False, K=.2):
         super().__init__(model, id=id, name=name, plot_backend=plot_backend)
-        if roughening or prior_editing:
-            raise NotImplementedError("Roughening / prior editing are not supported by the B200 engine yet")
+        if prior_editing:
+            raise NotImplementedError("Prior editing is not supported by the B200 engine yet")
+        self._roughening = bool(roughening)
+        self._roughening_tuning_param = float(K)   # pf.py:72-76
+        self.last_roughening_noise = None
         self._sample_size = 15  # pf.py:79
         self._X = None
         self.last_indices = None
@@ -348,9 +351,28 @@ class ParticleFilter(_Estimator):
         self._X_host = out
         self._X = None
 
-    def estimate(self, y=None, u=None, p=None, w=None, v=None, uniforms=None, **kwargs):
-        """One filter step. The random draws follow the reference (legacy NumPy global RNG, pf.py:363-365, 406) unless
-        ``w`` (process noise ``(B, n_s, n_x)``), ``v`` (measurement noise) and ``uniforms`` are passed explicitly."""
+    def _roughen(self, torch, roughening_noise):
+        """pf.py:411-421: jitter the resampled particles with N(0, K diag(max - min) n_s^(-1/n_x)) (drawn like the reference
+        draws it: legacy global RNG, after the resampling draw) and take the moments of the jittered set."""
+        X = self._X                                                    # (B, n_s, n_x), resampled by the kernel
+        B, ns, nx = X.shape
+        if roughening_noise is None:
+            rng_range = (X.amax(dim=1) - X.amin(dim=1)).cpu().numpy()  # (B, n_x)
+            scale = self._roughening_tuning_param * ns ** (-1. / nx)
+            roughening_noise = np.stack([np.random.multivariate_normal(np.zeros(nx), scale * np.diag(rng_range[b]),
+                                                                       size=ns) for b in range(B)])
+        dx = self._engine.tensor(roughening_noise).reshape(B, ns, nx)
+        self.last_roughening_noise = dx
+        X += dx
+        mean = X.mean(dim=1)
+        Xc = X - mean[:, None, :]
+        self._x.copy_(mean)
+        self._P.copy_(Xc.transpose(1, 2) @ Xc / (ns - 1))              # np.cov: unbiased
+
+    def estimate(self, y=None, u=None, p=None, w=None, v=None, uniforms=None, roughening_noise=None, **kwargs):
+        """One filter step. The random draws follow the reference (legacy NumPy global RNG, pf.py:363-365, 406, 413) unless
+        ``w`` (process noise ``(B, n_s, n_x)``), ``v`` (measurement noise), ``uniforms`` and (with roughening)
+        ``roughening_noise`` ``(B, n_s, n_x)`` are passed explicitly."""
         from . import _lib
         torch = _lib.require_cuda()
         self._check(y)
@@ -381,6 +403,8 @@ class ParticleFilter(_Estimator):
                  unif=eng.tensor(uniforms), q=q, idx=idx, work=work, status=status, substeps=self._substeps,
                  n_particles=ns, t0=self._t)
         self.last_indices, self.last_weights = idx, q
+        if self._roughening:
+            self._roughen(torch, roughening_noise)
         self._store(ypred)
         if self._single:
             return None

@@ -432,6 +432,7 @@ class NMPC(DynamicOptimization):
             u_ub=np.asarray(u_ub, dtype=float) / u_scale, x_guess=np.asarray(x_guess, dtype=float) / x_scale,
             u_guess=np.asarray(u_guess, dtype=float) / u_scale, exact_hessian=self._exact_hessian(), name=name)
         self._xs_full, self._us_full = x_scale, u_scale
+        self._scaling_cache = None
         self._nx0, self._nu0 = nx0, nu0
         from .engine import OcpEngine
         # `_build_module = False` (set by CPU-only tooling) skips nvcc; such an object cannot optimize()
@@ -488,6 +489,15 @@ class NMPC(DynamicOptimization):
         cols = [c.expand(nb, N, c.shape[2]) for c in cols]
         return torch.cat(cols, dim=2).contiguous()
 
+    def _scaling_tensors(self, torch, dev):
+        """Scaling vectors on the device, created once (two pageable host-to-device copies per call otherwise)."""
+        cache = getattr(self, '_scaling_cache', None)
+        if cache is None or cache[0] != dev:
+            cache = (dev, torch.tensor(self._xs_full, dtype=torch.float64, device=dev),
+                     torch.tensor(self._us_full, dtype=torch.float64, device=dev))
+            self._scaling_cache = cache
+        return cache[1], cache[2]
+
     def optimize(self, x0, cp=None, tvp=None, v0=None, runs=0, fix_x0=True, **kwargs):
         if not self._nlp_setup_done:
             raise RuntimeError("The NMPC is not set up. Run NMPC.setup() before optimizing.")
@@ -518,8 +528,7 @@ class NMPC(DynamicOptimization):
             raise ValueError(f"x0 must have {self._nx0} rows (single instance) or shape (B, {self._nx0}); got "
                              f"{tuple(x0t.shape)}")
         B = x0t.shape[0]
-        xs_t = torch.tensor(self._xs_full, dtype=torch.float64, device=dev)
-        us_t = torch.tensor(self._us_full, dtype=torch.float64, device=dev)
+        xs_t, us_t = self._scaling_tensors(torch, dev)
         # augmented state: path variables start from their previous predicted value (or the guess)
         if s.nx > self._nx0:
             if self._last is not None and self._last['x'].shape[0] == B:
@@ -575,8 +584,7 @@ class NMPC(DynamicOptimization):
             raise RuntimeError("No prediction available: call optimize() first")
         torch = __import__('torch')
         out = self._last
-        xs_t = torch.tensor(self._xs_full, dtype=torch.float64, device=out['x'].device)
-        us_t = torch.tensor(self._us_full, dtype=torch.float64, device=out['x'].device)
+        xs_t, us_t = self._scaling_tensors(torch, out['x'].device)
         x = out['x'] * xs_t
         u = out['u'] * us_t
         if x.shape[0] == 1:

@@ -108,9 +108,17 @@ def pf_resample_indices(q, uniforms):
     return cdf.searchsorted(np.asarray(uniforms, dtype=float), side='right')
 
 
-def pf_step(f, h, X, y, u, p, w, v, R, uniforms, dt=1., discrete=True, substeps=10):
-    """pf.py:363-421 without roughening / prior editing. ``X``: n x ns particles, ``w``: n x ns process noise,
-    ``v``: ny x ns measurement noise. Returns ``x_mean, P, X_resampled, q, idx``."""
+def pf_roughening_covariance(Xr, K):
+    """pf.py:411-414: the resampled particles are jittered with N(0, K diag(max - min) n_s^(-1/n_x)) (the range enters
+    as a VARIANCE, as in the reference)."""
+    n, ns = Xr.shape
+    return K * np.diag(Xr.max(axis=1) - Xr.min(axis=1)) * ns ** (-1. / n)
+
+
+def pf_step(f, h, X, y, u, p, w, v, R, uniforms, dt=1., discrete=True, substeps=10, roughening_noise=None):
+    """pf.py:363-421 without prior editing. ``X``: n x ns particles, ``w``: n x ns process noise, ``v``: ny x ns
+    measurement noise, ``roughening_noise``: n x ns jitter added after the resampling (pf.py:411-416; drawn by the caller
+    from ``pf_roughening_covariance``) or None. Returns ``x_mean, P, X_resampled, q, idx``."""
     ns = X.shape[1]
     Xp = np.stack([f(X[:, k], u, p) if discrete else rk4(f, X[:, k], u, p, dt, substeps) for k in range(ns)], axis=1)
     Y = np.stack([np.atleast_1d(h(Xp[:, k], u, p)) for k in range(ns)], axis=1)
@@ -121,4 +129,6 @@ def pf_step(f, h, X, y, u, p, w, v, R, uniforms, dt=1., discrete=True, substeps=
     q = (q / q.sum(axis=1, keepdims=True))[0]
     idx = pf_resample_indices(q, uniforms)
     Xr = Xp[:, idx]
+    if roughening_noise is not None:
+        Xr = Xr + roughening_noise
     return Xr.sum(axis=1) / ns, np.cov(Xr), Xr, q, idx

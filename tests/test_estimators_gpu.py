@@ -135,3 +135,51 @@ def test_pf_resample_entry_matches_numpy_choice(cuda_device):
                                 torch.cuda.current_stream().cuda_stream)
         assert rc == 0
         np.testing.assert_array_equal(idx.cpu().numpy(), np.stack(ref))
+
+
+def test_particle_filter_roughening_matches_oracle(cuda_device):
+    """pf.py:411-421: roughening after the resampling.  With explicit draws the engine must equal the oracle; with the
+    legacy global RNG seeded it must draw in the reference's order (process noise, measurement noise, resampling
+    uniforms, roughening jitter), i.e. equal the oracle fed with the numbers the same seed produces."""
+    from hilo_mpc_b200 import PF
+    from oracle import estimators as est
+    f, hfun = (lambda x_, u, p: x_ / 2 + 25 * x_ / (1 + x_ ** 2)), (lambda x_, u, p: x_ ** 2 / 20)
+    ns = 50
+    rng = np.random.default_rng(3)
+    X0 = rng.normal(9., 1., size=(1, ns, 1))
+    y = np.array([[3.2]])
+    # explicit draws, batch of 2 identical filters
+    pf = PF(scalar_model(), roughening=True, K=.3)
+    pf.setup(n_samples=ns)
+    pf.Q, pf.R = 10., 1.
+    pf.set_initial_guess(np.full((2, 1), 9.))
+    pf.set_particles(np.repeat(X0, 2, axis=0))
+    w = rng.normal(0., np.sqrt(10.), size=(1, ns, 1))
+    v = rng.normal(0., 1., size=(1, ns, 1))
+    unif = rng.random((1, ns))
+    jit = rng.normal(0., .1, size=(1, ns, 1))
+    rep = lambda a: np.repeat(a, 2, axis=0)
+    x, P = pf.estimate(y=rep(y), w=rep(w), v=rep(v), uniforms=rep(unif), roughening_noise=rep(jit))
+    xm, Pm, Xr, _, _ = est.pf_step(f, hfun, X0[0].T, y[0], None, None, w[0].T, v[0].T, np.array([[1.]]), unif[0],
+                                   roughening_noise=jit[0].T)
+    np.testing.assert_allclose(x[0].cpu().numpy(), xm, rtol=1e-12)
+    np.testing.assert_allclose(P[1].cpu().numpy().reshape(-1), np.atleast_1d(Pm).reshape(-1), rtol=1e-12)
+    np.testing.assert_allclose(pf.particles[0].cpu().numpy(), Xr.T, rtol=1e-12)
+    # legacy global RNG, single filter: same seed -> same numbers in the reference's order
+    pf1 = PF(scalar_model(), roughening=True, K=.2)
+    pf1.setup(n_samples=ns)
+    pf1.Q, pf1.R = 10., 1.
+    pf1.set_initial_guess(np.array([9.]))
+    pf1.set_particles(X0[0].T)
+    np.random.seed(77)
+    pf1.estimate(y=y[0])
+    np.random.seed(77)
+    w1 = np.random.multivariate_normal(np.zeros(1), np.array([[10.]]), size=ns)
+    v1 = (np.sqrt(np.array([[1.]])) @ np.random.randn(1, ns)).T
+    u1 = np.random.random_sample(ns)
+    _, _, Xres, _, _ = est.pf_step(f, hfun, X0[0].T, y[0], None, None, w1.T, v1.T, np.array([[1.]]), u1)
+    j1 = np.random.multivariate_normal(np.zeros(1), est.pf_roughening_covariance(Xres, .2), size=ns)
+    xm1, Pm1, Xr1, _, _ = est.pf_step(f, hfun, X0[0].T, y[0], None, None, w1.T, v1.T, np.array([[1.]]), u1,
+                                      roughening_noise=j1.T)
+    np.testing.assert_allclose(pf1.particles[0].cpu().numpy(), Xr1.T, rtol=1e-11)
+    np.testing.assert_allclose(np.asarray(pf1.solution['x'])[:, -1], xm1, rtol=1e-11)
