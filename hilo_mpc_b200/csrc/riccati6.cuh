@@ -46,6 +46,9 @@
 #ifndef HB_R6_PD
 #define HB_R6_PD 6
 #endif
+#ifndef HB_R6_SKIPFWD     // 1: an instance that the step kernel will find converged skips the forward sweep (tuning runs)
+#define HB_R6_SKIPFWD 0
+#endif
 
 namespace hb {
 
@@ -295,6 +298,24 @@ struct Riccati6 {
       backward<true>(a, L, b, lane, gs, ed, ok);
     }
     wp::syncwarp();
+#if HB_R6_SKIPFWD
+    {  // the convergence test of the step kernel (ls_prelude): when it will stop the instance, the step is never used
+      double cinf = 0.0, comp = 0.0;
+      for (int k = lane; k <= N; k += 32) {
+        cinf = dmax(cinf, a.s_cinf[(long long)b * (N + 1) + k]);
+        comp = dmax(comp, a.s_comp[(long long)b * (N + 1) + k]);
+      }
+      double e = dmax(cinf, comp);
+#pragma unroll
+      for (int m = 16; m >= 1; m >>= 1) e = dmax(e, wp::shfl_xor(e, m, 32));
+      const double e4 = wp::shfl(ed, 19, 32), e5 = wp::shfl(ed, 23, 32);
+      const double edual = NU > 1 ? dmax(e4, e5) : e4;
+      if (ok && st[ST_MU] <= a.mu_min * (1.0 + 1e-12) && dmax(e, edual) <= a.tol) {
+        if (lane == 0) st[ST_EDUAL] = edual;
+        return;
+      }
+    }
+#endif
 
     // =============================================================== forward sweep (x_0 fixed: dx_0 = 0)
     // product 1, A-operand rows 0-3: A[gid][tig] (global), rows 4-7: K[gid & 1][tig] (shared memory; rows 6, 7 idle copies)

@@ -23,13 +23,19 @@ __device__ __forceinline__ void cp16(void* dst, const void* src) {
 __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int NPENDING>
 __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NPENDING) : "memory"); }
+#ifndef HB_RCP_NEWTON_STEPS
+#define HB_RCP_NEWTON_STEPS 2
+#endif
 __device__ __forceinline__ double rcp(double x) {   // x > 0: hardware approximation + two Newton steps
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
   double e = fma(-x, r, 1.0);
   r = fma(r, e, r);
+#if HB_RCP_NEWTON_STEPS >= 2
   e = fma(-x, r, 1.0);
-  return fma(r, e, r);
+  r = fma(r, e, r);
+#endif
+  return r;
 }
 __device__ __forceinline__ double* dyn_smem() {
   extern __shared__ __align__(128) double hb_dyn_smem[];
