@@ -26,6 +26,19 @@ def build_all():
     s.setup(dt=1.)
     paths.append(build_est_module(s))
     paths.append(build_est_module(cstr_model(dt=0.005)))
+    bio = Model()   # 3-state bioreactor of the UKF sigma-point golden (tests/test_KFs.py:695-712)
+    bio.set_equations(equations="""
+        dT/dt = alpha*(T_amb - T(t))
+        dcB/dt = r - D(k)*cB(t)
+        dcS/dt = -r/Y - D(k)*cS(t)
+
+        y_0(k) = T(t)
+        y_1(k) = cB(t)
+
+        r = (mu_0 + mu_1*T(t))*cS(t)*cB(t)/(K + cS(t))
+        """)
+    bio.setup(dt=.1)
+    paths.append(build_est_module(bio))
     # LMPC double integrator (BASELINE config 1 / tests/test_LMPC.py:8-33) and its plant model
     from .lmpc import LMPC
     di = Model(discrete=True)

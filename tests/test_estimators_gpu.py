@@ -183,3 +183,19 @@ def test_particle_filter_roughening_matches_oracle(cuda_device):
                                       roughening_noise=j1.T)
     np.testing.assert_allclose(pf1.particles[0].cpu().numpy(), Xr1.T, rtol=1e-11)
     np.testing.assert_allclose(np.asarray(pf1.solution['x'])[:, -1], xm1, rtol=1e-11)
+
+
+def test_ukf_bioreactor_sigma_point_golden(cuda_device):
+    """tests/test_KFs.py:716-756 through the reference's positional predict / update pass-throughs (kf.py:309-325)."""
+    from hilo_mpc_b200 import UKF
+    from test_hostsim_estimators import bioreactor_model
+    from test_oracle_golden import UKF_BIO_P, UKF_BIO_PRED, UKF_BIO_UPD
+    ukf = UKF(bioreactor_model(), alpha=1.)
+    ukf.setup()
+    x = np.array([[299.876], [.217108], [20.]])
+    prediction = ukf.predict(np.append(x, np.eye(3), axis=1), np.append([.01], UKF_BIO_P), np.zeros((3, 3)))
+    np.testing.assert_allclose(prediction, UKF_BIO_PRED, atol=1e-3)
+    update, y_pred = ukf.update(UKF_BIO_PRED, np.array([[300.941], [.245805]]), np.append([.01], UKF_BIO_P),
+                                np.diag([.25, .01]))
+    np.testing.assert_allclose(update, UKF_BIO_UPD, atol=1e-3)
+    np.testing.assert_allclose(np.asarray(y_pred).reshape(-1), [299.925, .219434], atol=1e-3)

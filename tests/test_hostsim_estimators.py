@@ -115,3 +115,36 @@ def test_pf_step_indices_bit_exact_and_moments():
         np.testing.assert_array_equal(out['idx'][b], idx)
         np.testing.assert_allclose(out['x'][b], xm, rtol=1e-12)
         np.testing.assert_allclose(out['P'][b], np.atleast_2d(P), rtol=1e-10)
+
+
+def bioreactor_model():
+    """tests/test_KFs.py:695-712 (equation-string front end; parameters in order of appearance)."""
+    m = Model()
+    m.set_equations(equations="""
+        dT/dt = alpha*(T_amb - T(t))
+        dcB/dt = r - D(k)*cB(t)
+        dcS/dt = -r/Y - D(k)*cS(t)
+
+        y_0(k) = T(t)
+        y_1(k) = cB(t)
+
+        r = (mu_0 + mu_1*T(t))*cS(t)*cB(t)/(K + cS(t))
+        """)
+    m.setup(dt=.1)
+    return m
+
+
+def test_ukf_bioreactor_sigma_point_golden_through_the_kernel_bodies():
+    """tests/test_KFs.py:716-756 (atol 1e-3 there; the reference integrates with CVODES, the kernel with 10 RK4 steps)."""
+    from test_oracle_golden import UKF_BIO_P, UKF_BIO_PRED, UKF_BIO_UPD
+    m = bioreactor_model()
+    assert m.parameter_names == ['alpha', 'T_amb', 'mu_0', 'mu_1', 'K', 'Y']
+    h = HostEst(build_est_module(m, hostsim=True))
+    out = h.call('ukf', [299.876, .217108, 20.], P=np.eye(3), y=[0., 0.], u=[.01], p=UKF_BIO_P, Q=np.zeros((3, 3)),
+                 R=np.eye(2), dt=.1, substeps=10, alpha=1., do_update=False)
+    got = np.concatenate([out['x'][0][:, None], out['P'][0], out['X'][0].T], axis=1)
+    np.testing.assert_allclose(got, UKF_BIO_PRED, atol=1e-3)
+    out = h.call('ukf', UKF_BIO_PRED[:, 0], P=UKF_BIO_PRED[:, 1:4], X=UKF_BIO_PRED[:, 4:].T, y=[300.941, .245805],
+                 u=[.01], p=UKF_BIO_P, Q=np.zeros((3, 3)), R=np.diag([.25, .01]), dt=.1, alpha=1., do_predict=False)
+    np.testing.assert_allclose(np.concatenate([out['x'][0][:, None], out['P'][0]], axis=1), UKF_BIO_UPD, atol=1e-3)
+    np.testing.assert_allclose(out['y_pred'][0], [299.925, .219434], atol=1e-3)

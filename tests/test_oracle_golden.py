@@ -132,3 +132,34 @@ def test_gp_fitted_hyperparameters_exponential_golden():  # tests/test_GPs.py:85
     sn2, ls, sf2, _ = fit_hyperparameters(x.T, y.T, kind='E')
     assert sn2 < 1e-5
     np.testing.assert_allclose([ls[0], sf2], [.9769135, .5935212], rtol=1e-5)
+
+
+# tests/test_KFs.py:690-756: UKF sigma-point golden on the 3-state bioreactor (continuous model, dt = 0.1, alpha = 1);
+# the reference integrates with CVODES and asserts atol = 1e-3
+UKF_BIO_P = [.15, 303.15, .13, .00025, 15., .14]     # alpha, T_amb, mu_0, mu_1, K, Y (order of appearance)
+UKF_BIO_PRED = np.array([
+    [299.925, 0.970453, 1.08254e-06, -2.11206e-05, 299.925, 301.631, 299.925, 299.925, 298.218, 299.925, 299.925],
+    [0.219433, 1.08254e-06, 1.02165, -0.0848792, 0.219446, 0.219451, 1.97011, 0.219537, 0.21944, -1.53128, 0.219345],
+    [19.9619, -2.11206e-05, -0.0848792, 1.00427, 19.9618, 19.9617, 19.8164, 21.6914, 19.9618, 20.1075, 18.2322]])
+UKF_BIO_UPD = np.array([[300.733, 0.198539, -2.03814e-06, 1.56415e-06],
+                        [0.245549, -2.03814e-06, 0.00990874, -0.000819447],
+                        [19.9597, 1.56415e-06, -0.000819447, 0.997286]])
+
+
+def bioreactor_rhs(x, u, p):
+    T, cB, cS = x
+    D = np.atleast_1d(u)[0]
+    alpha, T_amb, mu0, mu1, K, Y = p
+    r = (mu0 + mu1 * T) * cS * cB / (K + cS)
+    return np.array([alpha * (T_amb - T), r - D * cB, -r / Y - D * cS])
+
+
+def test_ukf_bioreactor_sigma_point_golden():
+    h = lambda x, u, p: np.array([x[0], x[1]])
+    xp, Pp, X = est.ukf_predict(bioreactor_rhs, np.array([299.876, .217108, 20.]), np.eye(3), [.01], UKF_BIO_P,
+                                np.zeros((3, 3)), dt=.1, discrete=False, substeps=10, alpha=1.)
+    np.testing.assert_allclose(np.concatenate([xp[:, None], Pp, X], axis=1), UKF_BIO_PRED, atol=1e-3)
+    xu, Pu, yp = est.ukf_update(h, UKF_BIO_PRED[:, 0], UKF_BIO_PRED[:, 1:4], UKF_BIO_PRED[:, 4:],
+                                np.array([300.941, .245805]), [.01], UKF_BIO_P, np.diag([.25, .01]), alpha=1.)
+    np.testing.assert_allclose(np.concatenate([xu[:, None], Pu], axis=1), UKF_BIO_UPD, atol=1e-3)
+    np.testing.assert_allclose(yp, [299.925, .219434], atol=1e-3)
