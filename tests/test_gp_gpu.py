@@ -164,3 +164,20 @@ def test_gp_exponential_kernel_training(cuda_device):
     vals = [p.value for p in gp.hyperparameters]
     assert vals[0] < 1e-5
     np.testing.assert_allclose(vals[1:], [.9769135, .5935212], rtol=1e-5)
+
+
+def test_gp_rasmussen_regression_goldens(cuda_device):
+    """tests/test_GPs.py:1095-1124: LML of the Matern-3/2 GP with the (here pre-subtracted) mean 0.5 x + 1 = -11.9706317,
+    fitted hyper-parameters of the default SE model = gpml values to rtol 1e-6."""
+    from hilo_mpc_b200.gp import GP, Kernel
+    from test_oracle_golden import rasmussen_data
+    x, y, mu = rasmussen_data()
+    gp = GP(['x'], ['y'], kernel=Kernel.matern_32(length_scales=.25), noise_variance=.1 ** 2)
+    gp.set_training_data(x.T, (y - mu).T)
+    gp.setup()
+    np.testing.assert_approx_equal(gp.log_marginal_likelihood(), -11.9706317, significant=9)
+    gp1 = GP(['x'], ['y'], noise_variance=.1 ** 2)
+    gp1.set_training_data(x.T, y.T)
+    gp1.setup()
+    gp1.fit_model()
+    np.testing.assert_allclose([p.value for p in gp1.hyperparameters], [.0222571, .3703166, 3.9427837], rtol=1e-6)

@@ -163,3 +163,22 @@ def test_ukf_bioreactor_sigma_point_golden():
                                 np.array([300.941, .245805]), [.01], UKF_BIO_P, np.diag([.25, .01]), alpha=1.)
     np.testing.assert_allclose(np.concatenate([xu[:, None], Pu], axis=1), UKF_BIO_UPD, atol=1e-3)
     np.testing.assert_allclose(yp, [299.925, .219434], atol=1e-3)
+
+
+def rasmussen_data():
+    """tests/test_GPs.py:1102-1113: 20 points drawn from a Matern-3/2 GP (l = 0.25) around the mean 0.5 x + 1."""
+    from oracle.gp import lcg_randn, stationary_kernel
+    x = lcg_randn(.3, (20, 1))
+    K = stationary_kernel(x.T, kind='M32', length_scales=.25)
+    mu = .5 * x + 1.
+    y = np.linalg.cholesky(K) @ lcg_randn(.15, (20, 1)) + mu + .1 * lcg_randn(.2, (20, 1))
+    return x, y, mu
+
+
+def test_gp_rasmussen_regression_goldens():  # tests/test_GPs.py:1120-1124
+    from oracle.gp import fit_hyperparameters
+    x, y, mu = rasmussen_data()
+    o = GpOracle(x.T, (y - mu).T, noise_variance=.01, signal_variance=1., length_scales=.25, kind='M32')
+    np.testing.assert_approx_equal(o.log_marginal_likelihood(), -11.9706317, significant=9)
+    sn2, ls, sf2, _ = fit_hyperparameters(x.T, y.T, noise_variance=.01)
+    np.testing.assert_allclose([sn2, ls[0], sf2], [.0222571, .3703166, 3.9427837], rtol=1e-6)
