@@ -8,13 +8,13 @@ from .model import Model
 from .nmpc import NMPC
 from .lmpc import LMPC
 from .mhe import MHE, MovingHorizonEstimator
-from .gp import GP, GaussianProcess, Kernel
+from .gp import GP, GaussianProcess, Kernel, Mean
 from .ann import ANN, Layer
 from .control_loop import SimpleControlLoop
 from .estimators import EKF, KF, PF, UKF, ExtendedKalmanFilter, KalmanFilter, ParticleFilter, UnscentedKalmanFilter
 
 pi = 3.141592653589793
 
-__all__ = ['Model', 'NMPC', 'LMPC', 'MHE', 'MovingHorizonEstimator', 'GP', 'GaussianProcess', 'Kernel', 'ANN', 'Layer',
+__all__ = ['Model', 'NMPC', 'LMPC', 'MHE', 'MovingHorizonEstimator', 'GP', 'GaussianProcess', 'Kernel', 'Mean', 'ANN', 'Layer',
            'KF', 'EKF', 'UKF', 'PF', 'KalmanFilter', 'ExtendedKalmanFilter', 'UnscentedKalmanFilter',
            'ParticleFilter', 'SimpleControlLoop', 'symbolic', 'ca']

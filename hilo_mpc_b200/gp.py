@@ -89,6 +89,86 @@ class Matern52Kernel(StationaryKernel):         # kernel.py:889-916
     acronym, kind = 'M52', 3
 
 
+class Mean:
+    """Prior mean functions (gp/mean.py:45-499): sums of a linear term ``c^T x`` and constants.  ``m(X) = Phi(X) beta``
+    with the basis ``Phi`` (rows of X for the linear coefficients, ones for a bias); ``free`` marks the entries of ``beta``
+    that hyper-parameter training may change (mean hyper-parameters are not log-transformed, gp.py:197)."""
+
+    def __init__(self, terms):
+        self.terms = list(terms)   # (kind, value(s), fixed) with kind in 'linear', 'constant'
+
+    # factories of the reference (mean.py:173-241)
+    @staticmethod
+    def constant(bias=1., hyperprior=None, bounds=None):
+        if hyperprior is not None:
+            raise NotImplementedError("Hyper-priors are not supported by the B200 engine yet")
+        return Mean([('constant', np.atleast_1d(float(bias)), _is_fixed(bounds, 'bias'))])
+
+    @staticmethod
+    def zero():
+        return Mean([('constant', np.zeros(1), True)])
+
+    @staticmethod
+    def one():
+        return Mean([('constant', np.ones(1), True)])
+
+    @staticmethod
+    def linear(coefficient=1., hyperprior=None, bounds=None):
+        if hyperprior is not None:
+            raise NotImplementedError("Hyper-priors are not supported by the B200 engine yet")
+        return Mean([('linear', np.atleast_1d(np.asarray(coefficient, dtype=float)), _is_fixed(bounds, 'coefficient'))])
+
+    def __add__(self, other):
+        if not isinstance(other, Mean):
+            return NotImplemented
+        return Mean(self.terms + other.terms)
+
+    def _expanded(self, d):
+        out = []
+        for kind, val, fixed in self.terms:
+            if kind == 'linear':
+                val = np.full(d, float(val[0])) if val.size == 1 else val
+                if val.size != d:
+                    raise ValueError("Dimension of the linear mean coefficient does not match the number of features")
+            out.append((kind, np.array(val, dtype=float), fixed))
+        return out
+
+    def basis(self, X, xp=np):
+        """``Phi`` as a list of rows (one per entry of beta) for X of shape (d, m)."""
+        rows = []
+        for kind, val, _ in self._expanded(X.shape[0]):
+            rows += [X[k] for k in range(val.size)] if kind == 'linear' else [xp.ones_like(X[0])]
+        return rows
+
+    def beta(self, d):
+        return np.concatenate([val for _, val, _ in self._expanded(d)])
+
+    def free(self, d):
+        return np.concatenate([np.full(val.size, not fixed) for _, val, fixed in self._expanded(d)])
+
+    def set_beta(self, beta, d):
+        terms, o = [], 0
+        for kind, val, fixed in self._expanded(d):
+            terms.append((kind, np.array(beta[o:o + val.size], dtype=float), fixed))
+            o += val.size
+        self.terms = terms
+
+    def names(self, d):
+        out = []
+        for kind, val, _ in self._expanded(d):
+            out += [f'Lin.coefficient'] * val.size if kind == 'linear' else ['Const.bias']
+        return out
+
+    def __call__(self, X):
+        X = np.atleast_2d(np.asarray(X, dtype=float))
+        rows = self.basis(X)
+        return (np.stack(rows).T @ self.beta(X.shape[0])).reshape(1, -1) if rows else np.zeros((1, X.shape[1]))
+
+
+def _is_fixed(bounds, name):
+    return isinstance(bounds, dict) and bounds.get(name) == 'fixed'
+
+
 class Kernel:
     @staticmethod
     def squared_exponential(active_dims=None, signal_variance=1., length_scales=1., ard=False, bounds=None):
@@ -130,7 +210,9 @@ class GaussianProcess:
         self.kernel = kernel if kernel is not None else Kernel.squared_exponential()
         if not isinstance(self.kernel, StationaryKernel):
             raise NotImplementedError("Only the squared-exponential and Matern kernels are supported by the B200 engine")
-        self.prior_mean = 0. if mean is None else float(mean)
+        # a number = constant prior mean handled by the device kernels; a Mean object = m(X) subtracted from the targets
+        self.mean = mean if isinstance(mean, Mean) else None
+        self.prior_mean = 0. if (mean is None or self.mean is not None) else float(mean)
         self.noise_variance = float(noise_variance)
         self.id, self.name = id, name or 'GP'
         self._X = self._y = None
@@ -185,7 +267,8 @@ class GaussianProcess:
         d, n = self._X.shape
         ls = self.kernel.length_scale_vector(d)
         Xt = torch.tensor(self._X, **f8).contiguous()
-        yt = torch.tensor(self._y.reshape(-1), **f8).contiguous()
+        y_eff = self._y.reshape(-1) - (self.mean(self._X).reshape(-1) if self.mean is not None else 0.)
+        yt = torch.tensor(y_eff, **f8).contiguous()
         lst = torch.tensor(ls, **f8)
         L = torch.empty(n, n, **f8)
         Linv = torch.empty(n, n, **f8)
@@ -213,7 +296,11 @@ class GaussianProcess:
         reference's list, gp.py:215-240; tests/test_GPs.py:846-849 reads ``[p.value for p in gp.hyperparameters]``)."""
         from types import SimpleNamespace as NS
         ls = self.kernel.length_scales
-        return [NS(name='GP.noise_variance', value=self.noise_variance),
+        mean_par = []
+        if self.mean is not None:
+            d = len(self.features)
+            mean_par = [NS(name=n, value=float(v)) for n, v in zip(self.mean.names(d), self.mean.beta(d))]
+        return [NS(name='GP.noise_variance', value=self.noise_variance)] + mean_par + [
                 NS(name=f'{self.kernel.acronym}.length_scales', value=float(ls[0]) if ls.size == 1 else ls.copy()),
                 NS(name=f'{self.kernel.acronym}.signal_variance', value=self.kernel.signal_variance)]
 
@@ -231,6 +318,9 @@ class GaussianProcess:
             self.kernel.length_scales = np.where(free[1:1 + nl], np.exp(full[1:1 + nl]), self.kernel.length_scales)
         if free[1 + nl]:
             self.kernel.signal_variance = float(np.exp(full[1 + nl]))
+        nm = full.size - (2 + nl)                        # coefficients of the mean function (not log-transformed)
+        if nm and free[2 + nl:].any():
+            self.mean.set_beta(full[2 + nl:], d)
         try:
             self.setup()
         except RuntimeError:   # not positive definite at this trial point: reject the step
@@ -250,24 +340,31 @@ class GaussianProcess:
         else:
             g[1:1 + nl] = .5 * (WH[None] * D2).sum(dim=(1, 2)).cpu().numpy()
         g[1 + nl] = .5 * float(WK.sum().item())
+        if nm:                                           # dNLML/dbeta_j = -Phi_j^T alpha
+            Phi = torch.stack(self.mean.basis(X, xp=torch))
+            g[2 + nl:] = -(Phi @ alpha).cpu().numpy()
         del ls
         return -fit['lml'], g[free]
 
     def fit_model(self, fixed: Sequence[str] = (), maxiter: int = 500) -> None:
         """Optimise the hyper-parameters by minimising the negative log marginal likelihood (gp.py:660-697), starting from
         the current values.  ``fixed``: names out of ``'noise_variance'``, ``'length_scales'``, ``'signal_variance'`` that
-        keep their values (the reference's ``prior = 'Delta'`` / ``'fixed'`` bounds)."""
+        keep their values (the reference's ``prior = 'Delta'`` / ``'fixed'`` bounds); coefficients of a ``Mean`` object are
+        trained too unless created with ``bounds={'coefficient': 'fixed'}`` / ``Mean.one()`` / ``Mean.zero()``."""
         if not self._is_setup:
             raise RuntimeError("The GP has not been set up yet. Please run the setup() method before fitting.")
         import scipy.optimize as sopt
         nl = self.kernel.length_scales.size
+        d = self._X.shape[0]
+        beta = self.mean.beta(d) if self.mean is not None else np.zeros(0)
         base = np.concatenate([[np.log(self.noise_variance)], np.log(self.kernel.length_scales),
-                               [np.log(self.kernel.signal_variance)]])
+                               [np.log(self.kernel.signal_variance)], beta])
         names = ['noise_variance'] + ['length_scales'] * nl + ['signal_variance']
         unknown = [f for f in fixed if f not in names]
         if unknown:
             raise ValueError(f"Unknown hyper-parameter name(s) {unknown}")
-        free = np.array([n not in fixed for n in names])
+        free = np.concatenate([np.array([n not in fixed for n in names]),
+                               self.mean.free(d) if self.mean is not None else np.zeros(0, dtype=bool)])
         if not free.any():
             return
         res = sopt.minimize(self._nlml_and_grad, base[free], args=(free, base), jac=True, method='L-BFGS-B',
@@ -315,6 +412,10 @@ class GaussianProcess:
                                None if var is None else var.data_ptr(), work.data_ptr(),
                                torch.cuda.current_stream().cuda_stream)
         _lib.check(rc, 'hb_gp_predict_kernel')
+        if self.mean is not None:   # m(x*) = Phi(x*) beta, on the device
+            beta = self.mean.beta(d)
+            for bj, row in zip(beta, self.mean.basis(Xq, xp=torch)):
+                mean += float(bj) * row
         if is_tensor:
             return mean.reshape(1, M), (None if var is None else var.reshape(1, M))
         return mean.cpu().numpy().reshape(1, M), (None if var is None else var.cpu().numpy().reshape(1, M))
@@ -329,6 +430,11 @@ class GaussianProcess:
         ls = self.kernel.length_scale_vector(d)
         alpha = self._fit['alpha_host']
         mean = sx.Expr.const(self.prior_mean)
+        if self.mean is not None:
+            beta = self.mean.beta(d)
+            rows = self.mean.basis(np.array([[xi] for xi in xq], dtype=object))
+            for bj, row in zip(beta, rows):
+                mean = mean + float(bj) * (row[0] if isinstance(row, np.ndarray) else row)
         ks = []
         for i in range(n):
             d2 = sx.Expr.const(0.)

@@ -108,14 +108,18 @@ def lcg_randn(seed, shape):
     return np.reshape(x[:n], shape)
 
 
-def nlml_and_grad(theta, X, y, mean=0., ard=False, kind='SE'):
-    """Negative LML and its gradient w.r.t. theta = [log noise_variance, log length_scale(s), log signal_variance]:
-    dNLML/dtheta_j = 1/2 tr((K^-1 - alpha alpha^T) dK/dtheta_j) (Rasmussen & Williams eq. 5.9)."""
+def nlml_and_grad(theta, X, y, mean=0., ard=False, kind='SE', Phi=None):
+    """Negative LML and its gradient w.r.t. theta = [log noise_variance, log length_scale(s), log signal_variance, beta]:
+    dNLML/dtheta_j = 1/2 tr((K^-1 - alpha alpha^T) dK/dtheta_j) (Rasmussen & Williams eq. 5.9); ``Phi`` (n x m) is the
+    basis of a linear-in-parameters mean function m(X) = Phi beta (gp/mean.py: linear + constant terms, coefficients not
+    log-transformed, gp.py:197), dNLML/dbeta = -Phi^T alpha."""
     X = np.atleast_2d(np.asarray(X, dtype=float))
     y = np.asarray(y, dtype=float).reshape(-1)
     d, n = X.shape
     nl = d if ard else 1
     sn2, ls, sf2 = np.exp(theta[0]), np.exp(theta[1:1 + nl]), np.exp(theta[1 + nl])
+    if Phi is not None:
+        mean = mean + np.asarray(Phi, dtype=float) @ theta[2 + nl:]
     lsv = np.broadcast_to(ls, (d,))
     D2 = ((X[:, :, None] - X[:, None, :]) / lsv[:, None, None]) ** 2        # (d, n, n)
     gk, hk = stationary_g_h(D2.sum(0), kind)
@@ -132,17 +136,24 @@ def nlml_and_grad(theta, X, y, mean=0., ard=False, kind='SE'):
     else:
         g[1] = .5 * (W * Kh * D2.sum(0)).sum()
     g[1 + nl] = .5 * (W * Kse).sum()
+    if Phi is not None:
+        g[2 + nl:] = -np.asarray(Phi, dtype=float).T @ alpha
     return float(nlml), g
 
 
-def fit_hyperparameters(X, y, noise_variance=1., length_scales=1., signal_variance=1., mean=0., ard=False, kind='SE'):
+def fit_hyperparameters(X, y, noise_variance=1., length_scales=1., signal_variance=1., mean=0., ard=False, kind='SE',
+                        Phi=None, beta0=None):
     """Returns (noise_variance, length_scales, signal_variance) at the minimiser of the negative LML (L-BFGS on the logs,
     started from the given values)."""
     import scipy.optimize as sopt
     d = np.atleast_2d(X).shape[0]
     ls0 = np.broadcast_to(np.asarray(length_scales, dtype=float).reshape(-1), (d if ard else 1,))
     th0 = np.concatenate([[np.log(noise_variance)], np.log(ls0), [np.log(signal_variance)]])
-    res = sopt.minimize(nlml_and_grad, th0, args=(X, y, mean, ard, kind), jac=True, method='L-BFGS-B',
+    nk = th0.size
+    if Phi is not None:
+        th0 = np.concatenate([th0, np.zeros(np.asarray(Phi).shape[1]) if beta0 is None else np.asarray(beta0, float)])
+    res = sopt.minimize(nlml_and_grad, th0, args=(X, y, mean, ard, kind, Phi), jac=True, method='L-BFGS-B',
                         options=dict(maxiter=500, ftol=1e-15, gtol=1e-10))
     th = res.x
-    return float(np.exp(th[0])), np.exp(th[1:-1]), float(np.exp(th[-1])), res
+    res.beta = th[nk:]   # coefficients of the mean function (empty without one)
+    return float(np.exp(th[0])), np.exp(th[1:nk - 1]), float(np.exp(th[nk - 1])), res

@@ -181,3 +181,31 @@ def test_gp_rasmussen_regression_goldens(cuda_device):
     gp1.setup()
     gp1.fit_model()
     np.testing.assert_allclose([p.value for p in gp1.hyperparameters], [.0222571, .3703166, 3.9427837], rtol=1e-6)
+
+
+def test_gp_mean_functions(cuda_device):
+    """Mean objects (gp/mean.py): LML golden of tests/test_GPs.py:1120 with the mean 0.5 x + 1 given as
+    Mean.linear(fixed) + Mean.one(); all five hyper-parameters of the linear + constant mean model fitted to the gpml
+    values (:1125-1126, rtol 1e-6); predictions carry the mean."""
+    from hilo_mpc_b200 import Mean
+    from hilo_mpc_b200.gp import GP, Kernel
+    from oracle.gp import GpOracle
+    from test_oracle_golden import rasmussen_data
+    x, y, mu = rasmussen_data()
+    mean = Mean.linear(coefficient=.5, bounds={'coefficient': 'fixed'}) + Mean.one()
+    np.testing.assert_allclose(mean(x.T), mu.T, rtol=1e-15)
+    gp = GP(['x'], ['y'], mean=mean, kernel=Kernel.matern_32(length_scales=.25), noise_variance=.1 ** 2)
+    gp.set_training_data(x.T, y.T)
+    gp.setup()
+    np.testing.assert_approx_equal(gp.log_marginal_likelihood(), -11.9706317, significant=9)
+    xq = np.linspace(-1.9, 1.9, 101).reshape(1, -1)
+    m, v = gp.predict(xq)
+    mo, vo = GpOracle(x.T, (y - mu).T, noise_variance=.01, length_scales=.25, kind='M32').predict(xq)
+    np.testing.assert_allclose(m[0], mo + (.5 * xq[0] + 1.), atol=1e-10)
+    np.testing.assert_allclose(v[0], vo, atol=1e-10)
+    gp2 = GP(['x'], ['y'], mean=Mean.linear(coefficient=0.) + Mean.constant(bias=0.), noise_variance=.1 ** 2)
+    gp2.set_training_data(x.T, y.T)
+    gp2.setup()
+    gp2.fit_model()
+    np.testing.assert_allclose([p.value for p in gp2.hyperparameters],
+                               [.02183, 1.1918832, 1.4624534, .2201449, .4017997], rtol=1e-6)

@@ -182,3 +182,12 @@ def test_gp_rasmussen_regression_goldens():  # tests/test_GPs.py:1120-1124
     np.testing.assert_approx_equal(o.log_marginal_likelihood(), -11.9706317, significant=9)
     sn2, ls, sf2, _ = fit_hyperparameters(x.T, y.T, noise_variance=.01)
     np.testing.assert_allclose([sn2, ls[0], sf2], [.0222571, .3703166, 3.9427837], rtol=1e-6)
+
+
+def test_gp_trainable_mean_golden():  # tests/test_GPs.py:1125-1126, 1150-1155: linear + constant mean, all five fitted
+    from oracle.gp import fit_hyperparameters
+    x, y, _ = rasmussen_data()
+    Phi = np.column_stack([x[:, 0], np.ones(20)])
+    sn2, ls, sf2, res = fit_hyperparameters(x.T, y.T, noise_variance=.01, Phi=Phi)
+    np.testing.assert_allclose([sn2, res.beta[0], res.beta[1], ls[0], sf2],
+                               [.02183, 1.1918832, 1.4624534, .2201449, .4017997], rtol=1e-6)
