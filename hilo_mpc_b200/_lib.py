@@ -17,7 +17,14 @@ _IP = C.POINTER(C.c_int)
 
 class OcpDims(C.Structure):
     _fields_ = [(n, C.c_int) for n in ('nx', 'nu', 'N', 'nc', 'nsp', 'ntp', 'nuold', 'nap', 'stage_doubles',
-                                       'elim_doubles', 'method', 'fixed_x0', 'n_state')]
+                                       'elim_doubles', 'method', 'fixed_x0', 'n_state', 'block_a', 'block_h', 'frag')]
+
+
+class OcpRiccatiCall(C.Structure):   # mirrors struct hb_ocp_riccati_call, include/hilo_b200.h
+    _fields_ = [('B', C.c_int), ('riccati_variant', C.c_int), ('qa', C.c_void_p), ('qh', C.c_void_p),
+                ('qpN', C.c_void_p), ('dx', C.c_void_p), ('du', C.c_void_p), ('lam', C.c_void_p),
+                ('edual', C.c_void_p), ('status', C.c_void_p), ('work', C.c_void_p), ('work_doubles', C.c_size_t),
+                ('stream', C.c_void_p)]
 
 
 class OcpCall(C.Structure):
@@ -66,6 +73,9 @@ def load() -> C.CDLL:
     lib.hb_ocp_work_doubles.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.hb_ocp_work_doubles.restype = C.c_size_t
     lib.hb_ocp_solve.argtypes = [C.c_void_p, C.POINTER(OcpCall)]
+    lib.hb_ocp_riccati.argtypes = [C.c_void_p, C.POINTER(OcpRiccatiCall)]
+    lib.hb_ocp_riccati_work_doubles.argtypes = [C.c_void_p, C.c_int]
+    lib.hb_ocp_riccati_work_doubles.restype = C.c_size_t
     lib.hb_ocp_close.argtypes = [C.c_void_p]
     _register_optional(lib)
     _lib = lib

@@ -28,6 +28,8 @@ struct hb_ocp {
   void (*dims)(hb_ocp_dims*);
   size_t (*work)(int, int);
   int (*solve)(const hb_ocp_call*);
+  size_t (*ric_work)(int);
+  int (*ric)(const hb_ocp_riccati_call*);
   hb_ocp_dims d;
 };
 
@@ -68,6 +70,8 @@ int hb_ocp_open(const char* module_path, hb_ocp_t* out) {
   h->dims = (void (*)(hb_ocp_dims*))dlsym(dl, "hbm_ocp_dims");
   h->work = (size_t(*)(int, int))dlsym(dl, "hbm_ocp_work_doubles");
   h->solve = (int (*)(const hb_ocp_call*))dlsym(dl, "hbm_ocp_solve");
+  h->ric_work = (size_t(*)(int))dlsym(dl, "hbm_ocp_riccati_work_doubles");
+  h->ric = (int (*)(const hb_ocp_riccati_call*))dlsym(dl, "hbm_ocp_riccati");
   if (h->dims == nullptr || h->work == nullptr || h->solve == nullptr) {
     set_err("hb_ocp_open: %s is not a hilo_b200 OCP module (missing hbm_ocp_* symbols)", module_path);
     dlclose(dl);
@@ -88,6 +92,20 @@ int hb_ocp_get_dims(hb_ocp_t h, hb_ocp_dims* dims) {
 size_t hb_ocp_work_doubles(hb_ocp_t h, int B, int n_alpha) {
   if (h == nullptr || B <= 0 || n_alpha <= 0) return 0;
   return h->work(B, n_alpha);
+}
+
+size_t hb_ocp_riccati_work_doubles(hb_ocp_t h, int B) {
+  if (h == nullptr || h->ric_work == nullptr || B <= 0) return 0;
+  return h->ric_work(B);
+}
+
+int hb_ocp_riccati(hb_ocp_t h, const hb_ocp_riccati_call* call) {
+  if (h == nullptr || call == nullptr) { set_err("hb_ocp_riccati: null argument"); return -1; }
+  if (h->ric == nullptr) { set_err("hb_ocp_riccati: the module does not export the sweep"); return -4; }
+  const int rc = h->ric(call);
+  if (rc < 0) set_err("hb_ocp_riccati: invalid call (code %d: -1 argument, -2 workspace too small)", rc);
+  if (rc > 0) set_err("hb_ocp_riccati: CUDA error %d (%s)", rc, cudaGetErrorString((cudaError_t)rc));
+  return rc;
 }
 
 int hb_ocp_solve(hb_ocp_t h, const hb_ocp_call* call) {

@@ -87,6 +87,79 @@ struct OcpModule {
     d->nx = T::NX; d->nu = T::NU; d->N = T::N; d->nc = T::NC; d->nsp = T::NSP; d->ntp = T::NTP;
     d->nuold = T::NUOLD; d->nap = T::NAP; d->stage_doubles = T::NA + T::NH; d->elim_doubles = T::TD;
     d->method = P::METHOD; d->fixed_x0 = P::FIXED_X0 ? 1 : 0; d->n_state = ST_COUNT;
+    d->block_a = T::NAp; d->block_h = T::NHp; d->frag = T::FRAG ? 1 : 0;
+  }
+
+  // the sweep of one iteration, fastest version the problem admits (riccati_variant: see hb_ocp_call)
+  static int launch_riccati(const OcpArgs& a, int variant, cudaStream_t s) {
+    bool ric_done = false;
+    if (variant >= 2) {
+      int rc6 = -100;
+      auto try6 = [&](auto tag) {
+        using R = decltype(tag);
+        if constexpr (R::SUPPORTED) rc6 = launch_riccati6<R>(a, s);
+      };
+      switch (variant) {
+        case 6: try6(Riccati6<P, 4>{}); break;
+        case 8: try6(Riccati6<P, 5>{}); break;
+        case 9: try6(Riccati6<P, 3>{}); break;
+        default: try6(Riccati6<P, 2>{}); break;
+      }
+      if (rc6 > 0) return rc6;
+      ric_done = rc6 == 0;
+    }
+#if HB_DEVICE_BUILD
+    if constexpr (RiccatiTma2<P>::SUPPORTED) {
+      if (variant >= 2 && !ric_done) {
+        cudaError_t e = launch_riccati_tma2<P>(a, s);
+        if (e != cudaSuccess) return (int)e;
+        ric_done = true;
+      }
+    }
+#endif
+    if (!ric_done) launch_1d<OcpRiccati<P>>(a, a.B, s);
+    return 0;
+  }
+
+  struct RiccatiOnlyInit {  // (b): solver state of a stand-alone sweep
+    static HB_HD void run(const OcpArgs& a, int b) {
+      double* st = a.st + (long long)b * ST_COUNT;
+      for (int i = 0; i < ST_COUNT; ++i) st[i] = 0.0;
+      st[ST_ACTIVE] = 1.0;
+      a.status[b] = 0;
+    }
+  };
+  struct RiccatiOnlyFinish {  // (b): edual out
+    static HB_HD void run(const OcpArgs& a, int b) { a.s_cinf[b] = a.st[(long long)b * ST_COUNT + ST_EDUAL]; }
+  };
+  static size_t riccati_work_doubles(int B) {
+    return (size_t)B * ST_COUNT + (size_t)B * T::N * T::KD + 64;
+  }
+  static int riccati(const hb_ocp_riccati_call* c) {
+    if (c == nullptr || c->B <= 0) return -1;
+    if (c->work == nullptr || c->work_doubles < riccati_work_doubles(c->B)) return -2;
+    if (!c->qa || !c->qh || !c->qpN || !c->dx || !c->du || !c->lam || !c->edual || !c->status) return -1;
+    OcpArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = c->B;
+    a.qa = const_cast<double*>(c->qa); a.qh = const_cast<double*>(c->qh); a.qpN = const_cast<double*>(c->qpN);
+    a.dx = c->dx; a.du = c->du; a.lam = c->lam; a.status = c->status;
+    double* w = c->work;
+    w += ((128 - (reinterpret_cast<uintptr_t>(w) & 127)) & 127) / 8;
+    a.st = w; w += ((size_t)c->B * ST_COUNT + 15) & ~(size_t)15;
+    a.fb = w;
+    a.s_cinf = c->edual;   // carrier of the per-instance result
+    cudaStream_t s = (cudaStream_t)c->stream;
+    launch_1d<RiccatiOnlyInit>(a, a.B, s);
+    const int rc = launch_riccati(a, c->riccati_variant, s);
+    if (rc != 0) return rc;
+    launch_1d<RiccatiOnlyFinish>(a, a.B, s);
+#if HB_DEVICE_BUILD
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : (int)e;
+#else
+    return 0;
+#endif
   }
 
   // doubles of workspace needed for a batch of B instances with n_alpha line-search candidates
@@ -166,36 +239,10 @@ struct OcpModule {
 #endif
       tm.end();
       tm.begin(K_RICCATI);
-      // riccati_variant: 0 = one thread per instance (any size; the reference version of the sweep),
-      // >= 2 = the fastest sweep the problem admits: warp-per-instance tensor-pipe sweep (riccati6.cuh) for the
-      // operand-order layout (nx <= 4, nu <= 2, x0 fixed), the cp.async ring with 8 lanes per instance (riccati2.cuh)
-      // for the compact layout; 6 / 8 / 9 select the register-ring depth 4 / 5 / 3 of riccati6 instead of 2 (tuning runs)
-      bool ric_done = false;
-      if (c->riccati_variant >= 2) {
-        int rc6 = -100;
-        auto try6 = [&](auto tag) {
-          using R = decltype(tag);
-          if constexpr (R::SUPPORTED) rc6 = launch_riccati6<R>(a, s);
-        };
-        switch (c->riccati_variant) {
-          case 6: try6(Riccati6<P, 4>{}); break;
-          case 8: try6(Riccati6<P, 5>{}); break;
-          case 9: try6(Riccati6<P, 3>{}); break;
-          default: try6(Riccati6<P, 2>{}); break;
-        }
-        if (rc6 > 0) return rc6;
-        ric_done = rc6 == 0;
+      {
+        const int rcr = launch_riccati(a, c->riccati_variant, s);
+        if (rcr != 0) return rcr;
       }
-#if HB_DEVICE_BUILD
-      if constexpr (RiccatiTma2<P>::SUPPORTED) {
-        if (c->riccati_variant >= 2 && !ric_done) {
-          cudaError_t e = launch_riccati_tma2<P>(a, s);
-          if (e != cudaSuccess) return (int)e;
-          ric_done = true;
-        }
-      }
-#endif
-      if (!ric_done) launch_1d<OcpRiccati<P>>(a, a.B, s);
       tm.end();
       bool fused = false;
 #if HB_DEVICE_BUILD
@@ -281,4 +328,6 @@ struct OcpModule {
   extern "C" size_t hbm_ocp_work_doubles(int B, int n_alpha) {                                            \
     return hb::OcpModule<PROB>::work_doubles(B, n_alpha);                                                 \
   }                                                                                                       \
-  extern "C" int hbm_ocp_solve(const hb_ocp_call* c) { return hb::OcpModule<PROB>::solve(c); }
+  extern "C" int hbm_ocp_solve(const hb_ocp_call* c) { return hb::OcpModule<PROB>::solve(c); }                   \
+  extern "C" size_t hbm_ocp_riccati_work_doubles(int B) { return hb::OcpModule<PROB>::riccati_work_doubles(B); } \
+  extern "C" int hbm_ocp_riccati(const hb_ocp_riccati_call* c) { return hb::OcpModule<PROB>::riccati(c); }

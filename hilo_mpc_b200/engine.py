@@ -152,6 +152,30 @@ class OcpEngine:
         return dict(x=t['x'], u=t['u'], xc=t['xc'] if d.nc else None, lam=t['lam'], status=t['status'],
                     iters=t['iters'][:B], stats=t['stats'])
 
+    def riccati(self, qa, qh, qpN, riccati_variant: int = 2):
+        """The Riccati sweep alone (``hb_ocp_riccati``): ``qa [B, N, block_a]``, ``qh [B, N, block_h]`` (see
+        ``stage_blocks.pack_stage_blocks``), ``qpN [B, nx*nx + 2 nx]`` CUDA tensors -> dict of ``dx``, ``du``, ``lam``,
+        ``edual``, ``status`` (device tensors)."""
+        torch = _lib.require_cuda()
+        self._open()
+        lib = _lib.load()
+        d = self.dims
+        f8 = dict(dtype=torch.float64, device=self._device)
+        qa, qh, qpN = (v.to(**f8).contiguous() for v in (qa, qh, qpN))
+        B = qa.shape[0]
+        out = dict(dx=torch.zeros(B, d.N + 1, d.nx, **f8), du=torch.zeros(B, d.N, d.nu, **f8),
+                   lam=torch.zeros(B, d.N + 1, d.nx, **f8), edual=torch.zeros(B, **f8),
+                   status=torch.zeros(B, dtype=torch.int32, device=self._device))
+        work = torch.empty(lib.hb_ocp_riccati_work_doubles(self._handle, B), **f8)
+        call = _lib.OcpRiccatiCall(B=B, riccati_variant=riccati_variant, qa=qa.data_ptr(), qh=qh.data_ptr(),
+                                   qpN=qpN.data_ptr(), dx=out['dx'].data_ptr(), du=out['du'].data_ptr(),
+                                   lam=out['lam'].data_ptr(), edual=out['edual'].data_ptr(),
+                                   status=out['status'].data_ptr(), work=work.data_ptr(), work_doubles=work.numel(),
+                                   stream=torch.cuda.current_stream(self._device).cuda_stream)
+        _lib.check(lib.hb_ocp_riccati(self._handle, C.byref(call)), 'hb_ocp_riccati')
+        self._keep_ric = (qa, qh, qpN, work)
+        return out
+
     def close(self):
         if self._handle is not None:
             _lib.load().hb_ocp_close(self._handle)

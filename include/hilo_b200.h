@@ -46,6 +46,12 @@ typedef struct hb_ocp_dims {
   int method;               /* 0 collocation, 1 explicit RK, 2 discrete                                         */
   int fixed_x0;             /* 1: x_0 pinned to the measured state (NMPC), 0: free (MHE)                        */
   int n_state;              /* doubles of per-instance solver statistics                                        */
+  int block_a, block_h;     /* doubles of one stage block of qa = [A B b] / qh = [Q S R q r qbar rbar] as the sweep
+                               reads them (hb_ocp_riccati)                                                      */
+  int frag;                 /* 1: blocks in tensor-core operand order (nx <= 4, nu <= 2, x0 fixed): qa = the 4 x 8 matrix
+                               [A B b 0] column-major, qh = the 6 x 8 tile [Q S^T q qbar; S R r rbar] row-major, zero
+                               padded (ones on the diagonal of the R pad); 0: compact row-major blocks
+                               [A | B | b] and [Q | S | R | q | r | qbar | rbar], padded to an even number of doubles */
 } hb_ocp_dims;
 
 typedef struct hb_ocp_call {
@@ -104,11 +110,32 @@ typedef struct hb_ocp_call {
 #define HB_OCP_KERNELS 11
 #define HB_OCP_KERNEL_NAMES "init,eval,riccati,expand,prep,trial,decide,apply,commit,count,step"
 
+/* The Riccati sweep of one interior-point iteration alone (unit tests, profiling): the block-banded KKT system
+ *   min sum_k 1/2 [dx;du]^T [Q S^T; S R] [dx;du] + [q;r]^T [dx;du] + terminal,  dx_{k+1} = A dx_k + B du_k + b,  dx_0 = 0
+ * of B instances, stage data in the module's block layout (hb_ocp_dims.block_a / block_h / frag).                      */
+typedef struct hb_ocp_riccati_call {
+  int B;
+  int riccati_variant;      /* as in hb_ocp_call */
+  const double* qa;         /* [B][N][block_a] */
+  const double* qh;         /* [B][N][block_h] */
+  const double* qpN;        /* [B][nx*nx + 2 nx] terminal block [Q_N | q_N | qbar_N] */
+  double* dx;               /* out [B][N+1][nx] */
+  double* du;               /* out [B][N][nu]   */
+  double* lam;              /* out [B][N+1][nx] adjoint of the multiplier-form gradient (lam_N = qbar_N) */
+  double* edual;            /* out [B] max_k |rbar_k + B_k^T lam_{k+1}| (dual infeasibility of the inputs) */
+  int* status;              /* out [B] 0 ok, -1 factorisation failed */
+  double* work;             /* hb_ocp_riccati_work_doubles(B) doubles */
+  size_t work_doubles;
+  void* stream;
+} hb_ocp_riccati_call;
+
 typedef struct hb_ocp* hb_ocp_t;
 int hb_ocp_open(const char* module_path, hb_ocp_t* out);
 int hb_ocp_get_dims(hb_ocp_t h, hb_ocp_dims* dims);
 size_t hb_ocp_work_doubles(hb_ocp_t h, int B, int n_alpha);
 int hb_ocp_solve(hb_ocp_t h, const hb_ocp_call* call);   /* synchronises `stream` only to poll convergence */
+size_t hb_ocp_riccati_work_doubles(hb_ocp_t h, int B);
+int hb_ocp_riccati(hb_ocp_t h, const hb_ocp_riccati_call* call);   /* asynchronous on `stream` */
 int hb_ocp_close(hb_ocp_t h);
 
 /* ------------------------------------------------------------------------------------------------ estimators

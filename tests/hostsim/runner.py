@@ -11,7 +11,7 @@ import numpy as np
 
 class OcpDims(C.Structure):
     _fields_ = [(n, C.c_int) for n in ('nx', 'nu', 'N', 'nc', 'nsp', 'ntp', 'nuold', 'nap', 'stage_doubles',
-                                       'elim_doubles', 'method', 'fixed_x0', 'n_state')]
+                                       'elim_doubles', 'method', 'fixed_x0', 'n_state', 'block_a', 'block_h', 'frag')]
 
 
 _DP = C.POINTER(C.c_double)
@@ -36,7 +36,34 @@ def _dp(a):
     return a.ctypes.data_as(_DP)
 
 
+class OcpRiccatiCall(C.Structure):
+    _fields_ = [('B', C.c_int), ('riccati_variant', C.c_int), ('qa', C.c_void_p), ('qh', C.c_void_p),
+                ('qpN', C.c_void_p), ('dx', C.c_void_p), ('du', C.c_void_p), ('lam', C.c_void_p),
+                ('edual', C.c_void_p), ('status', C.c_void_p), ('work', C.c_void_p), ('work_doubles', C.c_size_t),
+                ('stream', C.c_void_p)]
+
+
 class HostOcp:
+    def riccati(self, qa, qh, qpN, riccati_variant=0):
+        """The sweep alone through the module's hbm_ocp_riccati entry (host build)."""
+        d = self.dims
+        qa, qh, qpN = (np.ascontiguousarray(v, dtype=np.float64) for v in (qa, qh, qpN))
+        B = qa.shape[0]
+        dx, du, lam = np.zeros((B, d.N + 1, d.nx)), np.zeros((B, d.N, d.nu)), np.zeros((B, d.N + 1, d.nx))
+        edual, status = np.zeros(B), np.zeros(B, dtype=np.int32)
+        self.lib.hbm_ocp_riccati_work_doubles.restype = C.c_size_t
+        self.lib.hbm_ocp_riccati_work_doubles.argtypes = [C.c_int]
+        work = np.zeros(self.lib.hbm_ocp_riccati_work_doubles(B))
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        call = OcpRiccatiCall(B=B, riccati_variant=riccati_variant, qa=vp(qa), qh=vp(qh), qpN=vp(qpN), dx=vp(dx),
+                              du=vp(du), lam=vp(lam), edual=vp(edual), status=vp(status), work=vp(work),
+                              work_doubles=work.size, stream=None)
+        self.lib.hbm_ocp_riccati.argtypes = [C.POINTER(OcpRiccatiCall)]
+        rc = self.lib.hbm_ocp_riccati(C.byref(call))
+        if rc != 0:
+            raise RuntimeError(f"hbm_ocp_riccati returned {rc}")
+        return dict(dx=dx, du=du, lam=lam, edual=edual, status=status)
+
     def __init__(self, so_path):
         self.lib = C.CDLL(so_path)
         self.lib.hbm_ocp_dims.argtypes = [C.POINTER(OcpDims)]

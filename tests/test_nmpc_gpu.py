@@ -262,3 +262,35 @@ def test_compaction_of_straggler_iterations_is_bitwise_neutral(cuda_device):
     assert spread >= 2, 'test problem should have stragglers'
     for k in ('x', 'u', 'lam', 'iters'):
         assert torch.equal(res[0][k], res[1][k]), k
+
+
+def test_sweep_entry_point_on_the_device(cuda_device):
+    """hb_ocp_riccati on the GPU (B = 1000 random instances, N = 50): the warp-per-instance tensor-pipe sweep equals the
+    one-thread-per-instance sweep and a plain NumPy recursion; indefinite R blocks take the regularising path."""
+    import torch
+    from hilo_mpc_b200.examples import cstr_nmpc
+    from hilo_mpc_b200.stage_blocks import pack_stage_blocks, riccati_reference
+    from test_hostsim_riccati import _random_stage_data
+    eng = cstr_nmpc(N=50).engine
+    eng._open()
+    d = eng.dims
+    assert d.frag == 1
+    rng = np.random.default_rng(5)
+    B = 1000
+    for indefinite_every in (0, 64):
+        A, Bm, b, Q, S, R, q, r, qb, rb, QN, qN, qbN = _random_stage_data(rng, B, d.N, d.nx, d.nu, indefinite_every)
+        qa, qh = pack_stage_blocks(d, A, Bm, b, Q, S, R, q, r, qb, rb)
+        qpN = np.concatenate([QN.reshape(B, -1), qN, qbN], axis=1)
+        t = lambda a: torch.tensor(a, device=cuda_device)
+        ref = eng.riccati(t(qa), t(qh), t(qpN), riccati_variant=0)
+        out = eng.riccati(t(qa), t(qh), t(qpN), riccati_variant=2)
+        assert (ref['status'] == 0).all() and (out['status'] == 0).all()
+        scale = max(1., ref['du'].abs().max().item())
+        tol = 1e-11 if not indefinite_every else 1e-8
+        for k in ('dx', 'du', 'lam'):
+            assert (out[k] - ref[k]).abs().max().item() <= tol * max(scale, ref[k].abs().max().item()), k
+        assert ((out['edual'] - ref['edual']).abs() <= 1e-12 * ref['edual'].abs()).all()
+        if not indefinite_every:
+            dx, du = riccati_reference(A[7], Bm[7], b[7], Q[7], S[7], R[7], q[7], r[7], QN[7], qN[7])
+            np.testing.assert_allclose(out['dx'][7].cpu().numpy(), dx, atol=1e-10)
+            np.testing.assert_allclose(out['du'][7].cpu().numpy(), du, atol=1e-10)
