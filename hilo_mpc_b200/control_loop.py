@@ -11,8 +11,6 @@ the trajectory is written to ``plant.solution`` (and to ``controller.solution`` 
 """
 from __future__ import annotations
 
-from typing import Optional
-
 import numpy as np
 
 from .simulate import _engine
