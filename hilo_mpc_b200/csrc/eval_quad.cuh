@@ -19,13 +19,21 @@
 namespace hb {
 
 // terminal node only (the k == N branch of OcpEval), launched over instances
-// What the quad kernel leaves to the one-thread-per-node body, as ONE launch over (instance, k = 0..N): the terminal node
-// (k = N), and the nodes whose statically pivoted elimination met a degenerate pivot (recomputed with partial pivoting)
+// What the quad kernel leaves to the one-thread-per-node body, as ONE launch: the terminal node (k = N) and the nodes
+// whose statically pivoted elimination met a degenerate pivot (recomputed with partial pivoting).  The body needs 255
+// registers, so a thread per node would cost five waves of threads that only read a flag: one thread takes CHUNK
+// consecutive nodes of an instance instead (index space (instance, chunk)); flagged nodes are rare and handled in turn.
 template <class P>
 struct OcpEvalTail {
-  static HB_HD void run(const OcpArgs& a, int i, int k) {
+  static constexpr int CHUNK = 8;
+  static constexpr int NCHUNK = (OcpT<P>::N + 1 + CHUNK - 1) / CHUNK;
+  static HB_HD void run(const OcpArgs& a, int i, int c) {
+    constexpr int N = OcpT<P>::N;
     const int b = a.instance(i);
-    if (k == OcpT<P>::N || a.nflag[(long long)b * OcpT<P>::N + k] != 0) OcpEval<P>::run(a, b, k);
+    if (a.st[(long long)b * ST_COUNT + ST_ACTIVE] == 0.0) return;
+    const int k1 = (c + 1) * CHUNK < N + 1 ? (c + 1) * CHUNK : N + 1;
+    for (int k = c * CHUNK; k < k1; ++k)
+      if (k == N || a.nflag[(long long)b * N + k] != 0) OcpEval<P>::run(a, b, k);
   }
 };
 
@@ -540,7 +548,7 @@ inline cudaError_t launch_eval_quad(const OcpArgs& a, cudaStream_t s) {
   const long long nodes = (long long)a.n_instances() * OcpT<P>::N;
   const int grid = (int)((nodes + E::QUADS - 1) / E::QUADS);
   eval_quad_kernel<P><<<grid, 128, E::SMEM_BYTES, s>>>(a);
-  launch_2d<OcpEvalTail<P>>(a, a.n_instances(), OcpT<P>::N + 1, s);
+  launch_2d<OcpEvalTail<P>>(a, a.n_instances(), OcpEvalTail<P>::NCHUNK, s);
   return cudaGetLastError();
 }
 
