@@ -8,11 +8,14 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline``
 import this package.  The product (``hilo_mpc_b200``) never does; it fails loudly if the CUDA library is missing.
 
 Parity status:
-* KF / EKF / UKF / LQR-Riccati / SE-Gram / GP-LML: pinned by the golden numbers in the reference's own tests
-  (``tests/test_KFs.py``, ``tests/test_LQR.py``, ``tests/test_kernels.py``, ``tests/test_GPs.py``) — reproduced in
-  ``tests/test_oracle_golden.py``.
+* KF / EKF / UKF (one step and the 3-state bioreactor sigma-point matrices) / LQR-Riccati / SE, Matern and exponential
+  Gram matrices / GP-LML / fitted GP hyper-parameters (gpml values, with and without a trainable mean): pinned by the
+  golden numbers in the reference's own tests (``tests/test_KFs.py``, ``tests/test_LQR.py``, ``tests/test_kernels.py``,
+  ``tests/test_GPs.py``) — reproduced in ``tests/test_oracle_golden.py``.
 * NMPC / LMPC / MHE / PF-estimate: the reference's tests hold NO numeric assertion for these and the reference
   cannot be executed here (``casadi`` is not installed) -> "parity unpinned" at the IPOPT/qpOASES boundary.  The
   oracle restates the transcription exactly and is validated by its own KKT residual, by SciPy's independent
-  solvers on small instances and by the LQR golden in the linear-quadratic special case.
+  solvers (SLSQP on the flat NMPC and MHE problems, trust-constr on the condensed LMPC QP:
+  ``tests/test_oracle_crosscheck.py``, ``tests/test_hostsim_lmpc_mhe.py``) and by the LQR golden in the linear-quadratic
+  special case.  ``tools/run_reference.py`` produces golden vectors with the real reference where CasADi exists.
 """
