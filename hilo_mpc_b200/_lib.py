@@ -56,11 +56,12 @@ def load() -> C.CDLL:
     if _lib is not None:
         return _lib
     path = LIB_PATH
-    if not os.path.exists(path):
-        try:
-            build_core()
-        except Exception as exc:  # noqa: BLE001
+    try:
+        build_core()   # no-op unless the library is missing or older than its sources (nvcc needed only then)
+    except Exception as exc:  # noqa: BLE001
+        if not os.path.exists(path):
             raise EngineUnavailable(f"libhilo_b200.so is missing and could not be built: {exc}") from exc
+        raise EngineUnavailable(f"libhilo_b200.so is older than its sources and could not be rebuilt: {exc}") from exc
     try:
         lib = C.CDLL(path)
     except OSError as exc:
@@ -82,22 +83,31 @@ def load() -> C.CDLL:
     return lib
 
 
+ABI_VERSION = 2   # HB_ABI_VERSION of include/hilo_b200.h this binding was written against
+
+
 def _register_optional(lib: C.CDLL) -> None:
-    """argtypes for the model-independent kernels (declared in include/hilo_b200.h)."""
-    vp, i, d, ll = C.c_void_p, C.c_int, C.c_double, C.c_longlong
+    """argtypes of the model-independent entry points, exactly as declared in include/hilo_b200.h."""
+    vp, i, d, sz = C.c_void_p, C.c_int, C.c_double, C.c_size_t
+    fit = [i, i, vp, vp, vp, d, d, d, vp, vp, vp, vp, vp, vp, vp]
+    pred = [i, i, i, vp, vp, vp, d, d, d, vp, vp, vp, vp, vp, vp]
     sigs = {
-        'hb_riccati_solve': [i, i, i, i, vp, vp, vp, vp, vp, vp, i, vp],
-        'hb_pf_resample': [i, i, vp, vp, vp, vp],
-        'hb_kf_step': [i, i, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i, vp],
-        'hb_gp_fit': [i, i, vp, vp, vp, d, d, vp, vp, vp, vp, vp],
-        'hb_gp_predict': [i, i, i, vp, vp, vp, vp, d, vp, vp, vp, i, vp],
-        'hb_lmpc_solve': None,
+        'hb_pf_resample': ([i, i, vp, vp, vp, vp, vp], i),
+        'hb_gp_fit_work_doubles': ([i], sz),
+        'hb_gp_predict_work_doubles': ([i, i], sz),
+        'hb_gp_fit': (fit, i),
+        'hb_gp_predict': (pred, i),
+        'hb_gp_fit_kernel': ([i] + fit, i),
+        'hb_gp_predict_kernel': ([i] + pred, i),
     }
-    for name, args in sigs.items():
-        fn = getattr(lib, name, None)
-        if fn is not None and args is not None:
-            fn.argtypes = args
-            fn.restype = C.c_int
+    for name, (args, res) in sigs.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = res
+    v = lib.hb_version()
+    if v != ABI_VERSION:
+        raise EngineUnavailable(f"libhilo_b200.so reports ABI version {v}, this package expects {ABI_VERSION}: "
+                                f"rebuild it (python -m hilo_mpc_b200.build --force)")
 
 
 def last_error() -> str:

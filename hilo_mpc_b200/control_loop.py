@@ -57,7 +57,7 @@ class SimpleControlLoop:
         xc = x[:, self._ind_states].contiguous()
         if self._has_optimize:
             cp = p
-            tvp_names = getattr(self._controller, '_time_varying_parameters', None) or []
+            tvp_names = getattr(self._controller, '_tvp_names', None) or []
             if p is not None and len(tvp_names) > 0:   # control_loop.py:357-362
                 keep = [i for i, n in enumerate(self._plant.parameter_names) if n not in tvp_names]
                 cp = [np.asarray(p, dtype=float).reshape(-1)[i] for i in keep]

@@ -67,6 +67,7 @@ struct EstModule {
 }  // namespace hb
 
 #define HB_DEFINE_EST_MODULE(EPROB)                                                                    \
+  extern "C" int hbm_abi_version() { return HB_ABI_VERSION; }                                          \
   extern "C" void hbm_est_dims(hb_est_dims* d) { hb::EstModule<EPROB>::dims(d); }                      \
   extern "C" size_t hbm_est_work_doubles(int B, int n) { return hb::EstModule<EPROB>::work_doubles(B, n); } \
   extern "C" int hbm_sim_step(const hb_est_call* c) { return hb::EstModule<EPROB>::sim(c); }           \

@@ -46,7 +46,7 @@ struct hb_est {
 
 extern "C" {
 
-int hb_version(void) { return 1; }
+int hb_version(void) { return HB_ABI_VERSION; }
 
 const char* hb_last_error(void) { return g_err; }
 
@@ -77,6 +77,17 @@ int hb_ocp_open(const char* module_path, hb_ocp_t* out) {
     dlclose(dl);
     delete h;
     return -3;
+  }
+  {
+    int (*abi)() = (int (*)())dlsym(dl, "hbm_abi_version");
+    const int v = abi ? abi() : 0;
+    if (v != HB_ABI_VERSION) {
+      set_err("hb_ocp_open: %s was built for ABI version %d, the library is version %d (stale module: rebuild it)",
+              module_path, v, HB_ABI_VERSION);
+      dlclose(dl);
+      delete h;
+      return -5;
+    }
   }
   h->dims(&h->d);
   *out = h;
@@ -133,6 +144,17 @@ int hb_est_open(const char* module_path, hb_est_t* out) {
     dlclose(dl);
     delete h;
     return -3;
+  }
+  {
+    int (*abi)() = (int (*)())dlsym(dl, "hbm_abi_version");
+    const int v = abi ? abi() : 0;
+    if (v != HB_ABI_VERSION) {
+      set_err("hb_est_open: %s was built for ABI version %d, the library is version %d (stale module: rebuild it)",
+              module_path, v, HB_ABI_VERSION);
+      dlclose(dl);
+      delete h;
+      return -5;
+    }
   }
   h->dims(&h->d);
   *out = h;

@@ -324,6 +324,7 @@ struct OcpModule {
 }  // namespace hb
 
 #define HB_DEFINE_OCP_MODULE(PROB)                                                                        \
+  extern "C" int hbm_abi_version() { return HB_ABI_VERSION; }                                             \
   extern "C" void hbm_ocp_dims(hb_ocp_dims* d) { hb::OcpModule<PROB>::dims(d); }                          \
   extern "C" size_t hbm_ocp_work_doubles(int B, int n_alpha) {                                            \
     return hb::OcpModule<PROB>::work_doubles(B, n_alpha);                                                 \

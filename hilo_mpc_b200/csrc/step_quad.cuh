@@ -59,7 +59,7 @@ struct StepQuad {
     // the per-instance solver state is edited by thread 0 between the phases: work on a shared-memory copy (one
     // coalesced load, no global round trips on the serial path) and write it back at the end
     double* st = smem + oST;
-    if (tid < ST_COUNT) st[tid] = stg[tid];
+    for (int i = tid; i < ST_COUNT; i += THREADS) st[i] = stg[i];   // THREADS may be < ST_COUNT (N <= 7)
     const double mu = stg[ST_MU];
     const double tau = dmax(0.99, 1.0 - mu);
     const bool node = k <= N, inter = k < N;
@@ -90,7 +90,7 @@ struct StepQuad {
       }
       __syncthreads();
       if ((int)ctrl[C_FLAG] == F_STOP) {
-        if (tid < ST_COUNT) stg[tid] = st[tid];
+        for (int i = tid; i < ST_COUNT; i += THREADS) stg[i] = st[i];
         return;
       }
       __syncthreads();   // ctrl / red are rewritten below
@@ -194,7 +194,8 @@ struct StepQuad {
     }
     __syncthreads();
     // per-instance line-search context, thread 0 only
-    double theta0 = 0.0, phi0 = 0.0, dphi0 = 0.0, err = 0.0, last_finite = -1.0;
+    double theta0 = 0.0, phi0 = 0.0, dphi0 = 0.0, err = 0.0, last_finite = -1.0, alpha_full = 0.0;
+    bool full_finite = false;
     int nf = 0;
     if (tid == 0) {
       double rap = 1.0, rad = 1.0, rd = 0.0, rc1 = 0.0, rphi = 0.0, rcinf = 0.0, rcomp = 0.0;
@@ -222,7 +223,7 @@ struct StepQuad {
     for (int ai = 0;; ++ai) {
       const int flag = (int)ctrl[C_FLAG];
       if (flag == F_STOP) {
-        if (tid < ST_COUNT) stg[tid] = st[tid];
+        for (int i = tid; i < ST_COUNT; i += THREADS) stg[i] = st[i];
         return;
       }
       if (flag == F_APPLY) break;
@@ -308,13 +309,15 @@ struct StepQuad {
         for (int w = 0; w < WARPS; ++w) { pht += red[w]; tht += red[32 + w]; }
         const LsVerdict vd = ls_candidate(a, st, alpha, pht, tht, theta0, phi0, dphi0, nf);
         if (vd.finite && (ai > 0 || a.n_alpha == 1)) last_finite = alpha;
+        if (ai == 0) { full_finite = vd.finite; alpha_full = alpha; }
         double chosen = -1.0;
         bool decided = false, augment = false;
         if (vd.accept) { chosen = alpha; augment = vd.augment; decided = true; }
         else if (ai + 1 >= a.n_alpha) {
-          // no candidate acceptable: smallest finite backtracking candidate, else the smallest one (no restoration phase)
+          // no candidate acceptable: smallest finite backtracking candidate, else the full step if only that was
+          // finite, else the instance fails with status -1 (same rule as OcpDecide; no restoration phase)
           chosen = last_finite;
-          if (chosen < 0.0 && a.n_alpha > 1) chosen = alpha;
+          if (chosen < 0.0 && a.n_alpha > 1 && full_finite) chosen = alpha_full;
           decided = true;
         }
         if (decided) {
@@ -348,7 +351,7 @@ struct StepQuad {
       }
     }
     // write the state back; the barrier parameter chosen by the line search is committed on the way
-    if (tid < ST_COUNT) stg[tid] = (tid == ST_MU) ? st[ST_NACC] : st[tid];
+    for (int i = tid; i < ST_COUNT; i += THREADS) stg[i] = (i == ST_MU) ? st[ST_NACC] : st[i];
   }
 };
 

@@ -180,7 +180,16 @@ class _KalmanFilter(_Estimator):
                  R=eng.tensor(self._R), y_pred=ypred, status=status, substeps=self._substeps, do_predict=do_predict,
                  do_update=do_update, t0=self._t, **extra)
         self._last_status = status
+        if self._single:   # one filter: a failed factorisation is an error (the batched path exposes `last_status`)
+            if int(status[0].item()) != 0:
+                raise RuntimeError(f"{self._label}: numerical failure (covariance not positive definite or singular "
+                                   f"innovation covariance); the estimate was left unchanged")
         return ypred
+
+    @property
+    def last_status(self):
+        """Per-instance status of the last step (device int32 tensor): 0 ok, -1 numerical failure (estimate unchanged)."""
+        return getattr(self, '_last_status', None)
 
     def _extra(self, B, torch, eng):
         return {}
@@ -302,6 +311,9 @@ class UnscentedKalmanFilter(_KalmanFilter):
         if pred.shape[1] >= 1 + n + 2 * n + 1:
             self._engine.open()
             self._X = self._engine.tensor(pred[:, 1 + n:].T.copy()).reshape(1, 2 * n + 1, n)
+        elif self._X is None:
+            raise ValueError("UKF.update needs the propagated sigma points: pass the full matrix returned by predict() "
+                             "([x | P | X], kf.py:549-553)")
 
 
 class ParticleFilter(_Estimator):

@@ -206,6 +206,11 @@ class DynamicOptimization:
         return self._nlp_setup_done
 
     @property
+    def _time_varying_parameters(self):
+        """Name the reference's control loop reads (control_loop.py:357-362)."""
+        return self._tvp_names
+
+    @property
     def solver_status_code(self):
         return self._solver_status_code
 
@@ -475,6 +480,9 @@ class NMPC(DynamicOptimization):
                 raise ValueError(f"The model has {n_cp} constant parameter(s): pass them to optimize with cp=...")
             cpt = torch.as_tensor(np.asarray(cp, dtype=float) if not torch.is_tensor(cp) else cp,
                                   dtype=torch.float64, device=device)
+            if cpt.numel() not in (n_cp, n_cp * B):
+                raise ValueError(f"cp has {cpt.numel()} elements, expected {n_cp} (shared) or {n_cp * B} (one row "
+                                 f"per instance)")
             cpt = cpt.reshape(-1, n_cp)
             cols.append(cpt.unsqueeze(1).expand(cpt.shape[0], N, n_cp))
         for slots, names, scale in self._ref_slots_sc:

@@ -29,7 +29,9 @@ extern "C" {
 #endif
 
 /* ------------------------------------------------------------------------------------------------ library */
-int hb_version(void);                 /* ABI version (integer, bumps on incompatible change) */
+#define HB_ABI_VERSION 2              /* bumps on every incompatible change of a struct or signature below */
+int hb_version(void);                 /* HB_ABI_VERSION the library was built with; generated modules export the same
+                                         number (hbm_abi_version) and hb_ocp_open / hb_est_open refuse a mismatch (-5) */
 const char* hb_last_error(void);      /* host string describing the last failure on this thread */
 int hb_device_info(int device, int* sm_count, size_t* total_mem, int* cc_major, int* cc_minor);
 
