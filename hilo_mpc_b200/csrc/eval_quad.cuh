@@ -43,44 +43,56 @@ template <class P>
 struct EvalQuad {
   using T = OcpT<P>;
   static constexpr int NX = T::NX, NU = T::NU, NC = T::NC, NE = T::NE, N = T::N, D = P::DEG;
-  static constexpr int RPL = (NC + 3) / 4;   // rows per lane
-  static constexpr bool NX4 = (NX % 4 == 0); // then the collocation point of a local row is a compile-time constant
   static constexpr int W = NC + NE + 1;      // columns of the plain system  [G_X | G_x G_u | c]
   static constexpr int WT = NC + 1;          // columns of the transposed system
+  // lanes per node: 4 while the lane's rows of the plain system fit the register budget (the BASELINE CSTR: 3 rows x 19
+  // columns), 8 for larger nodes (nx = 5..6 with deg 3: 2 rows x 24..28 columns)
+  static constexpr int LPN = (((NC + 3) / 4) * W <= 64) ? 4 : 8;
+  static constexpr int NPW = 32 / LPN;       // nodes per warp
+  static constexpr int RPL = (NC + LPN - 1) / LPN;   // rows per lane
+  static constexpr bool NXL = (NX % LPN == 0);       // then the collocation point of a local row is a compile-time constant
   static constexpr int NV = NX + NU + NC;    // bounded variables of a node: x_k | u_k | X_k
-  static constexpr bool SUPPORTED = (P::METHOD == METHOD_COLLOCATION) && P::FIXED_X0 && !P::HAS_GADD && !P::HAS_ARR &&
-                                    !P::OBJ_DISCRETE && (D <= 3) && (RPL * W <= 64) && (NC >= 4);
-  // per-quad scratch (doubles), sized for 3 CTAs per SM.  Lifetimes:  F (model derivatives) until the plain system is
+  // cost terms that live on the node itself rather than on the collocation points: the discrete-type objective
+  // l(x_k, u_k) (MHE, 'objective_function': 'discrete') and the arrival cost on x_0; evaluated by lane D
+  static constexpr bool NODECOST = P::OBJ_DISCRETE || P::HAS_ARR;
+  static constexpr bool SUPPORTED = (P::METHOD == METHOD_COLLOCATION) && (D <= 3) && (D < LPN) && (RPL * W <= 64) &&
+                                    (NC >= 4);
+  // per-node scratch (doubles).  Lifetimes:  F (model derivatives) until the plain system is
   // assembled, then the same words hold T (its solution);  PB (pivot row) during the two eliminations, the collocation
   // multipliers NU in between;  L (weighted cost derivatives + constraint curvature) until the partial sums of the
-  // reduced Hessian exist - from then on [F/T | PB | L] is the quad-reduction area RED and only the sums over the
+  // reduced Hessian exist - from then on [F/T | PB | L] is the reduction area RED and only the sums over the
   // collocation points of lu / luu (SUM) are still needed.
   static constexpr int FSZ = NX + NX * NX + NX * NU;                             // f | fx | fu of one point
   static constexpr int LSZ = 1 + NX + NU + NX * NX + NU * NX + NU * NU;          // l | lx | lu | lxx | lux | luu (weighted)
-  // partial Hessian/gradient [NE][NE+1] + multiplier-form gradient of one lane; ODD stride between the lanes' copies:
-  // the quads of a warp sit on the even 8-byte bank pairs (SCR below), two lanes of a quad share a half-warp (lane
-  // mapping in run()), so the second lane must land on the odd ones
-  static constexpr int NRED = (NE * (NE + 1) + NE) | 1;
+  // partial sums of one lane: lower triangle of the reduced Hessian [NE][NE] row by row, the Newton gradient [NE], the
+  // multiplier-form gradient [NE]; ODD stride between the lanes' copies: the nodes of a warp sit on the even 8-byte bank
+  // pairs (SCR below), two lanes of a node share a half-warp (lane mapping in run()), so the second lane must land on the
+  // odd ones
+  static constexpr int NTRI = NE * (NE + 1) / 2;
+  static HB_HD constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }   // j <= i
+  static constexpr int NRED = (NTRI + 2 * NE) | 1;
   static constexpr int FT = (D * FSZ > NC * (NE + 1)) ? D * FSZ : NC * (NE + 1);
   static constexpr int PBN = (2 * ((W + 1) & ~1) > NC) ? 2 * ((W + 1) & ~1) : NC;
-  static constexpr int A1 = FT + PBN + D * LSZ, A2 = 4 * NRED;
+  static constexpr int A1 = FT + PBN + D * LSZ, A2 = LPN * NRED;
+  static constexpr int NCSZ = NODECOST ? (NX + NU + NX * NX + NU * NX + NU * NU) : 0;  // gx | gu | Qn | Sn | Rn of the node cost
   static constexpr int oF = 0, oT = 0, oPB = FT, oNU = oPB, oL = oPB + PBN, oRED = 0,
                        oSUM = (A1 > A2 ? A1 : A2),                       // sum_i lu_i [NU] | sum_i luu_i [NU*NU]
                        oBG = oSUM + NU + NU * NU, oBD = oBG + NV, oBS = oBD + NV,   // barrier gradient | dz | sigma of x|u|X
-                       oEND = oBS + NV;
+                       oNC = oBS + NV, oEND = oNC + NCSZ;
+  static constexpr int oNCu = oNC + NX, oNCQ = oNCu + NU, oNCS = oNCQ + NX * NX, oNCR = oNCS + NU * NX;
   static constexpr int oGX = oBG + NX + NU, oDGX = oBD + NX + NU, oSGX = oBS + NX + NU;
-  // stride = 2 (mod 16) doubles: 16-byte aligned, and the 8 quads of a warp start 4 banks apart (conflict-free 64- and
+  // stride = 2 (mod 16) doubles: 16-byte aligned, and the nodes of a warp start 4 banks apart (conflict-free 64- and
   // 128-bit accesses to the same offset)
   static constexpr int SCR = ((oEND + 13) / 16) * 16 + 2;
-  static constexpr int QUADS = 32;                   // quads (nodes) per CTA, 128 threads
+  static constexpr int QUADS = 128 / LPN;            // nodes per CTA, 128 threads
   static constexpr int SMEM_BYTES = QUADS * SCR * 8;
   static constexpr bool EL_VEC2 = (NE % 2 == 0) && (T::oT % 2 == 0) && (T::TD % 2 == 0);
 
-  // lanes q, q^m of the same quad (lane = q * 8 + quad-in-warp, see run())
-  static __device__ __forceinline__ double qshfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m << 3); }
-  static __device__ __forceinline__ int qshfl_xor(int v, int m) { return __shfl_xor_sync(0xffffffffu, v, m << 3); }
+  // lanes q, q^m of the same node (lane = q * NPW + node-in-warp, see run())
+  static __device__ __forceinline__ double qshfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m * NPW); }
+  static __device__ __forceinline__ int qshfl_xor(int v, int m) { return __shfl_xor_sync(0xffffffffu, v, m * NPW); }
 
-  // Gauss-Jordan on rows R[RPL][NCOLS] (row lr of lane q is global row lr*4 + q) with the STATIC pivot order
+  // Gauss-Jordan on rows R[RPL][NCOLS] (row lr of lane q is global row lr*LPN + q) with the STATIC pivot order
   // "row c for column c": no search, no row selection; the owner lane and its local row are compile-time constants.
   // The owner publishes its (unnormalised) pivot row, every lane forms its own multipliers with a Newton-refined
   // reciprocal, and the rows are scaled by their inverse pivots once at the end.
@@ -96,7 +108,7 @@ struct EvalQuad {
     for (int lr = 0; lr < RPL; ++lr) ipiv[lr] = 1.0;
 #pragma unroll
     for (int c = 0; c < NPIV; ++c) {
-      const int po = c & 3, plr = c >> 2;   // owner lane / local row of the pivot row
+      const int po = c % LPN, plr = c / LPN;   // owner lane / local row of the pivot row
       const int j0 = c & ~1;                 // first (even) column of the broadcast; column j0 < c is dead weight
       double* prow = pb + (c & 1) * PS;      // double-buffered broadcast row
       if (q == po) {
@@ -134,10 +146,10 @@ struct EvalQuad {
 
   static __device__ void run(const OcpArgs& a) {
     extern __shared__ __align__(16) double smem[];
-    // lane = q * 8 + quad-in-warp: the lanes with the same role q of the 8 quads of a warp are adjacent.  The pivot-row
-    // store of the elimination (one lane per quad, 128 bits) then comes from ONE quarter-warp = one shared-memory
-    // wavefront instead of four, and two (not four) lanes of a quad meet in a half-warp for the 64-bit accesses.
-    const int quad = ((threadIdx.x >> 5) << 3) | (threadIdx.x & 7), q = (threadIdx.x >> 3) & 3;
+    // lane = q * NPW + node-in-warp: the lanes with the same role q of the nodes of a warp are adjacent.  The pivot-row
+    // store of the elimination (one lane per node, 128 bits) then comes from ONE quarter-warp = one shared-memory
+    // wavefront instead of four, and two (not four) lanes of a node meet in a half-warp for the 64-bit accesses.
+    const int quad = ((threadIdx.x >> 5) * NPW) | (threadIdx.x & (NPW - 1)), q = (threadIdx.x & 31) / NPW;
     const long long node = (long long)blockIdx.x * QUADS + quad;
     const long long total = (long long)a.n_instances() * N;   // late iterations run over the list of active instances
     const bool valid = node < total;
@@ -145,7 +157,7 @@ struct EvalQuad {
     const int b = a.instance((int)(nn / N)), k = (int)(nn % N);
     const double* st = a.st + (long long)b * ST_COUNT;
     const bool active = valid && st[ST_ACTIVE] != 0.0;
-    // a whole warp (8 nodes) leaves together; partially active warps compute everything and mask the stores
+    // a whole warp leaves together; partially active warps compute everything and mask the stores
     if (!__any_sync(0xffffffffu, active)) return;
     double* S = smem + (size_t)quad * SCR;
     const double mu = st[ST_MU];
@@ -155,7 +167,7 @@ struct EvalQuad {
     const double* uo = a.uold + (long long)b * a.uold_stride;
     const bool with_lag = k >= P::LAG_FROM;
     const bool first = (k == 0) && (T::NUOLD > 0);
-    const bool x_free = (k > 0);
+    const bool x_free = (k > 0) || !P::FIXED_X0;
 
     // run-time indexed accesses go to global memory (L1-resident); register arrays are only indexed statically
     const double* xg = a.x + nb * NX;
@@ -169,13 +181,13 @@ struct EvalQuad {
     for (int i = 0; i < NU; ++i) u[i] = ug[i];
 
     double phi = 0.0, comp = 0.0, c1 = 0.0, cinf = 0.0, maxinv = 0.0;
-    // ---------------------------------------------------------------- 1a. barrier terms, 4 variables at a time
+    // ---------------------------------------------------------------- 1a. barrier terms, LPN variables at a time
     {
       BarrierSum bs;
 #pragma unroll
-      for (int it = 0; it < (NV + 3) / 4; ++it) {
-        const int e = it * 4 + q;
-        const bool ok = (it * 4 + 3 < NV) || (e < NV);
+      for (int it = 0; it < (NV + LPN - 1) / LPN; ++it) {
+        const int e = it * LPN + q;
+        const bool ok = (it * LPN + LPN - 1 < NV) || (e < NV);
         const double *vp, *lp, *up, *zlp, *zup;
         bool use = ok;
         if (e < NX) {
@@ -212,7 +224,7 @@ struct EvalQuad {
       P::f_jac(Xq, u, sp, ti, dt, F, F + NX, F + NX + NX * NX);
       double* L = S + oL + q * LSZ;
       double l = 0.0, lx[NX], lu[NU], lxx[NX * NX], lux[NU * NX], luu[NU * NU];
-      if (with_lag) {
+      if (with_lag && !P::OBJ_DISCRETE) {
         P::lag_all(Xq, u, sp, ti, dt, &l, lx, lu, lxx, lux, luu);
         if (first) {
           double l2, lu2[NU], luu2[NU * NU];
@@ -249,11 +261,59 @@ struct EvalQuad {
 #pragma unroll
       for (int j = 0; j < NU * NU; ++j) L[1 + NX + NU + NX * NX + NU * NX + j] = w * luu[j];
     }
+    if constexpr (NODECOST) {
+      if (q == D) {   // cost terms on the node itself: l(x_k, u_k) of a discrete-type objective, arrival cost on x_0
+        double xk[NX], gxn[NX], gun[NU], Qn[NX * NX], Sn[NU * NX], Rn[NU * NU];
+#pragma unroll
+        for (int j = 0; j < NX; ++j) { xk[j] = xg[j]; gxn[j] = 0.0; }
+#pragma unroll
+        for (int j = 0; j < NU; ++j) gun[j] = 0.0;
+#pragma unroll
+        for (int j = 0; j < NX * NX; ++j) Qn[j] = 0.0;
+#pragma unroll
+        for (int j = 0; j < NU * NX; ++j) Sn[j] = 0.0;
+#pragma unroll
+        for (int j = 0; j < NU * NU; ++j) Rn[j] = 0.0;
+        if (P::OBJ_DISCRETE && with_lag) {
+          double l;
+          P::lag_all(xk, u, sp, t, dt, &l, gxn, gun, Qn, Sn, Rn);
+          if (first) {
+            double l2, lu2[NU], luu2[NU * NU];
+            P::lagdu_all(u, uo, &l2, lu2, luu2);
+            l += l2;
+#pragma unroll
+            for (int j = 0; j < NU; ++j) gun[j] += lu2[j];
+#pragma unroll
+            for (int j = 0; j < NU * NU; ++j) Rn[j] += luu2[j];
+          }
+          phi += l;
+        }
+        if (P::HAS_ARR && k == 0) {
+          double val, g[NX], H[NX * NX];
+          P::arr_all(xk, a.ap + (long long)b * a.ap_stride, &val, g, H);
+          phi += val;
+#pragma unroll
+          for (int j = 0; j < NX; ++j) gxn[j] += g[j];
+#pragma unroll
+          for (int j = 0; j < NX * NX; ++j) Qn[j] += H[j];
+        }
+#pragma unroll
+        for (int j = 0; j < NX; ++j) S[oNC + j] = gxn[j];
+#pragma unroll
+        for (int j = 0; j < NU; ++j) S[oNCu + j] = gun[j];
+#pragma unroll
+        for (int j = 0; j < NX * NX; ++j) S[oNCQ + j] = Qn[j];
+#pragma unroll
+        for (int j = 0; j < NU * NX; ++j) S[oNCS + j] = Sn[j];
+#pragma unroll
+        for (int j = 0; j < NU * NU; ++j) S[oNCR + j] = Rn[j];
+      }
+    }
     __syncwarp();
     // gX (cost + barrier) for every collocation state: gX[r] = w*lx_i[j] + barrier grad
 #pragma unroll
     for (int lr = 0; lr < RPL; ++lr) {
-      const int r = lr * 4 + q;
+      const int r = lr * LPN + q;
       if (r < NC) S[oGX + r] += S[oL + (r / NX) * LSZ + 1 + (r % NX)];
     }
     __syncwarp();
@@ -264,8 +324,8 @@ struct EvalQuad {
       double Rt[RPL][WT];
 #pragma unroll
       for (int lr = 0; lr < RPL; ++lr) {
-        const int r = lr * 4 + q;       // row (i', cc) of G_X^T  = column of G_X
-        const int ip = NX4 ? (lr * 4) / NX : r / NX, cc = NX4 ? ((lr * 4) % NX + q) : r % NX;  // ip = i' - 1
+        const int r = lr * LPN + q;       // row (i', cc) of G_X^T  = column of G_X
+        const int ip = NXL ? (lr * LPN) / NX : r / NX, cc = NXL ? ((lr * LPN) % NX + q) : r % NX;  // ip = i' - 1
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
           const int i = c / NX, rr = c % NX;   // column (i, rr): row of G_X
@@ -281,7 +341,7 @@ struct EvalQuad {
       maxinv = fmax(maxinv, gauss_jordan<WT, NC>(Rt, q, S + oPB));
 #pragma unroll
       for (int lr = 0; lr < RPL; ++lr)
-        if (lr * 4 + q < NC) S[oNU + lr * 4 + q] = Rt[lr][NC];
+        if (lr * LPN + q < NC) S[oNU + lr * LPN + q] = Rt[lr][NC];
       __syncwarp();
       if (q < D) {
         double ctau = 0.0;
@@ -305,8 +365,8 @@ struct EvalQuad {
 
     // sums over the collocation points of the input gradient / input Hessian of the cost (the L area is recycled later)
 #pragma unroll
-    for (int it = 0; it < (NU + NU * NU + 3) / 4; ++it) {
-      const int e = it * 4 + q;
+    for (int it = 0; it < (NU + NU * NU + LPN - 1) / LPN; ++it) {
+      const int e = it * LPN + q;
       if (e < NU + NU * NU) {
         const int off = (e < NU) ? (1 + NX + e) : (1 + NX + NU + NX * NX + NU * NX + (e - NU));
         double sacc = 0.0;
@@ -321,8 +381,8 @@ struct EvalQuad {
       double R[RPL][W];
 #pragma unroll
       for (int lr = 0; lr < RPL; ++lr) {
-        const int r = lr * 4 + q;  // row (i, rr)
-        const int ii = NX4 ? (lr * 4) / NX : r / NX, rr = NX4 ? ((lr * 4) % NX + q) : r % NX;  // ii = i - 1
+        const int r = lr * LPN + q;  // row (i, rr)
+        const int ii = NXL ? (lr * LPN) / NX : r / NX, rr = NXL ? ((lr * LPN) % NX + q) : r % NX;  // ii = i - 1
         const bool rv = r < NC;
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
@@ -352,7 +412,7 @@ struct EvalQuad {
       // own T rows stay in registers and are published to the scratch pad for the other lanes
 #pragma unroll
       for (int lr = 0; lr < RPL; ++lr) {
-        const int r = lr * 4 + q;
+        const int r = lr * LPN + q;
 #pragma unroll
         for (int j = 0; j <= NE; ++j) {
           Tr[lr][j] = (r < NC) ? -R[lr][NC + j] : 0.0;
@@ -367,14 +427,18 @@ struct EvalQuad {
     double* qh = a.qh + ((long long)b * T::N + k) * T::NHp;
     double* el = a.el + sb * T::TD;
     const double* Tm = S + oT;
-    // dynamics rows (lane q -> state rows q, q+4, ...)
+    // dynamics rows (lane q -> state rows q, q+LPN, ...)
 #pragma unroll
-    for (int it = 0; it < (NX + 3) / 4; ++it) {
-      const int rr = it * 4 + q;
+    for (int it = 0; it < (NX + LPN - 1) / LPN; ++it) {
+      const int rr = it * LPN + q;
       if (rr < NX) {
         double xf = P::CD(0) * xg[rr], bsum = 0.0;
 #pragma unroll
         for (int i = 1; i <= D; ++i) { xf += P::CD(i) * Xg[(i - 1) * NX + rr]; bsum += P::CD(i) * Tm[((i - 1) * NX + rr) * (NE + 1) + NE]; }
+        if (P::HAS_GADD) {
+#pragma unroll
+          for (int c = 0; c < NU; ++c) xf += P::GADD(rr * NU + c) * u[c];
+        }
         const double res = xf - xng[rr];
         c1 += dabs(res); cinf = dmax(cinf, dabs(res));
         if (active) {
@@ -387,7 +451,7 @@ struct EvalQuad {
           }
 #pragma unroll
           for (int c = 0; c < NU; ++c) {
-            double s = 0.0;
+            double s = P::HAS_GADD ? P::GADD(rr * NU + c) : 0.0;
 #pragma unroll
             for (int i = 1; i <= D; ++i) s += P::CD(i) * Tm[((i - 1) * NX + rr) * (NE + 1) + NX + c];
             qa[T::iB(rr, c)] = s;
@@ -396,12 +460,12 @@ struct EvalQuad {
         }
       }
     }
-    if (active) T::fill_pads(qa, qh, q, 4);   // operand-order layout: zero column of M, pads of small problems
+    if (active) T::fill_pads(qa, qh, q, LPN);   // operand-order layout: zero column of M, pads of small problems
     // elimination block for Expand, own rows straight from the registers: T | t0 | gX
     if (active) {
 #pragma unroll
       for (int lr = 0; lr < RPL; ++lr) {
-        const int r = lr * 4 + q;
+        const int r = lr * LPN + q;
         if (r < NC) {
           if constexpr (EL_VEC2) {
             double2* dst = reinterpret_cast<double2*>(el + T::oT + r * NE);
@@ -416,24 +480,23 @@ struct EvalQuad {
         }
       }
     }
-    // Partial sums over the OWN rows r = (i, l), all operands in registers:
-    //   Pq[ii][jj] += T[r][ii] * HT[r][jj]        HT[r][:] = (H_i + diag sigma)[l][:] T_i[:][:]  (+ gX[r] in column NE)
-    //   Pq[NX+a][jj] += Hu_i[a][l] * T[r][jj]     (jj = 0..NE; column NE is the gradient)
-    //   Pq[NX+b][NX+a] += Hu_i[a][l] * T[r][NX+b]
-    //   gb[ii]      += T[r][ii] * (gX + dz)[r]    multiplier-form gradient
-    // The block Pq[ii < NX][NX <= jj < NE] (S transposed) is never needed and not formed.
-    double Pq[NE][NE + 1], gbp[NE];
+    // Partial sums over the OWN rows r = (i, l), all operands in registers; only the LOWER triangle of the (symmetric)
+    // reduced Hessian is formed:
+    //   Pt[ii][jj] += T[r][ii] * HT[r][jj]        HT[r][:] = (H_i + diag sigma)[l][:] T_i[:][:]         (jj <= ii)
+    //   Pt[NX+a][jj] += Hu_i[a][l] * T[r][jj]     (jj <= NX+a)
+    //   Pt[NX+b][NX+a] += Hu_i[a][l] * T[r][NX+b] (a <= b: the transposed twin of the line above inside the R block)
+    //   gq[ii]      += T[r][ii] * HT[r][NE]  (+ Hu_i[a][l] T[r][NE] for input rows)   Newton gradient, HT[r][NE] incl. gX[r]
+    //   gb[ii]      += T[r][ii] * (gX + dz)[r]                                         multiplier-form gradient
+    double Pt[NTRI], gq[NE], gbp[NE];
 #pragma unroll
-    for (int ii = 0; ii < NE; ++ii) {
-      gbp[ii] = 0.0;
+    for (int ii = 0; ii < NE; ++ii) { gbp[ii] = 0.0; gq[ii] = 0.0; }
 #pragma unroll
-      for (int jj = 0; jj <= NE; ++jj) Pq[ii][jj] = 0.0;
-    }
+    for (int e = 0; e < NTRI; ++e) Pt[e] = 0.0;
 #pragma unroll
     for (int lr = 0; lr < RPL; ++lr) {
-      const int r = lr * 4 + q;
+      const int r = lr * LPN + q;
       if (r < NC) {
-        const int ii0 = NX4 ? (lr * 4) / NX : r / NX, l = NX4 ? ((lr * 4) % NX + q) : r % NX;
+        const int ii0 = NXL ? (lr * LPN) / NX : r / NX, l = NXL ? ((lr * LPN) % NX + q) : r % NX;
         const double* Hx = S + oL + ii0 * LSZ + 1 + NX + NU + l * NX;
         const double* Hu = S + oL + ii0 * LSZ + 1 + NX + NU + NX * NX;
         const double gXr = S[oGX + r];
@@ -452,17 +515,18 @@ struct EvalQuad {
 #pragma unroll
         for (int ii = 0; ii < NE; ++ii) {
           gbp[ii] += Tr[lr][ii] * gbx;
+          gq[ii] += Tr[lr][ii] * HTr[NE];
 #pragma unroll
-          for (int jj = 0; jj <= NE; ++jj)
-            if (!(ii < NX && jj >= NX && jj < NE)) Pq[ii][jj] += Tr[lr][ii] * HTr[jj];
+          for (int jj = 0; jj <= ii; ++jj) Pt[tri(ii, jj)] += Tr[lr][ii] * HTr[jj];
         }
 #pragma unroll
         for (int aa = 0; aa < NU; ++aa) {
           const double hu = Hu[aa * NX + l];
+          gq[NX + aa] += hu * Tr[lr][NE];
 #pragma unroll
-          for (int jj = 0; jj <= NE; ++jj) Pq[NX + aa][jj] += hu * Tr[lr][jj];
+          for (int jj = 0; jj <= NX + aa; ++jj) Pt[tri(NX + aa, jj)] += hu * Tr[lr][jj];
 #pragma unroll
-          for (int bb = 0; bb < NU; ++bb) Pq[NX + bb][NX + aa] += hu * Tr[lr][NX + bb];
+          for (int bb = aa; bb < NU; ++bb) Pt[tri(NX + bb, NX + aa)] += hu * Tr[lr][NX + bb];
         }
       }
     }
@@ -470,31 +534,34 @@ struct EvalQuad {
     {
       double* red = S + oRED + q * NRED;
 #pragma unroll
-      for (int ii = 0; ii < NE; ++ii) {
+      for (int e = 0; e < NTRI; ++e) red[e] = Pt[e];
 #pragma unroll
-        for (int jj = 0; jj <= NE; ++jj)
-          if (!(ii < NX && jj >= NX && jj < NE)) red[ii * (NE + 1) + jj] = Pq[ii][jj];
-        red[NE * (NE + 1) + ii] = gbp[ii];
-      }
+      for (int ii = 0; ii < NE; ++ii) { red[NTRI + ii] = gq[ii]; red[NTRI + NE + ii] = gbp[ii]; }
     }
     __syncwarp();
-    // every lane finalises whole rows (lane q -> rows q, q+4, ...): the column index is static
+    // every lane finalises whole rows (lane q -> rows q, q+LPN, ...): the column index is static
+    auto rsum = [&](int e) {   // sum of entry e over the lanes' copies
+      double v = S[oRED + e];
 #pragma unroll
-    for (int it = 0; it < (NE + 3) / 4; ++it) {
-      const int ii = it * 4 + q;
+      for (int c = 1; c < LPN; ++c) v += S[oRED + c * NRED + e];
+      return v;
+    };
+#pragma unroll
+    for (int it = 0; it < (NE + LPN - 1) / LPN; ++it) {
+      const int ii = it * LPN + q;
       if (ii < NE) {
-        const double* r0 = S + oRED + ii * (NE + 1);
-        const double* rg = S + oRED + NE * (NE + 1) + ii;
-        const double sg = rg[0] + rg[NRED] + rg[2 * NRED] + rg[3 * NRED];
-        const double sq = r0[NE] + r0[NRED + NE] + r0[2 * NRED + NE] + r0[3 * NRED + NE];
-        const bool xrow = NX4 ? (it * 4 < NX) : (ii < NX);
+        const double sg = rsum(NTRI + NE + ii);
+        const double sq = rsum(NTRI + ii);
+        const bool xrow = NXL ? (it * LPN < NX) : (ii < NX);
         if (xrow) {
-          const double g = S[oBG + ii];
+          double g = S[oBG + ii];
+          if constexpr (NODECOST) g += S[oNC + ii];
           if (active) {
 #pragma unroll
             for (int jj = 0; jj < NX; ++jj) {
-              double v = r0[jj] + r0[NRED + jj] + r0[2 * NRED + jj] + r0[3 * NRED + jj];
+              double v = rsum(jj <= ii ? tri(ii, jj) : tri(jj, ii));
               if (jj == ii) v += S[oBS + ii];
+              if constexpr (NODECOST) v += S[oNCQ + ii * NX + jj];
               qh[T::iQ(ii, jj)] = v;
             }
             qh[T::iq(ii)] = g + sq; el[T::ogx + ii] = g;
@@ -502,19 +569,22 @@ struct EvalQuad {
           }
         } else {
           const int aa = ii - NX;
-          const double g = S[oBG + ii] + S[oSUM + aa];
+          double g = S[oBG + ii] + S[oSUM + aa];
+          if constexpr (NODECOST) g += S[oNCu + aa];
           if (active) {
 #pragma unroll
             for (int jj = 0; jj < NX; ++jj) {
-              const double v = r0[jj] + r0[NRED + jj] + r0[2 * NRED + jj] + r0[3 * NRED + jj];
+              double v = rsum(tri(ii, jj));
+              if constexpr (NODECOST) v += S[oNCS + aa * NX + jj];
               qh[T::iS(aa, jj)] = v;
               if constexpr (T::FRAG) qh[T::iSt(aa, jj)] = v;
             }
 #pragma unroll
             for (int bb = 0; bb < NU; ++bb) {
-              double v = r0[NX + bb] + r0[NRED + NX + bb] + r0[2 * NRED + NX + bb] + r0[3 * NRED + NX + bb];
+              double v = rsum(bb <= aa ? tri(ii, NX + bb) : tri(NX + bb, ii));
               v += S[oSUM + NU + aa * NU + bb];
               if (bb == aa) v += S[oBS + ii];
+              if constexpr (NODECOST) v += S[oNCR + aa * NU + bb];
               qh[T::iR(aa, bb)] = v;
             }
             qh[T::ir(aa)] = g + sq; el[T::ogu + aa] = g;
@@ -525,7 +595,7 @@ struct EvalQuad {
     }
     // ---------------------------------------------------------------- 5. per-node scalars
 #pragma unroll
-    for (int m = 1; m < 4; m <<= 1) {
+    for (int m = 1; m < LPN; m <<= 1) {
       phi += qshfl_xor(phi, m); c1 += qshfl_xor(c1, m);
       comp = dmax(comp, qshfl_xor(comp, m)); cinf = dmax(cinf, qshfl_xor(cinf, m));
       maxinv = fmax(maxinv, qshfl_xor(maxinv, m));
@@ -538,7 +608,7 @@ struct EvalQuad {
 };
 
 template <class P>
-__global__ void __launch_bounds__(128, 3) eval_quad_kernel(OcpArgs a) { EvalQuad<P>::run(a); }
+__global__ void __launch_bounds__(128, EvalQuad<P>::LPN == 4 ? 3 : 2) eval_quad_kernel(OcpArgs a) { EvalQuad<P>::run(a); }
 
 template <class P>
 inline cudaError_t launch_eval_quad(const OcpArgs& a, cudaStream_t s) {

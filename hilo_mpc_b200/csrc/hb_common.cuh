@@ -132,6 +132,68 @@ HB_HD bool lu_solve_aug(double* M) {
   return true;
 }
 
+// Convexification of a symmetric NxN matrix by eigenvalue mirroring: H = V diag(l) V^T -> V diag(max(|l|, eps)) V^T
+// (cyclic Jacobi; N <= 16).  Negative curvature of magnitude |l| becomes positive curvature of the same magnitude, which
+// keeps the length scale of the Newton step in that direction instead of flattening it (Verschueren et al. 2017).
+// Returns true when the matrix was changed.
+template <int N>
+HB_HD bool sym_mirror(double* H, double eps) {
+  {  // cheap test first: Cholesky with all pivots above eps -> nothing to do
+    double L[N * N];
+    for (int i = 0; i < N * N; ++i) L[i] = H[i];
+    bool pd = true;
+    for (int j = 0; j < N && pd; ++j) {
+      double d = L[j * N + j];
+      for (int l = 0; l < j; ++l) d -= L[j * N + l] * L[j * N + l];
+      if (!(d > eps)) { pd = false; break; }
+      d = sqrt(d);
+      L[j * N + j] = d;
+      for (int i = j + 1; i < N; ++i) {
+        double s2 = L[i * N + j];
+        for (int l = 0; l < j; ++l) s2 -= L[i * N + l] * L[j * N + l];
+        L[i * N + j] = s2 / d;
+      }
+    }
+    if (pd) return false;
+  }
+  double A[N * N], V[N * N];
+  for (int i = 0; i < N; ++i)
+    for (int j = 0; j < N; ++j) { A[i * N + j] = 0.5 * (H[i * N + j] + H[j * N + i]); V[i * N + j] = (i == j) ? 1.0 : 0.0; }
+  for (int sweep = 0; sweep < 12; ++sweep) {
+    double off = 0.0, diag = 0.0;
+    for (int i = 0; i < N; ++i)
+      for (int j = 0; j < N; ++j) { if (i != j) off += A[i * N + j] * A[i * N + j]; else diag += A[i * N + i] * A[i * N + i]; }
+    if (off <= 1e-30 * (diag + 1e-300)) break;
+    for (int p = 0; p < N - 1; ++p)
+      for (int q = p + 1; q < N; ++q) {
+        const double apq = A[p * N + q];
+        if (apq == 0.0) continue;
+        const double th = (A[q * N + q] - A[p * N + p]) / (2.0 * apq);
+        const double t = (th >= 0.0 ? 1.0 : -1.0) / (dabs(th) + sqrt(th * th + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+        for (int k = 0; k < N; ++k) {
+          const double akp = A[k * N + p], akq = A[k * N + q];
+          A[k * N + p] = c * akp - sn * akq; A[k * N + q] = sn * akp + c * akq;
+        }
+        for (int k = 0; k < N; ++k) {
+          const double apk = A[p * N + k], aqk = A[q * N + k];
+          A[p * N + k] = c * apk - sn * aqk; A[q * N + k] = sn * apk + c * aqk;
+        }
+        for (int k = 0; k < N; ++k) {
+          const double vkp = V[k * N + p], vkq = V[k * N + q];
+          V[k * N + p] = c * vkp - sn * vkq; V[k * N + q] = sn * vkp + c * vkq;
+        }
+      }
+  }
+  for (int i = 0; i < N; ++i)
+    for (int j = 0; j <= i; ++j) {
+      double s2 = 0.0;
+      for (int k = 0; k < N; ++k) s2 += V[i * N + k] * dmax(dabs(A[k * N + k]), eps) * V[j * N + k];
+      H[i * N + j] = s2; H[j * N + i] = s2;
+    }
+  return true;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Log-barrier pieces for one scalar variable with bounds [lb, ub] (either side may be infinite).
 struct BarrierTerm {

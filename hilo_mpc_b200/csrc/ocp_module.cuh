@@ -184,6 +184,8 @@ struct OcpModule {
     a.B = c->B; a.n_alpha = c->n_alpha; a.max_iter = c->max_iter;
     a.tol = c->tol; a.acc_tol = c->acc_tol; a.mu_init = c->mu_init; a.mu_min = c->mu_min;
     a.time0 = c->time0; a.dt = c->dt; a.warm = c->warm_start;
+    a.convexify = c->regularization == 1 ? 1 : 0;
+    a.convexify_eps = c->regularization_eps > 0.0 ? c->regularization_eps : 1e-4;
     if (a.warm) a.mu_init = c->mu_init_warm;
     a.x0 = c->x0; a.sp = c->sp; a.sp_stride = c->sp_stride; a.tp = c->tp; a.tp_stride = c->tp_stride;
     a.uold = c->uold; a.uold_stride = c->uold_stride; a.ap = c->ap; a.ap_stride = c->ap_stride;
@@ -228,6 +230,7 @@ struct OcpModule {
         if (c->eval_variant != 0) {
           cudaError_t e = launch_eval_quad<P>(a, s);
           if (e != cudaSuccess) return (int)e;
+          if (a.convexify) launch_2d<OcpConvexify<P>>(a, a.n_instances(), T::N, s);
         } else {
           launch_2d<OcpEval<P>>(a, a.B, T::N + 1, s);
         }

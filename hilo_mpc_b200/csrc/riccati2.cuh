@@ -60,7 +60,7 @@ struct RiccatiTma2 {
   static constexpr int STRIDE = ((RAW + 15) / 16) * 16 + 4;  // doubles; instances of a warp start 8 banks apart
   static constexpr int SMEM_BYTES = CW * G * STRIDE * 8;
   static constexpr int CHA = T::NAp / 2, CHH = T::NHp / 2;   // 16-byte chunks of the dynamics / Hessian part of a stage
-  static constexpr bool SUPPORTED = (NE + 1 <= 32) && (NX <= 6) && (NU >= 1) && (NU <= 2) && (CW * G <= 32) &&
+  static constexpr bool SUPPORTED = (NE + 1 <= 32) && (NX <= 6) && (NU >= 1) && (NU <= 6) && (CW * G <= 32) &&
                                     (SMEM_BYTES <= 110 * 1024) && (N >= NBUF) && !T::FRAG;
 
   static __device__ __forceinline__ double gshfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src, LPI); }
@@ -115,22 +115,34 @@ struct RiccatiTma2 {
       }
       cp_async_commit();   // (possibly empty) group: the group count stays uniform
     };
+    const double* tn = a.qpN + (long long)bb * T::SDN;
+    double Pm[NX][NX], pv[NX], lam[NX];
+    double edual = 0.0;
+    bool ok = true;
+    // Inertia correction (IPOPT's algorithm IC on the stage structure, see InertiaSchedule): the backward sweep is
+    // repeated with delta_w on the diagonals of Q_k, R_k, Q_N until every Huu (and P_0 when x_0 is free) is positive
+    // definite.  The instances of a warp repeat together (the ring is shared machinery); one that was fine keeps its dw.
+    InertiaSchedule ic(st[ST_DW]);
+    double dw = 0.0;
+    double dx[NX];
+    double L0[P::FIXED_X0 ? 1 : NX][P::FIXED_X0 ? 1 : NX];
+    bool given_up = false;
+    for (int attempt = 0;; ++attempt) {
+    if (attempt > 0) { cp_async_wait<0>(); __syncwarp(); }
 #pragma unroll
     for (int j = 0; j < NBUF - 1; ++j) issue(j);
-    const double* tn = a.qpN + (long long)bb * T::SDN;
 
     // ---- terminal data: P = Q_N (replicated in every lane), p = q_N, lam = qbar_N
-    double Pm[NX][NX], pv[NX], lam[NX];
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
 #pragma unroll
-      for (int j = 0; j < NX; ++j) Pm[i][j] = tn[i * NX + j];
+      for (int j = 0; j < NX; ++j) Pm[i][j] = tn[i * NX + j] + ((i == j) ? dw : 0.0);
       pv[i] = tn[NX * NX + i];
       lam[i] = tn[NX * NX + NX + i];
     }
     if (active && g < NX) a.lam[((long long)b * (N + 1) + N) * NX + g] = pick<NX>(lam, g);
-    double edual = 0.0;
-    bool ok = true;
+    edual = 0.0;
+    ok = true;
 
     // ---- per-lane offsets (doubles, relative to a ring slot), fixed for the whole sweep
     int moff[NX];   // column g of [A B] / the affine column b
@@ -166,7 +178,7 @@ struct RiccatiTma2 {
 #pragma unroll
       for (int l = 0; l < NX; ++l) m[l] = slot[moff[l]];
 #pragma unroll
-      for (int i = 0; i < NE; ++i) h[i] = slot[coff[i]];
+      for (int i = 0; i < NE; ++i) h[i] = slot[coff[i]] + ((i == g) ? dw : 0.0);
       const double gbar = (g < NE) ? slot[goff] : 0.0;
       __syncwarp();                       // all lanes have the slot in registers (and are done with last stage's H)
 
@@ -218,27 +230,59 @@ struct RiccatiTma2 {
       for (int d = 0; d < NU; ++d)
 #pragma unroll
         for (int c = 0; c < NU; ++c) Huu[c][d] = xch[(NX + d) * CS + NX + c];
-      // Huu^{-1} in closed form (symmetrised), regularised until positive definite
+      // Huu^{-1} (symmetrised): closed form for nu <= 2, Cholesky + triangular inverse otherwise (every lane, redundantly)
       double inv[NU][NU];
-      {
-        double reg = 0.0;
-        for (int attempt = 0; attempt < 12; ++attempt) {
-          bool pd;
-          if constexpr (NU == 1) {
-            const double a0 = Huu[0][0] + reg;
-            pd = a0 > 0.0;
-            inv[0][0] = fast_rcp(pd ? a0 : 1.0);
-          } else {
-            const double a0 = Huu[0][0] + reg, d0 = Huu[1][1] + reg, b0 = 0.5 * (Huu[0][1] + Huu[1][0]);
-            const double det = a0 * d0 - b0 * b0;
-            pd = (a0 > 0.0) && (det > 0.0);
-            const double idet = fast_rcp(pd ? det : 1.0);
-            inv[0][0] = d0 * idet; inv[1][1] = a0 * idet; inv[0][1] = -b0 * idet; inv[1][0] = inv[0][1];
+      if constexpr (NU == 1) {
+        const double a0 = Huu[0][0];
+        const bool pd = a0 > 0.0;
+        ok = ok && pd;
+        inv[0][0] = fast_rcp(pd ? a0 : 1.0);
+      } else if constexpr (NU == 2) {
+        const double a0 = Huu[0][0], d0 = Huu[1][1], b0 = 0.5 * (Huu[0][1] + Huu[1][0]);
+        const double det = a0 * d0 - b0 * b0;
+        const bool pd = (a0 > 0.0) && (det > 0.0);
+        ok = ok && pd;
+        const double idet = fast_rcp(pd ? det : 1.0);
+        inv[0][0] = d0 * idet; inv[1][1] = a0 * idet; inv[0][1] = -b0 * idet; inv[1][0] = inv[0][1];
+      } else {
+        double Lc[NU][NU], Li[NU][NU];   // Huu = Lc Lc^T, Li = Lc^{-1} (lower), inv = Li^T Li
+#pragma unroll
+        for (int jj = 0; jj < NU; ++jj) {
+          double d = Huu[jj][jj];
+#pragma unroll
+          for (int l = 0; l < jj; ++l) d -= Lc[jj][l] * Lc[jj][l];
+          const bool pd = d > 0.0;
+          ok = ok && pd;
+          const double rs = rsqrt(pd ? d : 1.0);   // full-precision device rsqrt
+          Lc[jj][jj] = rs;                         // the reciprocal of the pivot is what is needed below
+#pragma unroll
+          for (int i = jj + 1; i < NU; ++i) {
+            double sacc = 0.5 * (Huu[i][jj] + Huu[jj][i]);
+#pragma unroll
+            for (int l = 0; l < jj; ++l) sacc -= Lc[i][l] * Lc[jj][l];
+            Lc[i][jj] = sacc * rs;
           }
-          if (pd) break;
-          reg = (reg == 0.0) ? 1e-8 : reg * 100.0;
-          if (attempt == 11) ok = false;
         }
+#pragma unroll
+        for (int jj = 0; jj < NU; ++jj) {          // column jj of Li by forward substitution
+#pragma unroll
+          for (int i = 0; i < NU; ++i) {
+            if (i < jj) { Li[i][jj] = 0.0; continue; }
+            double sacc = (i == jj) ? 1.0 : 0.0;
+#pragma unroll
+            for (int l = jj; l < i; ++l) sacc -= Lc[i][l] * Li[l][jj];
+            Li[i][jj] = sacc * Lc[i][i];
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < NU; ++c)
+#pragma unroll
+          for (int d = 0; d <= c; ++d) {
+            double sacc = 0.0;
+#pragma unroll
+            for (int l = c; l < NU; ++l) sacc += Li[l][c] * Li[l][d];
+            inv[c][d] = sacc; inv[d][c] = sacc;
+          }
       }
       // feedback gain K = -Huu^{-1} Hux (all of it, every lane) and the lower triangle of P' = Hxx + Hux^T K
       double K[NU][NX];
@@ -293,52 +337,61 @@ struct RiccatiTma2 {
       }
     }
 
-    // =============================================================== initial step
-    double dx[NX];
+    // =============================================================== factor P_0 (free x_0)
+    if constexpr (!P::FIXED_X0) {   // free x_0: P_0 is the last pivot block of the reduced Hessian
+#pragma unroll
+      for (int jj = 0; jj < NX; ++jj) {
+        double d = Pm[jj][jj];
+#pragma unroll
+        for (int l = 0; l < jj; ++l) d -= L0[jj][l] * L0[jj][l];
+        const bool pd = d > 0.0;
+        ok = ok && pd;
+        d = sqrt(pd ? d : 1.0);
+        L0[jj][jj] = d;
+        const double rd = 1.0 / d;
+#pragma unroll
+        for (int i = jj + 1; i < NX; ++i) {
+          double sacc = Pm[i][jj];
+#pragma unroll
+          for (int l = 0; l < jj; ++l) sacc -= L0[i][l] * L0[jj][l];
+          L0[i][jj] = sacc * rd;
+        }
+      }
+    }
+    // ---- inertia check of the whole warp
+    {
+      const bool fail = active && !ok;
+      if (!__any_sync(0xffffffffu, fail)) break;
+      if (fail) {
+        if (!ic.next()) given_up = true;
+        dw = ic.dw;
+      }
+      if (__all_sync(0xffffffffu, !fail || given_up)) break;
+    }
+    }   // attempt loop
+    if (given_up) ok = false;
     if (P::FIXED_X0) {
 #pragma unroll
       for (int i = 0; i < NX; ++i) dx[i] = 0.0;
     } else {
-      // free x_0: lam_0 must vanish; dx_0 = -P_0^{-1} p_0 (p_0 lives in lane NE)
+      // lam_0 must vanish; dx_0 = -P_0^{-1} p_0 (p_0 lives in lane NE)
 #pragma unroll
       for (int i = 0; i < NX; ++i) { edual = dmax(edual, dabs(lam[i])); pv[i] = gshfl(pv[i], NE); }
-      double L[NX][NX];
-      double reg = 0.0;
-      for (int attempt = 0; attempt < 12; ++attempt) {
-        bool pd = true;
+      if constexpr (!P::FIXED_X0) {
 #pragma unroll
-        for (int jj = 0; jj < NX; ++jj) {
-          double d = Pm[jj][jj] + reg;
+        for (int i = 0; i < NX; ++i) {
+          double sacc = -pv[i];
 #pragma unroll
-          for (int l = 0; l < jj; ++l) d -= L[jj][l] * L[jj][l];
-          pd = pd && (d > 0.0);
-          d = sqrt(d > 0.0 ? d : 1.0);
-          L[jj][jj] = d;
-#pragma unroll
-          for (int i = jj + 1; i < NX; ++i) {
-            double sacc = Pm[i][jj];
-#pragma unroll
-            for (int l = 0; l < jj; ++l) sacc -= L[i][l] * L[jj][l];
-            L[i][jj] = sacc / d;
-          }
+          for (int l = 0; l < i; ++l) sacc -= L0[i][l] * dx[l];
+          dx[i] = sacc / L0[i][i];
         }
-        if (pd) break;
-        reg = (reg == 0.0) ? 1e-8 : reg * 100.0;
-        if (attempt == 11) ok = false;
-      }
 #pragma unroll
-      for (int i = 0; i < NX; ++i) {
-        double sacc = -pv[i];
+        for (int i = NX - 1; i >= 0; --i) {
+          double sacc = dx[i];
 #pragma unroll
-        for (int l = 0; l < i; ++l) sacc -= L[i][l] * dx[l];
-        dx[i] = sacc / L[i][i];
-      }
-#pragma unroll
-      for (int i = NX - 1; i >= 0; --i) {
-        double sacc = dx[i];
-#pragma unroll
-        for (int l = i + 1; l < NX; ++l) sacc -= L[l][i] * dx[l];
-        dx[i] = sacc / L[i][i];
+          for (int l = i + 1; l < NX; ++l) sacc -= L0[l][i] * dx[l];
+          dx[i] = sacc / L0[i][i];
+        }
       }
     }
 
@@ -403,6 +456,7 @@ struct RiccatiTma2 {
     if (active && g == 0) {
       st[ST_EDUAL] = em;
       if (!ok) { a.status[b] = -1; st[ST_ACTIVE] = 0.0; }
+      else if (dw > 0.0) st[ST_DW] = dw;
     }
   }
 };

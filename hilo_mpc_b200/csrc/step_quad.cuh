@@ -14,7 +14,8 @@
 //   decide : thread 0, the same filter line-search helpers as OcpDecide, one candidate at a time (alpha_max 2^-i)
 //   apply  : own variables and multipliers updated in registers and stored.
 // Reductions over the instance are warp shuffles + one shared-memory round.  Supported: collocation, deg <= 3, continuous
-// objective, no additive input; everything else uses the thread-per-node bodies (step_fused.cuh or separate launches).
+// transcriptions incl. the MHE shape (free x_0, arrival cost, additive stage input, discrete-type objective); explicit RK
+// and discrete problems use the thread-per-node bodies (step_fused.cuh or separate launches).
 #pragma once
 #include "ocp_kernels.cuh"
 
@@ -27,8 +28,7 @@ struct StepQuad {
   static constexpr int NX = T::NX, NU = T::NU, NC = T::NC, NE = T::NE, N = T::N, D = P::DEG;
   static constexpr int NV = NX + NU + NC, NVIT = (NV + 3) / 4;
   static constexpr int THREADS = (((N + 1) * 4 + 31) / 32) * 32, WARPS = THREADS / 32;
-  static constexpr bool SUPPORTED = (P::METHOD == METHOD_COLLOCATION) && !P::OBJ_DISCRETE && !P::HAS_GADD && (D <= 3) &&
-                                    (THREADS <= 1024);
+  static constexpr bool SUPPORTED = (P::METHOD == METHOD_COLLOCATION) && (D <= 3) && (THREADS <= 1024);
   // shared memory (doubles): trial copy of the instance | warp partials | control block
   static constexpr int oTRIAL = 0, oRED = oTRIAL + (N + 1) * NV, oCTRL = oRED + 8 * 32, oST = oCTRL + 8,
                        SMEM = oST + ST_COUNT;
@@ -273,7 +273,7 @@ struct StepQuad {
               for (int j = 1; j <= D; ++j) xp += cc[j] * Xs[(j - 1) * NX + r];
               c1 += dabs(dt * f[r] - xp);
             }
-            if (with_lag) {
+            if (with_lag && !P::OBJ_DISCRETE) {
               double l = P::lag_val(Xi, ut, sp, ti, dt);
               if (first) l += P::lagdu_val(ut, uo);
               phi += dt * cb * l;
@@ -285,13 +285,24 @@ struct StepQuad {
               double xf = P::CD(0) * xs[r];
 #pragma unroll
               for (int i = 1; i <= D; ++i) xf += P::CD(i) * Xs[(i - 1) * NX + r];
+              if (P::HAS_GADD) {   // additive stage input (MHE state noise)
+#pragma unroll
+                for (int c = 0; c < NU; ++c) xf += P::GADD(r * NU + c) * us[c];
+              }
               c1 += dabs(xf - xn[r]);
             }
-            if (k == 0 && P::HAS_ARR) {
-              double x0[NX];
+            if ((k == 0 && P::HAS_ARR) || (P::OBJ_DISCRETE && with_lag)) {   // cost terms on the node itself
+              double xk[NX], uk[NU > 0 ? NU : 1];
 #pragma unroll
-              for (int r = 0; r < NX; ++r) x0[r] = xs[r];
-              phi += P::arr_val(x0, a.ap + (long long)b * a.ap_stride);
+              for (int r = 0; r < NX; ++r) xk[r] = xs[r];
+#pragma unroll
+              for (int r = 0; r < NU; ++r) uk[r] = us[r];
+              if (k == 0 && P::HAS_ARR) phi += P::arr_val(xk, a.ap + (long long)b * a.ap_stride);
+              if (P::OBJ_DISCRETE && with_lag) {
+                double l = P::lag_val(xk, uk, sp, t, dt);
+                if (first) l += P::lagdu_val(uk, uo);
+                phi += l;
+              }
             }
           }
         } else if (q == 0) {

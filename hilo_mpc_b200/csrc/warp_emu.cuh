@@ -177,6 +177,7 @@ __device__ __forceinline__ void zero_if(int f, double& v0, double& v1) {
 }  // namespace wp
 }  // namespace hb
 #define HB_WP __device__ __forceinline__
+#define HB_WP_COLD __device__ __noinline__   // rare paths: kept out of the register allocation of the hot one
 #else
 #include <pthread.h>
 #include <thread>
@@ -346,4 +347,5 @@ inline void launch(const Args& a, int grid, int threads, size_t smem_bytes) {
 }  // namespace wp
 }  // namespace hb
 #define HB_WP inline
+#define HB_WP_COLD inline
 #endif

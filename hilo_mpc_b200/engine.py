@@ -95,7 +95,8 @@ class OcpEngine:
               acc_tol: float = 1e-6, max_iter: int = 3000, n_alpha: int = 8, mu_init: float = .1,
               mu_min: Optional[float] = None, check_every: int = 4, stream=None, kernel_ms=None, kernel_count=None,
               riccati_variant: int = 2, warm_start: int = 0, mu_init_warm: float = 1e-4,
-              eval_variant: int = 1, step_variant: int = 2, adaptive_poll: bool = True, compaction: bool = True):
+              eval_variant: int = 1, step_variant: int = 2, adaptive_poll: bool = True, compaction: bool = True,
+              regularization: int = 0, regularization_eps: float = 1e-4):
         """``x0``: CUDA tensor ``[B, nx]`` (scaled). Optional ``sp [B|1, N, nsp]``, ``tp``, ``uold``, ``ap`` tensors.
         Returns dict of device tensors: x [B,N+1,nx], u [B,N,nu], xc, lam, status, iters, stats."""
         torch = _lib.require_cuda()
@@ -141,7 +142,8 @@ class OcpEngine:
             warm_start=warm, first_check=(getattr(self, 'last_needed', 0) if (warm and adaptive_poll) else 0),
             n_iterations_needed=C.pointer(needed),
             mu_init_warm=mu_init_warm, eval_variant=eval_variant, step_variant=step_variant,
-            no_compaction=int(not compaction))
+            no_compaction=int(not compaction), regularization=int(regularization),
+            regularization_eps=float(regularization_eps))
         _lib.check(lib.hb_ocp_solve(self._handle, C.byref(call)), 'hb_ocp_solve')
         self.last_launched = launched.value
         self.last_needed = needed.value

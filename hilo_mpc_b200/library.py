@@ -17,14 +17,15 @@ CSTR = dict(k10=1.287e12, k20=1.287e12, k30=9.043e9, E1=9758.3, E2=9758.3, E3=85
             cA0=5.1)
 
 
-def cstr_rhs(x, u, c=CSTR, exp=None, side_reaction=None):
+def cstr_rhs(x, u, c=CSTR, exp=None, side_reaction=None, k1_scale=1.):
     """Right-hand side for symbolic (``exp=sx.exp``) or NumPy (``exp=np.exp``) arguments; states
     ``[c_A, c_B, T_R, T_K]``, inputs ``[F, Q_dot]``.  ``side_reaction(c_A, T_R)``, if given, replaces the rate term
-    ``k_3(T_R) c_A^2`` (BASELINE config 3: that term learned by a Gaussian process)."""
+    ``k_3(T_R) c_A^2`` (BASELINE config 3: that term learned by a Gaussian process); ``k1_scale`` multiplies the
+    pre-exponential factor ``k_10`` (BASELINE config 4: the parameter the MHE estimates)."""
     exp = exp or sx.exp
     cA, cB, TR, TK = x[0], x[1], x[2], x[3]
     F, Qd = u[0], u[1]
-    k1 = c['k10'] * exp(-c['E1'] / (TR + 273.15))
+    k1 = k1_scale * c['k10'] * exp(-c['E1'] / (TR + 273.15))
     k2 = c['k20'] * exp(-c['E2'] / (TR + 273.15))
     k3 = c['k30'] * exp(-c['E3'] / (TR + 273.15))
     r3 = k3 * cA * cA if side_reaction is None else side_reaction(cA, TR)
@@ -41,13 +42,15 @@ def cstr_side_reaction(cA, TR, c=CSTR, exp=np.exp):
     return c['k30'] * exp(-c['E3'] / (TR + 273.15)) * cA * cA
 
 
-def cstr_model(dt: float = 0.005, side_reaction=None, name: str = 'cstr_klatt_engell') -> Model:
+def cstr_model(dt: float = 0.005, side_reaction=None, name: str = 'cstr_klatt_engell', with_parameter: bool = False) -> Model:
+    """``with_parameter``: ``k1_scale`` becomes a model parameter (config 4: estimated by the MHE)."""
     model = Model(name=name, time_unit='h')
     x = model.set_dynamical_states(['c_A', 'c_B', 'T_R', 'T_K'])
     u = model.set_inputs(['F', 'Q_dot'])
+    k1s = model.set_parameters(['k1_scale'])[0] if with_parameter else 1.
     model.set_measurements(['y_cB', 'y_TR'])
     model.set_measurement_equations([x[1], x[2]])
-    model.set_dynamical_equations(cstr_rhs(x, u, side_reaction=side_reaction))
+    model.set_dynamical_equations(cstr_rhs(x, u, side_reaction=side_reaction, k1_scale=k1s))
     model.setup(dt=dt)
     return model
 

@@ -85,8 +85,7 @@ class MovingHorizonEstimator(DynamicOptimization):
         self._w_lb = self._w_ub = self._p_lb = self._p_ub = None
         self._w_guess = self._p_guess = None
         self._w_scaling = self._p_scaling = None
-        self._y_history: List[np.ndarray] = []
-        self._u_history: List[np.ndarray] = []
+        self._window = None   # [B, N, nu + ny] device tensor: the measurements inside the horizon
         self._meas_counter = 0
         self._horizon_is_reached = False
         self._last = None
@@ -223,26 +222,54 @@ class MovingHorizonEstimator(DynamicOptimization):
 
     # ------------------------------------------------------------------ measurements / estimate
     def add_measurements(self, y_meas, u_meas=None) -> None:
-        """Append one sample; ``y_meas`` ``(ny,)`` or batched ``(B, ny)`` (mhe.py:274-309)."""
+        """Append one sample; ``y_meas`` ``(ny,)`` or batched ``(B, ny)``, NumPy or device tensor (mhe.py:274-309).
+        The horizon window ``[u_meas | y_meas]`` of every instance lives on the device (``[B, N, nu + ny]``, the stage
+        parameters of the solve): a sample costs one copy of its own bytes, not of the window."""
         if not self._nlp_setup_done:
             raise RuntimeError("You need to setup the MHE by running .setup() before running add_measurements")
+        from . import _lib
+        torch = _lib.require_cuda()
+        eng = self._engine
+        eng._open()
+        dev = eng._device
         m = self._model
-        y = np.asarray(y_meas.cpu() if hasattr(y_meas, 'cpu') else y_meas, dtype=float)
-        y = y.reshape(1, -1) if y.size == m.n_y else y.reshape(-1, m.n_y)
-        self._y_history.append(y)
+        N = self._prediction_horizon
+
+        def as_dev(v, n, what):
+            t = v.to(device=dev, dtype=torch.float64) if torch.is_tensor(v) else \
+                torch.as_tensor(np.asarray(v, dtype=float), dtype=torch.float64, device=dev)
+            if t.numel() == n:
+                return t.reshape(1, n)
+            if t.numel() % n != 0:
+                raise ValueError(f"{what} has {t.numel()} elements, expected a multiple of {n}")
+            return t.reshape(-1, n)
+        y = as_dev(y_meas, m.n_y, 'y_meas')
         if m.n_u:
             if u_meas is None:
                 raise ValueError(f"The model has {m.n_u} input(s): pass their measured values with u_meas=")
-            u = np.asarray(u_meas.cpu() if hasattr(u_meas, 'cpu') else u_meas, dtype=float)
-            u = u.reshape(1, -1) if u.size == m.n_u else u.reshape(-1, m.n_u)
-            self._u_history.append(u)
+            u = as_dev(u_meas, m.n_u, 'u_meas')
+        else:
+            u = None
+        B = max(y.shape[0], 1 if u is None else u.shape[0])
+        win = getattr(self, '_window', None)
+        if win is None or win.shape[0] != B:
+            if win is not None and self._meas_counter > 0 and win.shape[0] != 1:
+                raise ValueError(f"The batch size changed from {win.shape[0]} to {B} while the horizon window is filling")
+            new = torch.zeros(B, N, m.n_u + m.n_y, dtype=torch.float64, device=dev)
+            if win is not None and self._meas_counter > 0:
+                new.copy_(win.expand(B, -1, -1))
+            self._window = win = new
+        if self._meas_counter >= N:   # window full: drop the oldest sample
+            win[:, :-1] = win[:, 1:].clone()
+            pos = N - 1
+        else:
+            pos = self._meas_counter
+        if u is not None:
+            win[:, pos, :m.n_u] = u
+        win[:, pos, m.n_u:] = y
         self._meas_counter += 1
-        if self._meas_counter == self._prediction_horizon:
+        if self._meas_counter >= N:
             self._horizon_is_reached = True
-        if self._meas_counter > self._prediction_horizon:
-            self._y_history.pop(0)
-            if m.n_u:
-                self._u_history.pop(0)
 
     def estimate(self, x_arrival=None, p_arrival=None, v0=None, runs=0, **kwargs):
         if not self._nlp_setup_done:
@@ -257,37 +284,37 @@ class MovingHorizonEstimator(DynamicOptimization):
         dev = eng._device
         m, s = self._model, self._spec
         nx, npar, N = m.n_x, m.n_p, s.N
-        Y = np.stack(self._y_history, axis=1)  # [B, N, ny]
-        B = Y.shape[0]
-        parts = []
-        if m.n_u:
-            U = np.stack(self._u_history, axis=1)
-            parts.append(np.broadcast_to(U, (B, N, m.n_u)))
-        parts.append(Y)
-        sp = torch.tensor(np.concatenate(parts, axis=2), dtype=torch.float64, device=dev)
-        xa = self._x_arrival if x_arrival is None else np.asarray(x_arrival, dtype=float)
-        if xa is None:
-            raise ValueError("No arrival guess for the states: use quad_arrival_cost.add_states(weights, guess)")
-        pa = self._p_arrival if p_arrival is None else np.asarray(p_arrival, dtype=float)
-        xa = np.broadcast_to(np.asarray(xa, dtype=float).reshape(-1, nx), (B, nx))
-        ap = xa if npar == 0 else np.concatenate([xa, np.broadcast_to(np.asarray(pa, dtype=float).reshape(-1, npar),
-                                                                       (B, npar))], axis=1)
-        apt = torch.tensor(np.ascontiguousarray(ap), dtype=torch.float64, device=dev)
-        x0_dummy = torch.zeros(B, s.nx, dtype=torch.float64, device=dev)
+        sp = self._window
+        B = sp.shape[0]
+        f8 = dict(dtype=torch.float64, device=dev)
+
+        def arrival(given, stored, n, what):
+            v = stored if given is None else given
+            if v is None:
+                raise ValueError(f"No arrival guess for the {what}: use quad_arrival_cost.add_{what}(weights, guess)")
+            t = v.to(**f8) if torch.is_tensor(v) else torch.as_tensor(np.asarray(v, dtype=float), **f8)
+            return t.reshape(-1, n).expand(B, n)
+        xa = arrival(x_arrival, self._x_arrival, nx, 'states')
+        apt = xa if npar == 0 else torch.cat([xa, arrival(p_arrival, self._p_arrival, npar, 'parameters')], dim=1)
+        apt = apt.contiguous()
+        if getattr(self, '_x0_dummy', None) is None or self._x0_dummy.shape[0] != B:
+            self._x0_dummy = torch.zeros(B, s.nx, **f8)
         if getattr(self, '_batch', None) != B:
             eng.reset_guess()
             self._batch = B
         num = self._solver_numbers()
-        out = eng.solve(x0_dummy, dt=self._sampling_interval, time0=self._time - N * self._sampling_interval, sp=sp,
-                        ap=apt, **num)
+        out = eng.solve(self._x0_dummy, dt=self._sampling_interval, time0=self._time - N * self._sampling_interval,
+                        sp=sp, ap=apt, **num)
         self._last = out
-        xs_t = torch.tensor(np.concatenate([self._x_scaling, self._p_scaling]), dtype=torch.float64, device=dev)
+        if getattr(self, '_xs_dev', None) is None or self._xs_dev.device != dev:
+            self._xs_dev = torch.tensor(np.concatenate([self._x_scaling, self._p_scaling]), **f8)
+        xs_t = self._xs_dev
         xN = out['x'][:, N, :] * xs_t
-        # arrival update 'smoothing' (mhe.py:254-256 reads node 2 of the previous solution)
+        # arrival update 'smoothing' (mhe.py:254-256 reads node 2 of the previous solution); kept on the device
         node = min(2, N)
-        self._x_arrival = (out['x'][:, node, :nx] * xs_t[:nx]).cpu().numpy()
+        self._x_arrival = out['x'][:, node, :nx] * xs_t[:nx]
         if npar:
-            self._p_arrival = (out['x'][:, 0, nx:] * xs_t[nx:]).cpu().numpy()
+            self._p_arrival = out['x'][:, 0, nx:] * xs_t[nx:]
         st = out['status']
         if B == 1:
             code = int(st[0].item())

@@ -200,7 +200,9 @@ class DynamicOptimization:
                     eval_variant=int(o.get('b200.eval_variant', 1)),
                     step_variant=int(o.get('b200.step_variant', 2)),
                     compaction=bool(int(o.get('b200.compaction', 1))),
-                    adaptive_poll=bool(o.get('b200.adaptive_poll', True)))
+                    adaptive_poll=bool(o.get('b200.adaptive_poll', True)),
+                    regularization={'inertia': 0, 'mirror': 1}[str(o.get('b200.regularization', 'inertia'))],
+                    regularization_eps=float(o.get('b200.regularization_eps', 1e-4)))
 
     def is_setup(self) -> bool:
         return self._nlp_setup_done

@@ -70,6 +70,9 @@ def build_all():
     mhe.set_box_constraints(x_lb=[0., 0.], x_ub=[1., 1.], p_lb=[.1], p_ub=[5.])
     mhe.setup()
     paths.append(mhe.engine.module_path)
-    from .examples import robot_nn_nmpc
+    from .examples import cstr_mhe, robot_nn_nmpc
     paths.append(robot_nn_nmpc(N=5, hidden=8).engine.module_path)
+    # BASELINE configs 4 and 5 at their stated problem sizes
+    paths.append(cstr_mhe(N=20).engine.module_path)
+    paths.append(robot_nn_nmpc(N=30, hidden=32).engine.module_path)
     return paths

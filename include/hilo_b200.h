@@ -106,6 +106,12 @@ typedef struct hb_ocp_call {
                                one thread per node; 0: separate kernels                                            */
   int no_compaction;        /* 0 (default): once a poll finds at most half of the batch active, the node / sweep / step
                                kernels run over the list of those instances; 1: always over the whole batch        */
+  int regularization;       /* treatment of negative curvature of the exact Lagrangian Hessian.  0 (default): IPOPT's
+                               inertia correction - the sweep is repeated with delta_w * I on the primal variables
+                               until every Huu is positive definite (Waechter & Biegler 2006, algorithm IC);
+                               1: additionally every reduced stage Hessian [Q S^T; S R] is convexified before the sweep
+                               by mirroring its negative eigenvalues (|lambda|, floor regularization_eps)            */
+  double regularization_eps;
 } hb_ocp_call;
 
 /* kernel indices of kernel_ms / kernel_count */

@@ -29,7 +29,8 @@ class OcpCall(C.Structure):
                 ('work', _DP), ('work_doubles', C.c_size_t), ('stream', C.c_void_p),
                 ('n_iterations_launched', _IP), ('n_kernel_launches', C.POINTER(C.c_longlong)),
                 ('kernel_ms', _DP), ('kernel_count', C.POINTER(C.c_longlong)), ('riccati_variant', C.c_int), ('warm_start', C.c_int), ('mu_init_warm', C.c_double), ('eval_variant', C.c_int), ('first_check', C.c_int),
-                ('n_iterations_needed', C.POINTER(C.c_int)), ('step_variant', C.c_int), ('no_compaction', C.c_int)]
+                ('n_iterations_needed', C.POINTER(C.c_int)), ('step_variant', C.c_int), ('no_compaction', C.c_int),
+                ('regularization', C.c_int), ('regularization_eps', C.c_double)]
 
 
 def _dp(a):
@@ -75,7 +76,7 @@ class HostOcp:
         self.lib.hbm_ocp_dims(C.byref(self.dims))
 
     def solve(self, x0, x, u, xc, xlb, xub, ulb, uub, dt, time0=0., sp=None, tp=None, uold=None, ap=None, tol=1e-8,
-              max_iter=200, n_alpha=8, mu_init=.1, riccati_variant=0):
+              max_iter=200, n_alpha=8, mu_init=.1, riccati_variant=0, regularization=0, regularization_eps=1e-4):
         d = self.dims
         B = x.shape[0]
         f8 = lambda a, shape: np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(shape))
@@ -111,9 +112,10 @@ class HostOcp:
                        xlb=_dp(b[0]), xub=_dp(b[1]), ulb=_dp(b[2]), uub=_dp(b[3]), x=_dp(x), u=_dp(u), xc=_dp(xc),
                        lam=_dp(lam), status=status.ctypes.data_as(_IP), iters=iters.ctypes.data_as(_IP),
                        stats=_dp(stats), work=_dp(work), work_doubles=nwork, stream=None,
-                       n_iterations_launched=C.pointer(launched), riccati_variant=riccati_variant)
+                       n_iterations_launched=C.pointer(launched), riccati_variant=riccati_variant,
+                       regularization=regularization, regularization_eps=regularization_eps)
         rc = self.lib.hbm_ocp_solve(C.byref(call))
         if rc != 0:
             raise RuntimeError(f"hbm_ocp_solve returned {rc}")
         return dict(x=x, u=u, xc=xc.reshape(B, d.N, d.nc) if d.nc else None, lam=lam, status=status,
-                    iters=iters[:B], stats=stats, launched=launched.value)
+                    iters=iters[:B], stats=stats, launched=launched.value, work=work, n_alpha=n_alpha)

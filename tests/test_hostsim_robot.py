@@ -11,16 +11,17 @@ from runner import HostOcp
 def test_mlp_graph_matches_numeric_forward_pass_and_true_dynamics():
     from hilo_mpc_b200 import symbolic as sx
     net = bicycle_ann(32)
-    z = sx.sym('z', 4)
+    z = sx.sym('z', 5)
     F = sx.Function('mlp', [('z', z)], [('y', net.predict(z))])
     rng = np.random.default_rng(1)
-    Z = np.column_stack([rng.uniform(0., 6., 50), rng.uniform(-2., 2., 50), rng.uniform(-1., 1., 50),
-                         rng.uniform(-.5, .5, 50)]).T
+    v, phi = rng.uniform(0., 6., 50), rng.uniform(-6., 6., 50)   # heading outside [-pi, pi]: the features are periodic
+    a, delta = rng.uniform(-1., 1., 50), rng.uniform(-.5, .5, 50)
+    Z = np.vstack([v, np.sin(phi), np.cos(phi), a, delta])
     np.testing.assert_allclose(F(Z), net.predict(Z), rtol=1e-12, atol=1e-13)
-    true = np.array([bicycle_rhs([0., 0., c[0], c[1]], [c[2], c[3]], sin=np.sin, cos=np.cos, tan=np.tan,
-                                 atan=np.arctan) for c in Z.T]).T
-    # the random-feature surrogate only has to be a smooth, roughly faithful stand-in for the trained network
-    assert np.corrcoef(net.predict(Z).ravel(), true.ravel())[0, 1] > .9
+    true = np.array([bicycle_rhs([0., 0., v[i], phi[i]], [a[i], delta[i]], sin=np.sin, cos=np.cos, tan=np.tan,
+                                 atan=np.arctan) for i in range(50)]).T
+    # the surrogate has to be a smooth, faithful stand-in for the trained network
+    assert np.corrcoef(net.predict(Z).ravel(), true.ravel())[0, 1] > .98
 
 
 def test_path_following_nn_nmpc_host_kernels_match_oracle():
