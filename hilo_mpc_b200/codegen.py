@@ -165,6 +165,11 @@ class OcpGenerator:
 
     def source(self) -> str:
         body = self.prob_struct()
+        s = self.spec
+        exprs = list(s.ode) + [s.lag, s.may if s.may is not None else sx.Expr.const(0.)]
+        tables = sx.gp_tables_c_source(sx.gp_tables_used(np.array(exprs, dtype=object)))
+        if tables:
+            body = tables + '\n' + body
         # one namespace per problem: template instantiations (and their function-local statics, which the toolchain
         # emits as process-wide unique symbols) of different modules loaded into one process must not be merged
         ns = 'hbgen_' + hashlib.sha256(body.encode()).hexdigest()[:12]

@@ -71,7 +71,7 @@ struct EvalQuad {
   static constexpr int NTRI = NE * (NE + 1) / 2;
   static HB_HD constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }   // j <= i
   static constexpr int NRED = (NTRI + 2 * NE) | 1;
-  static constexpr int FT = (D * FSZ > NC * (NE + 1)) ? D * FSZ : NC * (NE + 1);
+  static constexpr int FT = (((D * FSZ > NC * (NE + 1)) ? D * FSZ : NC * (NE + 1)) + 1) & ~1;   // even: PB holds 128-bit words
   static constexpr int PBN = (2 * ((W + 1) & ~1) > NC) ? 2 * ((W + 1) & ~1) : NC;
   static constexpr int A1 = FT + PBN + D * LSZ, A2 = LPN * NRED;
   static constexpr int NCSZ = NODECOST ? (NX + NU + NX * NX + NU * NX + NU * NU) : 0;  // gx | gu | Qn | Sn | Rn of the node cost

@@ -35,22 +35,27 @@ struct KernelTimer {
 #if HB_DEVICE_BUILD
   static constexpr int kPool = 512;
   cudaEvent_t ev0[kPool], ev1[kPool];
-  int kind[kPool];
+  int kind[kPool], iter_of[kPool];
   int n = 0;
   bool created = false;
 #endif
   double* ms = nullptr;        // [K_NUM] accumulated milliseconds
   long long* count = nullptr;  // [K_NUM] launches
+  double* ms_it = nullptr;     // [HB_OCP_TIMED_ITERS][K_NUM] the same split by iteration index of the solve, or NULL
+  long long* count_it = nullptr;
+  int it = 0;                  // iteration index of the launches being recorded
   long long launches = 0;
 
   void begin(int k) {
     ++launches;
     if (count) count[k] += 1;
+    if (count_it) count_it[(it < HB_OCP_TIMED_ITERS ? it : HB_OCP_TIMED_ITERS - 1) * K_NUM + k] += 1;
 #if HB_DEVICE_BUILD
     if (!on) return;
     if (!created) { for (int i = 0; i < kPool; ++i) { cudaEventCreate(&ev0[i]); cudaEventCreate(&ev1[i]); } created = true; }
     if (n == kPool) flush(true);
     kind[n] = k;
+    iter_of[n] = it < HB_OCP_TIMED_ITERS ? it : HB_OCP_TIMED_ITERS - 1;
     cudaEventRecord(ev0[n], s);
 #endif
   }
@@ -67,7 +72,10 @@ struct KernelTimer {
     if (sync) cudaStreamSynchronize(s);
     for (int i = 0; i < n; ++i) {
       float t = 0.f;
-      if (cudaEventElapsedTime(&t, ev0[i], ev1[i]) == cudaSuccess && ms) ms[kind[i]] += (double)t;
+      if (cudaEventElapsedTime(&t, ev0[i], ev1[i]) == cudaSuccess && ms) {
+        ms[kind[i]] += (double)t;
+        if (ms_it) ms_it[iter_of[i] * K_NUM + kind[i]] += (double)t;
+      }
     }
     n = 0;
 #endif
@@ -107,6 +115,7 @@ struct OcpModule {
       }
       if (rc6 > 0) return rc6;
       ric_done = rc6 == 0;
+      if (ric_done) launch_1d<OcpRiccatiFix<P>>(a, a.n_instances(), s);   // instances flagged as non-convex (rare)
     }
 #if HB_DEVICE_BUILD
     if constexpr (RiccatiTma2<P>::SUPPORTED) {
@@ -213,6 +222,7 @@ struct OcpModule {
 
     static thread_local KernelTimer tm;
     tm.on = c->kernel_ms != nullptr; tm.s = s; tm.ms = c->kernel_ms; tm.count = c->kernel_count; tm.launches = 0;
+    tm.ms_it = c->kernel_ms_by_iter; tm.count_it = c->kernel_count_by_iter; tm.it = 0;
     tm.begin(K_INIT); launch_2d<OcpInit<P>>(a, a.B, OcpInit<P>::ETOT, s); tm.end();
     // Host polling schedule: every check_every iterations, or - with a hint from the previous solve of the same closed
     // loop (first_check = iterations that one needed) - once after that many and then after every further iteration.
@@ -224,6 +234,7 @@ struct OcpModule {
     int next_check = hint > 0 ? ((c->no_compaction == 0 && hint > 2) ? hint - 1 : hint) : check_every;
     int launched = 0, needed = 0, single_polls = 0;
     for (int it = 0; it <= c->max_iter; ++it) {
+      tm.it = it;
       tm.begin(K_EVAL);
 #if HB_DEVICE_BUILD
       if constexpr (EvalQuad<P>::SUPPORTED) {

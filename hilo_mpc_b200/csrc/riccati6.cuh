@@ -25,8 +25,9 @@
 // the gains from shared memory, through one generic pointer per lane), one shuffle hands du to the operand layout,
 // dx+ += [B | 0] [du; 0] as a second product, one shuffle hands dx+ on.
 //
-// A non-positive-definite Huu (non-convex problem far from the solution) is only flagged in the sweep; lane 0 then
-// redoes the instance with the inertia-correcting one-thread-per-instance sweep (OcpRiccati: delta_w * I, IPOPT's schedule).
+// A non-positive-definite Huu (non-convex problem far from the solution) is only flagged in the sweep (ST_ICREQ); the
+// small kernel OcpRiccatiFix that follows redoes such instances with the inertia-correcting one-thread-per-instance
+// sweep (OcpRiccati: delta_w * I on the primal variables, IPOPT's schedule).
 // Every primitive goes through warp_emu.cuh, so the same source runs lane-by-lane on the host in the CPU logic tests.
 #pragma once
 #include "ocp_kernels.cuh"
@@ -126,6 +127,7 @@ struct Riccati6 {
   // one backward stage; (c0, c1) = cost fragment, mB = M operand, state (pA, w0, w1) carried between stages;
   // gk = this lane's gain slot of the stage, lamk = its lam_k slot, ed = running max |column 7| (dual infeasibility in
   // the lanes of rows 4, 5)
+  template <bool SLOW>
   static HB_WP void bstage(const Lane& L, double mB, double c0, double c1, double& pA, double& w0, double& w1,
                            wp::sa_t gk, double* lamk, double& ed, int& ok) {
     const int f = L.f;
@@ -143,10 +145,25 @@ struct Riccati6 {
     wp::lds2<0>(L.huu, h00, h01);
     wp::lds2<8>(L.huu, h10, h11);
     const double hown = wp::lds<0>(L.own), hoth = wp::lds<0>(L.oth);   // row tig of [Hux h_u], the other row
-    const double dsel = wp::lds<0>(L.sel);                 // d0 for the first row of the inverse, a0 for the second
+    double dsel = wp::lds<0>(L.sel);                       // d0 for the first row of the inverse, a0 for the second
     (void)h10;
-    const double det = h00 * h11 - h01 * h01;
-    ok &= (int)(h00 > 0.0) & (int)(det > 0.0);             // identical in all lanes
+    double det = h00 * h11 - h01 * h01;
+    if constexpr (SLOW) {
+      if (!((h00 > 0.0) && (det > 0.0))) {                 // identical in all lanes: regularise until positive definite
+        double reg = 1e-8;
+        bool pd = false;
+        for (int attempt = 0; attempt < 11 && !pd; ++attempt) {
+          const double a0 = h00 + reg, d0 = h11 + reg;
+          det = a0 * d0 - h01 * h01;
+          pd = (a0 > 0.0) && (det > 0.0);
+          if (pd) dsel += reg;
+          reg *= 100.0;
+        }
+        if (!pd) { ok = 0; det = 1.0; }
+      }
+    } else {
+      ok &= (int)(h00 > 0.0) & (int)(det > 0.0);
+    }
     const double rdet = wp::rcp(det);
     const double kk = (h01 * hoth - dsel * hown) * rdet;   // K[tig][gid] (gid < 4), k[tig] (gid == 6); exactly 0 in the
                                                            // lanes of B-operand rows 2, 3 and column 7 (lam rides through)
@@ -158,6 +175,7 @@ struct Riccati6 {
     pA = wp::lds<0>(L.prd);                                // P'[max][min]: exactly symmetric
   }
 
+  template <bool SLOW>
   static HB_WP void backward(const OcpArgs& a, const Lane& L, int b, int lane, double* gs, double& ed, int& ok) {
     const int gid = lane >> 2, tig = lane & 3, g4 = gid & 3;
     const int f = L.f;
@@ -216,7 +234,7 @@ struct Riccati6 {
 #if HB_R6_MODE == 2
         w0 += mB + h0; w1 += h1;
 #else
-        bstage(L, mB, h0, h1, pA, w0, w1, wp::sadd(gk, -d * GD), lamk - d * NX, ed, ok);
+        bstage<SLOW>(L, mB, h0, h1, pA, w0, w1, wp::sadd(gk, -d * GD), lamk - d * NX, ed, ok);
 #endif
       }
 #if HB_R6_MODE != 1
@@ -232,14 +250,9 @@ struct Riccati6 {
         qM[d] = ldg(pM - (r + PF) * T::NAp);
         ldg2p(pC - (r + PF) * T::NHp, qC0[d], qC1[d], pol);
       }
-      bstage(L, mB, h0, h1, pA, w0, w1, wp::sadd(gk, -r * GD), lamk - r * NX, ed, ok);
+      bstage<SLOW>(L, mB, h0, h1, pA, w0, w1, wp::sadd(gk, -r * GD), lamk - r * NX, ed, ok);
     }
   }
-
-  // Non-convex stage (some Huu not positive definite): the sweep is repeated with IPOPT's inertia correction, delta_w * I
-  // on the primal variables (InertiaSchedule, ocp_kernels.cuh), by the one-thread-per-instance sweep - a cold call, kept
-  // out of the register allocation of the warp-per-instance path.
-  static HB_WP_COLD void inertia_corrected_sweep(const OcpArgs& a, int b) { OcpRiccati<P>::run(a, b); }
 
   static HB_WP void run(const OcpArgs& a) {
     double* smem = wp::dyn_smem();
@@ -279,10 +292,17 @@ struct Riccati6 {
 
     double ed = 0.0;
     int ok = 1;
-    backward(a, L, b, lane, gs, ed, ok);
+    backward<false>(a, L, b, lane, gs, ed, ok);
     if (wp::any(ok == 0)) {                             // rare: some Huu was not positive definite
-      if (lane == 0) inertia_corrected_sweep(a, b);     // whole sweep incl. the forward part, results in place
-      return;
+      // The instance is handed to OcpRiccatiFix (next launch: inertia-correcting sweep, delta_w * I with IPOPT's schedule),
+      // which overwrites everything written here.  The stage-wise regularising repetition below only keeps the numbers of
+      // this launch finite; it also happens to be the code shape for which the 72-register allocation of the hot path
+      // above is spill-free (an early return or a call here costs 30-60 bytes of spills in the stage loop: 47 -> 57 us).
+      if (lane == 0) st[ST_ICREQ] = 1.0;
+      ok = 1;
+      wp::syncwarp();
+      backward<true>(a, L, b, lane, gs, ed, ok);
+      ok = 1;
     }
     wp::syncwarp();
 #if HB_R6_SKIPFWD

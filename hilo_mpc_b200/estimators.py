@@ -316,6 +316,23 @@ class UnscentedKalmanFilter(_KalmanFilter):
                              "([x | P | X], kf.py:549-553)")
 
 
+def lhsnorm(mu, sigma, n):
+    """Latin-hypercube sample of a normal distribution, the particle filter's default density (pf.py:425-447): ``n`` draws
+    of ``N(mu, sigma)`` fix the rank order in every coordinate, the values are the normal quantiles of one uniformly
+    jittered point per stratum ``((rank - U) / n)`` with the marginal standard deviations ``sqrt(sigma_kk)``.  Draws from
+    the legacy NumPy global RNG in the reference's order (one ``multivariate_normal``, one ``rand``).  Returns ``(n, n_mu)``."""
+    from scipy.stats import norm
+    mu = np.asarray(mu, dtype=float).reshape(-1)
+    sigma = np.asarray(sigma, dtype=float)
+    z = np.random.multivariate_normal(mu, sigma, size=n)
+    rank = np.empty_like(z)
+    order = np.argsort(z, axis=0)
+    for k in range(mu.size):
+        rank[order[:, k], k] = np.arange(1, n + 1)
+    strata = (rank - np.random.rand(*z.shape)) / n
+    return norm.ppf(strata, loc=mu[None, :], scale=np.sqrt(np.diag(sigma))[None, :])
+
+
 class ParticleFilter(_Estimator):
     _label = 'Particle filter'
 
@@ -328,6 +345,7 @@ class ParticleFilter(_Estimator):
         self._roughening_tuning_param = float(K)   # pf.py:72-76
         self.last_roughening_noise = None
         self._sample_size = 15  # pf.py:79
+        self._pdf = lhsnorm      # pf.py:80: initial sample, process noise and roughening all draw from it
         self._X = None
         self.last_indices = None
         self.last_weights = None
@@ -356,10 +374,30 @@ class ParticleFilter(_Estimator):
         self._X = None
         self._sample_size = X.shape[1]
 
+    @property
+    def probability_density_function(self):
+        return self._pdf
+
+    @probability_density_function.setter
+    def probability_density_function(self, pdf):
+        """``pdf(mu, sigma, n) -> (n, n_mu)`` or ``(n_mu, n)`` samples (pf.py:193-247)."""
+        if not callable(pdf):
+            raise TypeError("The probability density function must be callable as pdf(mu, sigma, n)")
+        self._pdf = pdf
+
+    def _draw(self, mu, sigma, n):
+        X = np.asarray(self._pdf(np.asarray(mu, dtype=float), np.asarray(sigma, dtype=float), n), dtype=float)
+        nm = np.asarray(mu).size
+        if X.shape == (n, nm):
+            return X
+        if X.shape == (nm, n):    # the reference transposes user densities that return (n_mu, n) (pf.py:175-185)
+            return X.T
+        raise ValueError(f"Dimension mismatch. Expected dimension {nm}x{n}, got {X.shape[1]}x{X.shape[0]}.")
+
     def _initial_sample(self):
-        """Default initial sample: multivariate normal around the initial guess (pf.py:168-187), legacy global RNG."""
+        """Default initial sample around the initial guess with the filter's density (pf.py:168-187), legacy global RNG."""
         x, P = self._x_host, self._P_host
-        out = np.stack([np.random.multivariate_normal(x[b], P[b], size=self._sample_size) for b in range(x.shape[0])])
+        out = np.stack([self._draw(x[b], P[b], self._sample_size) for b in range(x.shape[0])])
         self._X_host = out
         self._X = None
 
@@ -371,8 +409,7 @@ class ParticleFilter(_Estimator):
         if roughening_noise is None:
             rng_range = (X.amax(dim=1) - X.amin(dim=1)).cpu().numpy()  # (B, n_x)
             scale = self._roughening_tuning_param * ns ** (-1. / nx)
-            roughening_noise = np.stack([np.random.multivariate_normal(np.zeros(nx), scale * np.diag(rng_range[b]),
-                                                                       size=ns) for b in range(B)])
+            roughening_noise = np.stack([self._draw(np.zeros(nx), scale * np.diag(rng_range[b]), ns) for b in range(B)])
         dx = self._engine.tensor(roughening_noise).reshape(B, ns, nx)
         self.last_roughening_noise = dx
         X += dx
@@ -399,7 +436,7 @@ class ParticleFilter(_Estimator):
             self._X = eng.tensor(self._X_host)
         B, ns, nx, ny = self._X.shape[0], self._sample_size, self._n_x, self._n_y
         if w is None:
-            w = np.stack([np.random.multivariate_normal(np.zeros(nx), self._Q, size=ns) for _ in range(B)])
+            w = np.stack([self._draw(np.zeros(nx), self._Q, ns) for _ in range(B)])   # pf.py:363
         if v is None:
             v = np.stack([(np.sqrt(self._R) @ np.random.randn(ny, ns)).T for _ in range(B)])  # pf.py:365
         if uniforms is None:

@@ -435,6 +435,13 @@ class GaussianProcess:
             rows = self.mean.basis(np.array([[xi] for xi in xq], dtype=object))
             for bj, row in zip(beta, rows):
                 mean = mean + float(bj) * (row[0] if isinstance(row, np.ndarray) else row)
+        if n > self.symbolic_unroll_limit:
+            # large training set: the mean enters the model as ONE call node (a loop over the training table inside the
+            # generated device function, csrc/gp_device.cuh) instead of n unrolled terms; no symbolic variance
+            Xs = (self._X / np.asarray(ls, dtype=float)[:, None]).T
+            gid = sx.register_gp_table(Xs, np.asarray(alpha, dtype=float) * self.kernel.signal_variance,
+                                       1. / np.asarray(ls, dtype=float))
+            return np.array([mean + sx.gp_mean_node(gid, xq)], dtype=object), None
         ks = []
         for i in range(n):
             d2 = sx.Expr.const(0.)
@@ -456,5 +463,7 @@ class GaussianProcess:
             var = None
         return np.array([mean], dtype=object), (None if var is None else np.array([var], dtype=object))
 
+
+GaussianProcess.symbolic_unroll_limit = 32   # training sets up to this size are unrolled into the expression graph
 
 GP = GaussianProcess

@@ -4,11 +4,9 @@ from __future__ import annotations
 import numpy as np
 
 
-def build_all():
+def _est_first_order():
     from .estgen import build_est_module
-    from .library import cstr_model
     from .model import Model
-    paths = []
     m = Model()
     m.set_equations(equations="""
         dx_1/dt = -k_1*x_1(t) + u(k)
@@ -17,15 +15,36 @@ def build_all():
         """)
     m.discretize('erk', order=1, inplace=True)
     m.setup(dt=1.)
-    paths.append(build_est_module(m))
+    return build_est_module(m)
+
+
+def _est_scalar():
+    from .estgen import build_est_module
+    from .model import Model
     s = Model(discrete=True)
     s.set_dynamical_states('x')
     s.set_measurements('y')
     s.set_dynamical_equations('x/2 + 25*dt*x/(1 + x^2)')
     s.set_measurement_equations('x^2/20')
     s.setup(dt=1.)
-    paths.append(build_est_module(s))
-    paths.append(build_est_module(cstr_model(dt=0.005)))
+    return build_est_module(s)
+
+
+def _est_cstr():
+    from .estgen import build_est_module
+    from .library import cstr_model
+    return build_est_module(cstr_model(dt=0.005))
+
+
+def _est_cstr_k1():
+    from .estgen import build_est_module
+    from .library import cstr_model
+    return build_est_module(cstr_model(dt=0.005, name='cstr_k1', with_parameter=True))
+
+
+def _est_bioreactor():
+    from .estgen import build_est_module
+    from .model import Model
     bio = Model()   # 3-state bioreactor of the UKF sigma-point golden (tests/test_KFs.py:695-712)
     bio.set_equations(equations="""
         dT/dt = alpha*(T_amb - T(t))
@@ -38,21 +57,36 @@ def build_all():
         r = (mu_0 + mu_1*T(t))*cS(t)*cB(t)/(K + cS(t))
         """)
     bio.setup(dt=.1)
-    paths.append(build_est_module(bio))
-    # LMPC double integrator (BASELINE config 1 / tests/test_LMPC.py:8-33) and its plant model
-    from .lmpc import LMPC
+    return build_est_module(bio)
+
+
+def _double_integrator():
+    from .model import Model
     di = Model(discrete=True)
     di.A = np.array([[1, di.dt], [0, 1]])
     di.B = np.array([[di.dt ** 2 / 2], [di.dt]])
     di.setup(dt=.5)
-    paths.append(build_est_module(di))
-    mpc = LMPC(di)
+    return di
+
+
+def _est_double_integrator():
+    from .estgen import build_est_module
+    return build_est_module(_double_integrator())
+
+
+def _lmpc():
+    # LMPC double integrator (BASELINE config 1 / tests/test_LMPC.py:8-33)
+    from .lmpc import LMPC
+    mpc = LMPC(_double_integrator())
     mpc.Q, mpc.R, mpc.horizon = np.eye(2), 1, 10
     mpc.set_box_constraints(x_lb=[-5, -5], x_ub=[5, 5], u_lb=[-1], u_ub=[1])
     mpc.setup()
-    paths.append(mpc.engine.module_path)
-    # MHE test problem and BASELINE config 5 (MLP dynamics + path following)
+    return mpc.engine.module_path
+
+
+def _mhe_reaction():
     from .mhe import MHE
+    from .model import Model
     rm = Model(name='reaction')
     x = rm.set_dynamical_states(['ca', 'cb'])
     u = rm.set_inputs(['f'])
@@ -69,10 +103,46 @@ def build_all():
     mhe.quad_stage_cost.add_state_noise(weights=[20., 20.])
     mhe.set_box_constraints(x_lb=[0., 0.], x_ub=[1., 1.], p_lb=[.1], p_ub=[5.])
     mhe.setup()
-    paths.append(mhe.engine.module_path)
-    from .examples import cstr_mhe, robot_nn_nmpc
-    paths.append(robot_nn_nmpc(N=5, hidden=8).engine.module_path)
-    # BASELINE configs 4 and 5 at their stated problem sizes
-    paths.append(cstr_mhe(N=20).engine.module_path)
-    paths.append(robot_nn_nmpc(N=30, hidden=32).engine.module_path)
-    return paths
+    return mhe.engine.module_path
+
+
+def _robot_small():
+    from .examples import robot_nn_nmpc
+    return robot_nn_nmpc(N=5, hidden=8).engine.module_path
+
+
+def _mhe_cstr():   # BASELINE config 4 at its stated problem size
+    from .examples import cstr_mhe
+    return cstr_mhe(N=20).engine.module_path
+
+
+def _robot_full():   # BASELINE config 5 at its stated problem size
+    from .examples import robot_nn_nmpc
+    return robot_nn_nmpc(N=30, hidden=32).engine.module_path
+
+
+def _cstr(N, method):
+    from .examples import cstr_nmpc
+    return cstr_nmpc(N=N, integration_method=method).engine.module_path
+
+
+def jobs():
+    """Callables that each build one generated module and return its path (run concurrently by ``build_all``)."""
+    from functools import partial
+    out = [_est_first_order, _est_scalar, _est_cstr, _est_cstr_k1, _est_bioreactor, _est_double_integrator, _lmpc,
+           _mhe_reaction, _robot_small, _mhe_cstr, _robot_full]
+    for N, method in ((50, 'collocation'), (10, 'collocation'), (10, 'rk4')):
+        out.append(partial(_cstr, N, method))
+    return out
+
+
+def _run(job):
+    return job()
+
+
+def build_all(workers: int = 6):
+    """Every module the tests, the smoke test and the bench need.  One PROCESS per job: the symbolic layer interns its
+    expression nodes in process-wide tables, which must not be shared between concurrently transcribed problems."""
+    import multiprocessing as mp
+    with mp.get_context('spawn').Pool(workers) as pool:
+        return pool.map(_run, jobs(), chunksize=1)

@@ -336,6 +336,65 @@ def fmax(a, b) -> Expr:
     return Expr('fmax', (Expr.wrap(a), Expr.wrap(b)))
 
 
+# ---------------------------------------------------------------------- learned components as call nodes
+# A Gaussian-process mean with hundreds of training points is not unrolled into the expression graph: it enters as a
+# node ``gp:<id>:<what>`` whose arguments are the query coordinates; ``<what>`` = m (mean), g<j> (d/dx_j) or h<j>_<l>
+# (d2/dx_j dx_l, j >= l).  Differentiation maps m -> g -> h; the emitters turn all nodes of one (GP, query) pair into ONE
+# call of a loop over the training table (``hb::gp_se_eval`` in csrc/gp_device.cuh; a vectorised NumPy loop for the
+# numeric evaluation used by the host-side tools and the oracle).
+GP_TABLES: Dict[str, dict] = {}
+
+
+def register_gp_table(Xs: np.ndarray, c: np.ndarray, inv_ls: np.ndarray) -> str:
+    """``Xs (n, d)``: training inputs divided by the length scales, ``c (n,)``: ``alpha_i * sigma_f^2``,
+    ``inv_ls (d,)``.  Returns the table id (content hash, so that equal GPs share a table)."""
+    import hashlib
+    Xs, c, inv_ls = (np.ascontiguousarray(v, dtype=float) for v in (Xs, c, inv_ls))
+    gid = hashlib.sha256(Xs.tobytes() + c.tobytes() + inv_ls.tobytes()).hexdigest()[:10]
+    GP_TABLES[gid] = dict(Xs=Xs, c=c, inv_ls=inv_ls, d=Xs.shape[1], n=Xs.shape[0])
+    return gid
+
+
+def gp_mean_node(gid: str, xq) -> 'Expr':
+    args = tuple(Expr.wrap(v) for v in as_vector(xq))
+    if len(args) != GP_TABLES[gid]['d']:
+        raise ValueError("gp_mean_node: dimension of the query point does not match the table")
+    return Expr(f'gp:{gid}:m', args)
+
+
+def _gp_parts(op: str):
+    _, gid, what = op.split(':')
+    return gid, what
+
+
+def _gp_out_index(what: str, d: int) -> int:
+    if what == 'm':
+        return 0
+    if what[0] == 'g':
+        return 1 + int(what[1:])
+    j, l = (int(v) for v in what[1:].split('_'))
+    return 1 + d + j * (j + 1) // 2 + l
+
+
+def _gp_numpy(gid: str, order: int, *xq):
+    """Numeric evaluation of one GP group: returns the list of outputs [m, g_0.., h_00, h_10, h_11, ...] (each shaped like
+    the broadcast query coordinates; complex arguments allowed for complex-step checks)."""
+    t = GP_TABLES[gid]
+    d, Xs, c, il = t['d'], t['Xs'], t['c'], t['inv_ls']
+    xs = [np.asarray(xq[j]) * il[j] for j in range(d)]
+    shape = np.broadcast(*xs).shape
+    r = [xs[j][..., None] - Xs[:, j] for j in range(d)]               # (..., n)
+    ck = c * np.exp(-.5 * sum(rj * rj for rj in r))
+    out = [ck.sum(axis=-1)]
+    if order >= 1:
+        out += [-(ck * r[j]).sum(axis=-1) * il[j] for j in range(d)]
+    if order >= 2:
+        for j in range(d):
+            for l in range(j + 1):
+                out.append((ck * (r[j] * r[l] - (1. if j == l else 0.))).sum(axis=-1) * il[j] * il[l])
+    return [np.broadcast_to(o, shape) for o in out]
+
+
 # ---------------------------------------------------------------------- vectors
 def sym(name: str, n: Optional[int] = None, m: Optional[int] = None):
     """``sym('x')`` -> scalar symbol; ``sym('x', 3)`` -> (3,) object array ``x_0..x_2``; ``sym('P', 2, 2)`` matrix."""
@@ -449,7 +508,7 @@ def _rebuild(op: str, args: tuple) -> Expr:
         return _pow(*args)
     if op == 'neg':
         return _neg(*args)
-    if op in ('atan2', 'fmin', 'fmax'):
+    if op in ('atan2', 'fmin', 'fmax') or op.startswith('gp:'):
         return Expr(op, args)
     return _unary(op, args[0])
 
@@ -512,6 +571,22 @@ def _deriv_node(node: Expr, d: List[Optional[Expr]]) -> Optional[Expr]:
         return t
     if op in ('fmin', 'fmax'):
         raise NotImplementedError("fmin/fmax are not differentiable in this layer")
+    if op.startswith('gp:'):
+        gid, what = _gp_parts(op)
+        t = None
+        for j, dj in enumerate(d):
+            if dj is None:
+                continue
+            if what == 'm':
+                part = Expr(f'gp:{gid}:g{j}', a)
+            elif what[0] == 'g':
+                i = int(what[1:])
+                part = Expr(f'gp:{gid}:h{max(i, j)}_{min(i, j)}', a)
+            else:
+                raise NotImplementedError("Third derivatives of a GP mean are not available")
+            term = _mul(part, dj)
+            t = term if t is None else _add(t, term)
+        return t
     if d[0] is None:
         return None
     x = a[0]
@@ -632,6 +707,8 @@ def _emit(outputs: List[Expr], inputs: Dict[int, str], lang: str, tmp: str = 't'
             uses[a.id] = uses.get(a.id, 0) + 1
     names: Dict[int, str] = {}
     lines: List[str] = []
+    gp_groups: Dict[tuple, str] = {}
+    order_nodes = order
     k = 0
     for node in order:
         if node.op == 'const':
@@ -644,6 +721,28 @@ def _emit(outputs: List[Expr], inputs: Dict[int, str], lang: str, tmp: str = 't'
             continue
         a = [names[x.id] for x in node.args]
         op = node.op
+        if op.startswith('gp:'):
+            gid, what = _gp_parts(op)
+            key = (gid,) + tuple(x.id for x in node.args)
+            if key not in gp_groups:
+                # highest derivative order any node of this (GP, query) group asks for -> one call for all of them
+                order = 0
+                for other in order_nodes:
+                    if other.op.startswith(f'gp:{gid}:') and tuple(x.id for x in other.args) == key[1:]:
+                        w2 = _gp_parts(other.op)[1]
+                        order = max(order, 0 if w2 == 'm' else (1 if w2[0] == 'g' else 2))
+                dd = GP_TABLES[gid]['d']
+                var = f'{tmp}gp{len(gp_groups)}'
+                if lang == 'c':
+                    nout = 1 + (dd if order >= 1 else 0) + (dd * (dd + 1) // 2 if order >= 2 else 0)
+                    lines.append(f'double {var}[{nout}]; {{ const double {var}x[{dd}] = {{{", ".join(a)}}}; '
+                                 f'hb::gp_se_eval<{dd}, {order}>(hb_gp_tab_{gid}, {GP_TABLES[gid]["n"]}, hb_gp_ils_{gid}, '
+                                 f'{var}x, {var}); }}')
+                else:
+                    lines.append(f'{var} = _gp_numpy({gid!r}, {order}, {", ".join(a)})')
+                gp_groups[key] = var
+            names[node.id] = f'{gp_groups[key]}[{_gp_out_index(what, GP_TABLES[gid]["d"])}]'
+            continue
         if op in _INFIX:
             rhs = f'{a[0]} {_INFIX[op]} {a[1]}'
         elif op == 'neg':
@@ -709,7 +808,7 @@ class Function:
             rets.append('[' + ', '.join(outs[pos:pos + len(vec)]) + ']')
             pos += len(vec)
         src.append('    return (' + ', '.join(rets) + ',)')
-        ns = {'np': np}
+        ns = {'np': np, '_gp_numpy': _gp_numpy}
         exec('\n'.join(src), ns)
         return ns[self.name]
 
@@ -769,6 +868,30 @@ class Function:
 
     def n_nodes(self) -> int:
         return len(topo_sort([o for vec in self.outputs for o in vec]))
+
+
+def gp_tables_used(exprs) -> List[str]:
+    """Ids of the GP tables referenced by ``exprs`` (in first-use order)."""
+    ids: List[str] = []
+    for node in topo_sort(as_vector(exprs)):
+        if node.op.startswith('gp:'):
+            gid = _gp_parts(node.op)[0]
+            if gid not in ids:
+                ids.append(gid)
+    return ids
+
+
+def gp_tables_c_source(ids: Sequence[str]) -> str:
+    """Definitions of the training tables for a generated module (device constants + host copies for the CPU logic build)."""
+    out = []
+    for gid in ids:
+        t = GP_TABLES[gid]
+        rows = np.concatenate([t['Xs'], t['c'][:, None]], axis=1).reshape(-1)
+        body = ', '.join(_c_const(float(v)) for v in rows)
+        ils = ', '.join(_c_const(float(v)) for v in t['inv_ls'])
+        out.append(f'HB_GP_TABLE double hb_gp_tab_{gid}[{rows.size}] = {{{body}}};')
+        out.append(f'HB_GP_TABLE double hb_gp_ils_{gid}[{t["d"]}] = {{{ils}}};')
+    return '\n'.join(out)
 
 
 def evaluate(exprs, symbols, values):

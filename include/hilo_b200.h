@@ -29,7 +29,7 @@ extern "C" {
 #endif
 
 /* ------------------------------------------------------------------------------------------------ library */
-#define HB_ABI_VERSION 2              /* bumps on every incompatible change of a struct or signature below */
+#define HB_ABI_VERSION 3              /* bumps on every incompatible change of a struct or signature below */
 int hb_version(void);                 /* HB_ABI_VERSION the library was built with; generated modules export the same
                                          number (hbm_abi_version) and hb_ocp_open / hb_est_open refuse a mismatch (-5) */
 const char* hb_last_error(void);      /* host string describing the last failure on this thread */
@@ -112,10 +112,16 @@ typedef struct hb_ocp_call {
                                1: additionally every reduced stage Hessian [Q S^T; S R] is convexified before the sweep
                                by mirroring its negative eigenvalues (|lambda|, floor regularization_eps)            */
   double regularization_eps;
+  double* kernel_ms_by_iter;        /* host in/out [HB_OCP_TIMED_ITERS][HB_OCP_KERNELS] or NULL: kernel_ms split by the iteration
+                                       index of the solve (last row = that index and beyond).  Iteration 0 of a solve is the
+                                       one launch in which every instance of the batch is active: the roofline of a kernel
+                                       is quoted on it                                                                   */
+  long long* kernel_count_by_iter;  /* host in/out, same shape, or NULL                                                  */
 } hb_ocp_call;
 
 /* kernel indices of kernel_ms / kernel_count */
 #define HB_OCP_KERNELS 11
+#define HB_OCP_TIMED_ITERS 8
 #define HB_OCP_KERNEL_NAMES "init,eval,riccati,expand,prep,trial,decide,apply,commit,count,step"
 
 /* The Riccati sweep of one interior-point iteration alone (unit tests, profiling): the block-banded KKT system

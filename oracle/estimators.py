@@ -132,3 +132,17 @@ def pf_step(f, h, X, y, u, p, w, v, R, uniforms, dt=1., discrete=True, substeps=
     if roughening_noise is not None:
         Xr = Xr + roughening_noise
     return Xr.sum(axis=1) / ns, np.cov(Xr), Xr, q, idx
+
+
+def lhsnorm(mu, sigma, n, rng=np.random):
+    """pf.py:425-447, restated: Latin-hypercube normal sample, ``(n, n_mu)``; ``rng`` = the legacy global RNG module."""
+    from scipy.stats import norm
+    mu = np.asarray(mu, dtype=float)
+    z = rng.multivariate_normal(mu, sigma, size=n)
+    x = np.zeros_like(z)
+    for k in range(mu.size):
+        x[np.argsort(z[:, k]), k] = np.arange(1, n + 1)
+    x = (x - rng.rand(*x.shape)) / n
+    for k in range(mu.size):
+        x[:, k] = norm.ppf(x[:, k], loc=mu[k], scale=np.sqrt(sigma[k][k]))
+    return x

@@ -137,6 +137,30 @@ def test_pf_resample_entry_matches_numpy_choice(cuda_device):
         np.testing.assert_array_equal(idx.cpu().numpy(), np.stack(ref))
 
 
+def test_pf_resampling_indices_equal_the_executed_reference_block(cuda_device):
+    """tests/golden/reference_numeric.json: ``ind`` of pf.py:406 obtained by executing the reference's own source with the
+    legacy RNG seeded; hb_pf_resample fed with the uniforms that seed produces must return the same integers."""
+    import ctypes as C
+    import json
+    import os
+    import torch
+    from hilo_mpc_b200 import _lib
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'reference_numeric.json')))
+    lib = _lib.load()
+    for c in gold['pf_resample_block']['cases']:
+        n = c['n_s']
+        np.random.seed(c['seed'])
+        unif = np.random.random_sample(n)
+        qt = torch.tensor(np.array(c['q'])[None], device=cuda_device)
+        ut = torch.tensor(unif[None], device=cuda_device)
+        cdf = torch.empty_like(qt)
+        idx = torch.zeros(1, n, dtype=torch.int64, device=cuda_device)
+        rc = lib.hb_pf_resample(1, n, qt.data_ptr(), ut.data_ptr(), cdf.data_ptr(), idx.data_ptr(),
+                                torch.cuda.current_stream().cuda_stream)
+        assert rc == 0
+        np.testing.assert_array_equal(idx.cpu().numpy()[0], np.array(c['ind']))
+
+
 def test_particle_filter_roughening_matches_oracle(cuda_device):
     """pf.py:411-421: roughening after the resampling.  With explicit draws the engine must equal the oracle; with the
     legacy global RNG seeded it must draw in the reference's order (process noise, measurement noise, resampling
@@ -174,11 +198,11 @@ def test_particle_filter_roughening_matches_oracle(cuda_device):
     np.random.seed(77)
     pf1.estimate(y=y[0])
     np.random.seed(77)
-    w1 = np.random.multivariate_normal(np.zeros(1), np.array([[10.]]), size=ns)
+    w1 = est.lhsnorm(np.zeros(1), np.array([[10.]]), ns)      # the filter's default density (pf.py:80, :363)
     v1 = (np.sqrt(np.array([[1.]])) @ np.random.randn(1, ns)).T
     u1 = np.random.random_sample(ns)
     _, _, Xres, _, _ = est.pf_step(f, hfun, X0[0].T, y[0], None, None, w1.T, v1.T, np.array([[1.]]), u1)
-    j1 = np.random.multivariate_normal(np.zeros(1), est.pf_roughening_covariance(Xres, .2), size=ns)
+    j1 = est.lhsnorm(np.zeros(1), est.pf_roughening_covariance(Xres, .2), ns)
     xm1, Pm1, Xr1, _, _ = est.pf_step(f, hfun, X0[0].T, y[0], None, None, w1.T, v1.T, np.array([[1.]]), u1,
                                       roughening_noise=j1.T)
     np.testing.assert_allclose(pf1.particles[0].cpu().numpy(), Xr1.T, rtol=1e-11)

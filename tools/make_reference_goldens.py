@@ -1,0 +1,143 @@
+#!/usr/bin/env python
+"""Golden vectors produced by EXECUTING the reference's own source (read from /root/reference at generation time only).
+
+CasADi is not installable here, so the reference package cannot be imported.  Some routines on the hot path are pure
+NumPy/SciPy though and touch CasADi only through a couple of trivial calls; this script extracts their source text from
+the reference tree, executes it unmodified in a namespace with a *stub* ``ca`` (only ``collocation_points``, ``sum2`` and
+``DM``-free helpers, restated below) and stores inputs and outputs as fixtures under ``tests/golden/``:
+
+* ``RungeKutta._construct_polynomial_basis`` (hilo_mpc/util/modeling.py:1091-1127): the collocation constants B, C, D, tau
+  every collocation transcription is built from (NMPC, MHE).
+* ``lhsnorm`` (hilo_mpc/modules/estimator/pf.py:425-447): Latin-hypercube normal sampling of the particle filter.
+* the resampling / roughening / moment block of ``ParticleFilter.estimate`` (pf.py:405-421), with the legacy global RNG.
+
+Run:  python tools/make_reference_goldens.py   (needs /root/reference; the tests only read the committed JSON).
+"""
+import ast
+import json
+import os
+import sys
+import textwrap
+
+import numpy as np
+from scipy.stats import norm
+
+REF = os.environ.get('HILO_REFERENCE', '/root/reference')
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden',
+                   'reference_numeric.json')
+
+
+class _CaStub:
+    """The two CasADi calls the extracted sources make."""
+
+    @staticmethod
+    def collocation_points(degree, method):
+        # casadi.collocation_points: Gauss-Legendre points / Radau IIA points on (0, 1] (roots of the shifted Legendre /
+        # of P_{n-1} - P_n), computed here from the Legendre polynomials
+        from numpy.polynomial import legendre as L
+        if method == 'legendre':
+            r = L.legroots([0] * degree + [1])
+        elif method == 'radau':
+            c = np.zeros(degree + 1)
+            c[degree - 1], c[degree] = 1., -1.          # P_{n-1} - P_n has the root x = 1 (right end point)
+            r = L.legroots(c)
+        else:
+            raise ValueError(method)
+        return sorted(float(v) for v in (np.real(r) + 1.) / 2.)
+
+    @staticmethod
+    def sum2(a):
+        return np.sum(np.asarray(a), axis=1)
+
+
+class _H(float):
+    """Stands in for the symbolic step size ``h``: ``h.zeros(n)`` and ``h * tau`` are all the source needs."""
+
+    def zeros(self, n):
+        return np.zeros(n)
+
+
+def _function_source(path, name, cls=None):
+    src = open(path).read()
+    tree = ast.parse(src)
+    nodes = tree.body
+    if cls is not None:
+        nodes = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == cls).body
+    fn = next(n for n in nodes if isinstance(n, ast.FunctionDef) and n.name == name)
+    lines = src.split('\n')[fn.lineno - 1:fn.end_lineno]
+    return textwrap.dedent('\n'.join(lines)), (fn.lineno, fn.end_lineno)
+
+
+def main():
+    out = {'reference': 'hilo-mpc/hilo-mpc @ /root/reference', 'generator': 'tools/make_reference_goldens.py'}
+    ca = _CaStub()
+
+    # ---- collocation constants
+    path = os.path.join(REF, 'hilo_mpc', 'util', 'modeling.py')
+    src, span = _function_source(path, '_construct_polynomial_basis', cls='RungeKutta')
+    ns = {'np': np, 'ca': ca, 'Symbolic': object}
+    exec(src.replace('@staticmethod\n', ''), ns)
+    basis = {}
+    for method in ('radau', 'legendre'):
+        for deg in (1, 2, 3, 4, 5):
+            B, C, D, T = ns['_construct_polynomial_basis'](deg, method, _H(1.))
+            basis[f'{method}{deg}'] = {'B': B.tolist(), 'C': C.tolist(), 'D': D.tolist(), 'T': np.asarray(T).tolist()}
+    out['polynomial_basis'] = {'source': f'hilo_mpc/util/modeling.py:{span[0]}-{span[1]}', 'values': basis}
+
+    # ---- lhsnorm
+    path = os.path.join(REF, 'hilo_mpc', 'modules', 'estimator', 'pf.py')
+    src, span = _function_source(path, 'lhsnorm')
+    ns = {'np': np, 'norm': norm}
+    exec(src, ns)
+    cases = []
+    for seed, mu, sigma, n in ((0, [0., 0.], [[1., 0.], [0., 1.]], 15), (7, [1., -2., .5], [[.5, .1, 0.], [.1, 2., .3], [0., .3, 1.]], 40)):
+        np.random.seed(seed)
+        x = ns['lhsnorm'](np.array(mu), np.array(sigma), n)
+        cases.append({'seed': seed, 'mu': mu, 'sigma': sigma, 'n': n, 'x': x.tolist()})
+    out['lhsnorm'] = {'source': f'hilo_mpc/modules/estimator/pf.py:{span[0]}-{span[1]}', 'cases': cases}
+
+    # ---- resampling / roughening / moments block of ParticleFilter.estimate
+    lines = open(path).read().split('\n')
+    start = next(i for i, ln in enumerate(lines) if '# Resample (Survival of the fittest)' in ln)
+    end = next(i for i, ln in enumerate(lines) if 'P = convert(np.cov(X), ca.DM)' in ln)
+    block = textwrap.dedent('\n'.join(lines[start:end + 1]))
+
+    class _Q:   # q.full().flatten()
+        def __init__(self, a):
+            self.a = np.asarray(a, dtype=float)
+
+        def full(self):
+            return self.a.reshape(1, -1)
+
+    pf_cases = []
+    for seed, n_x, n_s, rough in ((3, 2, 15, False), (11, 3, 64, True), (5, 4, 200, True)):
+        rng = np.random.RandomState(1000 + seed)
+        X = rng.standard_normal((n_x, n_s)) * np.arange(1, n_x + 1)[:, None] + np.arange(n_x)[:, None]
+        Y = X[:1] ** 2
+        q = rng.uniform(.01, 1., n_s)
+        q /= q.sum()
+
+        class _Self:
+            _sample_size = n_s
+            _roughening = rough
+            _n_x = n_x
+            _roughening_tuning_param = .2
+            _transpose_pdf = True
+            _pdf = staticmethod(ns['lhsnorm'])
+        env = {'np': np, 'ca': ca, 'self': _Self(), 'X': X.copy(), 'Y': Y.copy(), 'q': _Q(q),
+               'convert': lambda a, _t: np.asarray(a)}
+        ca.DM = None
+        np.random.seed(seed)
+        exec(block, env)
+        pf_cases.append({'seed': seed, 'n_x': n_x, 'n_s': n_s, 'roughening': rough, 'K': .2, 'X_in': X.tolist(),
+                         'q': q.tolist(), 'ind': np.asarray(env['ind']).tolist(), 'X_out': np.asarray(env['X']).tolist(),
+                         'x_mean': np.asarray(env['x']).tolist(), 'P': np.asarray(env['P']).tolist()})
+    out['pf_resample_block'] = {'source': f'hilo_mpc/modules/estimator/pf.py:{start + 1}-{end + 1}', 'cases': pf_cases}
+
+    with open(OUT, 'w') as f:
+        json.dump(out, f)
+    print('wrote', OUT, os.path.getsize(OUT), 'bytes')
+
+
+if __name__ == '__main__':
+    sys.exit(main())
