@@ -95,6 +95,8 @@ def _register_optional(lib: C.CDLL) -> None:
     pred = [i, i, i, vp, vp, vp, d, d, d, vp, vp, vp, vp, vp, vp]
     sigs = {
         'hb_pf_resample': ([i, i, vp, vp, vp, vp, vp], i),
+        'hb_lmpc_work_doubles': ([i, i, i], sz),
+        'hb_lmpc_solve': ([i, i, i, i] + [vp] * 13 + [d, i, vp, sz, vp], i),
         'hb_gp_fit_work_doubles': ([i], sz),
         'hb_gp_predict_work_doubles': ([i, i], sz),
         'hb_gp_fit': (fit, i),

@@ -12,6 +12,7 @@
 
 #include "../../include/hilo_b200.h"
 #include "est_kernels.cuh"
+#include "lmpc_qp.cuh"
 
 namespace {
 thread_local char g_err[1024] = "";
@@ -199,6 +200,31 @@ int hb_pf_resample(int B, int n, const double* q, const double* unif, double* cd
   hb::launch_1d<hb::PfResampleOnly>(a, B, (cudaStream_t)stream);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_err("hb_pf_resample: %s", cudaGetErrorString(e)); return (int)e; }
+  return 0;
+}
+
+size_t hb_lmpc_work_doubles(int B, int n, int mx) {
+  if (B <= 0 || n <= 0 || mx < 0) return 0;
+  return (size_t)B * hb::lmpc_work_per_instance(n, mx);
+}
+
+int hb_lmpc_solve(int B, int n, int mx, int nx, const double* H, const double* F, const double* Gam, const double* Phi,
+                  const double* ulb, const double* uub, const double* xlb, const double* xub, const double* x0,
+                  double* u, double* xpred, int* status, int* iters, double tol, int max_iter, double* work,
+                  size_t work_doubles, void* stream) {
+  if (B <= 0 || n <= 0 || n > 256 || mx < 0 || nx <= 0 || !H || !F || !ulb || !uub || !x0 || !u || !status || !iters ||
+      (mx > 0 && (!Gam || !Phi || !xlb || !xub))) {
+    set_err("hb_lmpc_solve: invalid argument");
+    return -1;
+  }
+  if (work == nullptr || work_doubles < hb_lmpc_work_doubles(B, n, mx)) { set_err("hb_lmpc_solve: workspace too small"); return -2; }
+  hb::LmpcArgs a;
+  a.B = B; a.n = n; a.mx = mx; a.nx = nx; a.max_iter = max_iter > 0 ? max_iter : 100; a.tol = tol > 0.0 ? tol : 1e-10;
+  a.H = H; a.F = F; a.Gam = Gam; a.Phi = Phi; a.ulb = ulb; a.uub = uub; a.xlb = xlb; a.xub = xub; a.x0 = x0;
+  a.u = u; a.xpred = xpred; a.status = status; a.iters = iters; a.work = work;
+  hb::launch_1d<hb::LmpcDenseQp>(a, B, (cudaStream_t)stream);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_err("hb_lmpc_solve: %s", cudaGetErrorString(e)); return (int)e; }
   return 0;
 }
 

@@ -49,7 +49,7 @@ def cstr_side_reaction_gp(n_train: int = 24, seed: int = 1):
     return gp
 
 
-def cstr_gp_nmpc(gp, N: int = 10, dt: float = 0.005, solver_options=None) -> NMPC:
+def cstr_gp_nmpc(gp, N: int = 10, dt: float = 0.005, solver_options=None, setup: bool = True) -> NMPC:
     """Config 3 (GP-output-feedback NMPC): the CSTR of config 2 with the side-reaction rate replaced by the posterior
     mean of ``gp`` (symbolic query, the way the reference embeds learned components: dynamic_model.py:3040-3080)."""
     from . import symbolic as sx
@@ -69,7 +69,8 @@ def cstr_gp_nmpc(gp, N: int = 10, dt: float = 0.005, solver_options=None) -> NMP
     nmpc.set_initial_guess(x_guess=x_ss, u_guess=u_ss)
     if solver_options:
         nmpc.set_solver_opts(solver_options)
-    nmpc.setup()
+    if setup:
+        nmpc.setup()
     return nmpc
 
 

@@ -80,7 +80,7 @@ def _lmpc():
     mpc = LMPC(_double_integrator())
     mpc.Q, mpc.R, mpc.horizon = np.eye(2), 1, 10
     mpc.set_box_constraints(x_lb=[-5, -5], x_ub=[5, 5], u_lb=[-1], u_ub=[1])
-    mpc.setup()
+    mpc.setup(solver='riccati')   # the stage-structured path; the condensed dense-QP path needs no generated module
     return mpc.engine.module_path
 
 

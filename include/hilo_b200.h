@@ -204,6 +204,22 @@ int hb_est_close(hb_est_t h);
  * cdf_work [B][n] scratch, idx [B][n] out; indices are bit-identical to NumPy's for the same q and uniforms.      */
 int hb_pf_resample(int B, int n, const double* q, const double* unif, double* cdf_work, long long* idx, void* stream);
 
+/* ------------------------------------------------------------------------------------------------ linear MPC
+ * LMPC.optimize for B instances (replaces ca.conic('solver','qpoases',{h,a}) + solver(h=,g=,a=,lbx=,ubx=,lba=,uba=),
+ * mpc.py:2268-2276, :2374): the horizon is condensed once on the host (LMPC.setup),
+ *     x_pred = Phi x0 + Gam u,   H = Gam^T Qbar Gam + Rbar [n][n],   F = Gam^T Qbar Phi [n][nx],
+ * n = N nu, mx = N nx, and every instance solves the dense QP
+ *     min_u 1/2 u^T H u + (F x0)^T u   s.t.  ulb <= u <= uub [n],  xlb <= Phi x0 + Gam u <= xub [mx]
+ * with a primal-dual interior-point method (relative KKT tolerance tol; |bound| >= 1e19 = none).  The equality block of the
+ * reference's QP enters only through Phi / Gam, so both the intended input block I_N (x) B and the reference's kron(B, I_N)
+ * (mpc.py:2243, LMPC(bug_compat=True)) are served by the same entry point.
+ * u [B][n] out, xpred [B][mx] out or NULL, status [B]: 1 optimal, 5 iteration cap, -1 numerical failure.            */
+size_t hb_lmpc_work_doubles(int B, int n, int mx);
+int hb_lmpc_solve(int B, int n, int mx, int nx, const double* H, const double* F, const double* Gam, const double* Phi,
+                  const double* ulb, const double* uub, const double* xlb, const double* xub, const double* x0,
+                  double* u, double* xpred, int* status, int* iters, double tol, int max_iter, double* work,
+                  size_t work_doubles, void* stream);
+
 /* ------------------------------------------------------------------------------------------------ Gaussian process
  * Exact inference with the squared-exponential kernel (machine_learning/gp/inference.py:197-217, kernel.py:650-734).
  * X is (d, n) row-major like the reference's training data (gp.py:347-354); hyper-parameters are passed in natural

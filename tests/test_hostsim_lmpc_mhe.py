@@ -28,7 +28,7 @@ def _lmpc(N=10):
     mpc.horizon = N
     mpc.set_box_constraints(x_lb=[-5, -5], x_ub=[5, 5], u_lb=[-1], u_ub=[1])
     mpc._build_module = False
-    mpc.setup()
+    mpc.setup(solver='riccati')   # the stage-structured path (the condensed dense-QP path needs no generated module)
     return mpc
 
 
@@ -82,7 +82,7 @@ def test_unconstrained_lq_problem_reproduces_lqr_golden():
     mpc = LMPC(model)
     mpc.Q, mpc.R, mpc.horizon = np.eye(3), np.eye(2), 6
     mpc._build_module = False
-    mpc.setup()
+    mpc.setup(solver='riccati')
     spec = mpc.spec
     host = HostOcp(OcpGenerator(spec).build(hostsim=True))
     x0 = np.array([[1., 0., 1.]])
