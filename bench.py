@@ -41,7 +41,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-KERNEL_NAMES = "init,eval,riccati,expand,prep,trial,decide,apply,commit,count,step".split(',')
+KERNEL_NAMES = "init,eval,riccati,expand,prep,trial,decide,apply,commit,count,step,ricfix".split(',')
 TIMED_ITERS = 8
 CSTR_DIST = np.array([.02, .02, .5, .5])    # closed-loop disturbance added to the predicted next state (configs 2, 3)
 ROBOT_DIST = np.array([.05, .05, .02, .01])  # config 5
@@ -174,7 +174,7 @@ WORKLOADS = {
     4: dict(metric='batched MHE + UKF estimates/sec (CSTR, N=20)', unit='estimates/s', batch=4096,
             workload='MHE (horizon 20, Radau-3, 4 states + 1 estimated parameter, state noise, arrival cost) + UKF on the '
                      'CSTR, seeded synthetic measurement stream (cstr_mhe_data, seed 2 + rank), one estimate = '
-                     'add_measurements + MHE.estimate + UKF.estimate, tol=1e-8'),
+                     'add_measurements + MHE.estimate + UKF.estimate, tol=1e-8, warm start shifted with the window'),
     5: dict(metric='batched NMPC steps/sec (path following, MLP dynamics, N=30)', unit='steps/s', batch=4096,
             workload='path-following NMPC of a mobile robot, right-hand side = 1x32 tanh MLP, path variable, nx=5 nu=3 '
                      'N=30 dt=1 Radau-3, closed loop from x0 = [15,30,0,0] + diag(2,2,.5,.2) U(-1,1) (seed 3 + rank) '
@@ -192,7 +192,8 @@ def make_nmpc(config, solver_options=None, build=True):
         nmpc = cstr_gp_nmpc(gp, N=50, setup=False)
     elif config == 5:
         nmpc = robot_nn_nmpc(N=30, hidden=32, setup=False)
-        solver_options = dict(solver_options or {}, **{'b200.regularization': 'mirror', 'ipopt.max_iter': 1500})
+        solver_options = dict({'b200.regularization': 'mirror', 'b200.regularization_mu': 1e-4, 'ipopt.max_iter': 1500},
+                              **(solver_options or {}))
     else:
         raise ValueError(config)
     if solver_options:
@@ -241,44 +242,55 @@ def _cpu_nlp(config):
 
 
 def _cpu_closed_loop(arg):
-    """One worker: closed loop of `steps` solves for each instance of its chunk. Returns (solves, optimal)."""
+    """One worker: for each instance of its chunk an UNTIMED first solve (cold start: the GPU arm keeps it out of its
+    timed region as well), then `steps` timed closed-loop solves with the primal warm start of the reference
+    (mpc.py:725-726).  Returns (timed solves, converged, seconds in the timed solves)."""
     config, idx, steps, rank = arg
     nlp, ctl = _cpu_nlp(config)
     done = ok = 0
+    secs = 0.
     if config == 4:
         from hilo_mpc_b200.examples import cstr_mhe_data
         N = 20
-        u, y, _, _ = cstr_mhe_data(int(max(idx)) + 1, N + steps, seed=2 + rank)
+        u, y, _, _ = cstr_mhe_data(int(max(idx)) + 1, N + steps + 1, seed=2 + rank)
         xs = np.concatenate([ctl._x_scaling, ctl._p_scaling])
         for b in idx:
             ap = np.concatenate([ctl.quad_arrival_cost.x_guess, ctl.quad_arrival_cost.p_guess])
             v0 = None
-            for k in range(steps):
+            for k in range(steps + 1):
                 sp = np.concatenate([u[k:k + N, b], y[k:k + N, b]], axis=1)
+                t0 = time.perf_counter()
                 res, xo, _ = nlp.solve(None, v0=v0, dt=ctl.sampling_interval, sps=sp, ap=ap)
+                el = time.perf_counter() - t0
                 v0 = res.x
                 ap = np.concatenate([xo[:4, 2] * xs[:4], xo[4:, 0] * xs[4:]])   # smoothing update (mhe.py:254-256)
-                done += 1
-                ok += int(res.status in (1, 2))
-        return done, ok
+                if k > 0:
+                    done += 1
+                    ok += int(res.status in (1, 2))
+                    secs += el
+        return done, ok, secs
     x0 = initial_states(config, int(max(idx)) + 1, rank)
-    noise = disturbance(config, steps, int(max(idx)) + 1, rank)
+    noise = disturbance(config, steps + 1, int(max(idx)) + 1, rank)
     xs = np.asarray(ctl._xs_full)
     nx0 = 4
     for b in idx:
         x = x0[b].copy()
         theta = 0.
         v0 = None
-        for k in range(steps):
+        for k in range(steps + 1):
             xa = x if len(xs) == nx0 else np.concatenate([x, [theta]])
+            t0 = time.perf_counter()
             res, xo, _ = nlp.solve(xa / xs, v0=v0, dt=ctl.sampling_interval)
+            el = time.perf_counter() - t0
             v0 = res.x                                     # primal warm start only (mpc.py:725-726)
             x = xo[:nx0, 1] * xs[:nx0] + noise[k, b]
             if len(xs) > nx0:
                 theta = xo[nx0, 1] * xs[nx0]
-            done += 1
-            ok += int(res.status in (1, 2))
-    return done, ok
+            if k > 0:
+                done += 1
+                ok += int(res.status in (1, 2))
+                secs += el
+    return done, ok, secs
 
 
 def _cpu_warm(config):
@@ -287,25 +299,22 @@ def _cpu_warm(config):
 
 
 def cpu_sample(config, n_instances, steps, n_procs, rank=0):
-    """Times the oracle on the first ``n_instances`` instances of the workload for ``steps`` closed-loop steps with
-    ``n_procs`` worker processes.  Returns (units_per_s, seconds, optimal_fraction)."""
+    """Times the oracle on the first ``n_instances`` instances of the workload for ``steps`` warm closed-loop steps each
+    (after an untimed cold first solve) with ``n_procs`` worker processes.  Returns (units_per_s, seconds of the timed
+    solves on the slowest worker, converged fraction, wall seconds incl. the cold solves)."""
     idx = np.arange(n_instances)
     _cpu_nlp(config)   # in the parent: forked workers inherit the problem (config 3 fits its GP on the device here)
+    t_wall = time.perf_counter()
     if n_procs <= 1:
-        _cpu_warm(config)
-        t0 = time.perf_counter()
-        done, ok = _cpu_closed_loop((config, idx, steps, rank))
-        el = time.perf_counter() - t0
+        done, ok, el = _cpu_closed_loop((config, idx, steps, rank))
     else:
         import multiprocessing as mp
         chunks = [c for c in np.array_split(idx, n_procs) if len(c)]
         with mp.get_context('fork').Pool(len(chunks)) as pool:
-            pool.map(_cpu_warm, [config] * len(chunks))   # symbolic stage functions once per worker (the reference's setup())
-            t0 = time.perf_counter()
             res = pool.map(_cpu_closed_loop, [(config, c, steps, rank) for c in chunks])
-            el = time.perf_counter() - t0
         done, ok = sum(r[0] for r in res), sum(r[1] for r in res)
-    return done / el, el, ok / max(done, 1)
+        el = max(r[2] for r in res)
+    return done / el, el, ok / max(done, 1), time.perf_counter() - t_wall
 
 
 def run_reference(args):
@@ -315,14 +324,12 @@ def run_reference(args):
     w = WORKLOADS[args.config]
     cores = os.cpu_count() or 1
     # config 3 needs the GP fitted on a device (hb_gp_fit); the CPU arm then differs from config 2 only by the GP terms
-    per_worker_steps = {2: 3, 3: 2, 4: 3, 5: 2}[args.config]
+    per_worker_steps = {2: 4, 3: 3, 4: 4, 5: 2}[args.config]
     n_inst = cores
-    if args.config != 5:   # warm-up: forks, page cache, symbolic set-up (a cold config-5 solve alone takes ~a minute)
-        cpu_sample(args.config, min(n_inst, cores), 1, cores)
     times, done_total = [], 0
     t_budget = time.perf_counter()
     for k in range(max(1, args.steps // 10)):
-        v, el, okf = cpu_sample(args.config, n_inst, per_worker_steps, cores)
+        v, el, okf, wall = cpu_sample(args.config, n_inst, per_worker_steps, cores)
         times.append(el)
         done_total += n_inst * per_worker_steps
         if time.perf_counter() - t_budget > 30.:   # bounded sample: the whole arm stays within a few minutes
@@ -336,7 +343,8 @@ def run_reference(args):
         'config': {'workload': w['workload'], 'config': args.config, 'sample_instances': n_inst,
                    'sample_closed_loop_steps': per_worker_steps,
                    'note': 'one timed sample = the first `sample_instances` instances of the workload for '
-                           '`sample_closed_loop_steps` closed-loop steps each, one instance per worker process'},
+                           '`sample_closed_loop_steps` warm closed-loop steps each (after an untimed cold first solve, '
+                           'which the GPU arm also keeps out of its timed region), one instance per worker process'},
         'cpu_baseline': {'value': value, 'unit': w['unit'], 'cores': cores, 'kind': 'port',
                          'sample': f'{n_inst} instances x {per_worker_steps} closed-loop steps x {len(times)} repeats, '
                                    f'{cores} processes; NumPy/SciPy restatement of the reference\'s flat NLP + IPOPT '
@@ -416,6 +424,20 @@ def measured_peaks_in_run(dev):
     return out
 
 
+def _extra_opts(args):
+    out = {}
+    for kv in args.opt:
+        k, v = kv.split('=', 1)
+        try:
+            out[k] = int(v)
+        except ValueError:
+            try:
+                out[k] = float(v)
+            except ValueError:
+                out[k] = v
+    return out
+
+
 class NmpcLoop:
     """Closed loop of configs 2, 3, 5."""
 
@@ -428,6 +450,7 @@ class NmpcLoop:
             opts['b200.riccati_variant'] = args.riccati_variant
         if args.no_compaction:
             opts['b200.compaction'] = 0
+        opts.update(_extra_opts(args))
         self.nmpc = make_nmpc(config, opts)
         self.eng = self.nmpc.engine
         self.nx0 = 4
@@ -521,7 +544,9 @@ class MheUkfLoop:
         self.torch, self.dev, self.rank = torch, dev, rank
         self.B = args.batch or WORKLOADS[4]['batch']
         self.N = 20
-        opts = {'b200.warm_start': args.warm_start, 'b200.warm_start_mu': args.warm_mu}
+        # the horizon window moves by one sample per estimate: the kept solution is shifted with it
+        opts = {'b200.warm_start': args.warm_start, 'b200.warm_start_mu': args.warm_mu, 'b200.shift_warm_start': 1}
+        opts.update(_extra_opts(args))
         self.opts = opts
         self.make_mhe = lambda: cstr_mhe(N=self.N, solver_options=opts)
         self.mhe = self.make_mhe()
@@ -649,6 +674,8 @@ def main():
     ap.add_argument('--hessian', default='exact', choices=['exact', 'gauss-newton'])
     ap.add_argument('--riccati-variant', type=int, default=None, help='override b200.riccati_variant (tuning runs)')
     ap.add_argument('--no-compaction', action='store_true', help='b200.compaction=0: every launch over the whole batch')
+    ap.add_argument('--opt', action='append', default=[], metavar='KEY=VALUE',
+                    help='extra solver option (tuning runs), e.g. --opt b200.eval_variant=0')
     ap.add_argument('--warm-start', type=int, default=1, help='1: reuse multipliers + small initial barrier parameter '
                                                               'between closed-loop steps; 0: IPOPT-default restart')
     ap.add_argument('--warm-mu', type=float, default=None,
@@ -796,7 +823,8 @@ def main():
         a_r = alg['riccati'] / (full_launch['riccati'] * 1e-6) / 1e9
         roofline['riccati_sweep'] = {'achieved': a_r, 'frac': a_r / peak, 'launch_us': full_launch['riccati'],
                                      'algorithmic_bytes_per_launch': alg['riccati'],
-                                     'note': 'launch time includes the no-op fix-up launch that follows the sweep'}
+                                     'note': 'the sweep kernel alone; the (normally empty) fix-up launch that follows it is '
+                                             'timed as kernel "ricfix"'}
     traffic_path = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
     if os.path.exists(traffic_path) and args.config == 2:
         with open(traffic_path) as f:
@@ -816,14 +844,15 @@ def main():
 
     cpu_baseline = None
     if not args.no_cpu_baseline:
-        steps_cpu = {2: 3, 3: 2, 4: 3, 5: 2}[args.config]
+        steps_cpu = {2: 4, 3: 3, 4: 4, 5: 2}[args.config]
         if args.config == 5:
-            args.cpu_sample = 1      # a cold solve of this problem takes the oracle about a minute
-        v, el, okf = cpu_sample(args.config, args.cpu_sample, steps_cpu, 1)
+            args.cpu_sample = 1      # the (untimed) cold solve of this problem alone takes the oracle minutes
+        v, el, okf, wall = cpu_sample(args.config, args.cpu_sample, steps_cpu, 1)
         cpu_baseline = {'value': v, 'unit': w['unit'], 'cores': 1, 'kind': 'port',
-                        'sample': f'first {args.cpu_sample} instances of the same closed loop x {steps_cpu} steps (cold '
-                                  f'first solve, primal warm start afterwards), {el:.1f} s, single process; NumPy/SciPy '
-                                  f'restatement of the reference\'s flat NLP + IPOPT algorithm', 'converged_frac': okf}
+                        'sample': f'first {args.cpu_sample} instances of the same closed loop x {steps_cpu} warm steps '
+                                  f'(primal warm start; the cold first solve is not timed), {el:.1f} s, single process; '
+                                  f'NumPy/SciPy restatement of the reference\'s flat NLP + IPOPT algorithm',
+                        'converged_frac': okf}
 
     work_mb = loop.eng._t['work'].numel() * 8 / 1e6
     cfg = {'workload': w['workload'], 'config': args.config, 'batch_per_gpu': B, 'parallelism': f'batch-shard x{world}',

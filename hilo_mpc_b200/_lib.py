@@ -41,7 +41,7 @@ class OcpCall(C.Structure):
                 ('n_iterations_launched', _IP), ('n_kernel_launches', C.POINTER(C.c_longlong)),
                 ('kernel_ms', _DP), ('kernel_count', C.POINTER(C.c_longlong)), ('riccati_variant', C.c_int), ('warm_start', C.c_int), ('mu_init_warm', C.c_double), ('eval_variant', C.c_int), ('first_check', C.c_int),
                 ('n_iterations_needed', C.POINTER(C.c_int)), ('step_variant', C.c_int), ('no_compaction', C.c_int),
-                ('regularization', C.c_int), ('regularization_eps', C.c_double),
+                ('regularization', C.c_int), ('regularization_eps', C.c_double), ('regularization_mu', C.c_double), ('shift_warm_start', C.c_int),
                 ('kernel_ms_by_iter', C.c_void_p), ('kernel_count_by_iter', C.c_void_p)]
 
 
@@ -85,7 +85,7 @@ def load() -> C.CDLL:
     return lib
 
 
-ABI_VERSION = 3   # HB_ABI_VERSION of include/hilo_b200.h this binding was written against
+ABI_VERSION = 6   # HB_ABI_VERSION of include/hilo_b200.h this binding was written against
 
 
 def _register_optional(lib: C.CDLL) -> None:

@@ -27,7 +27,8 @@ struct OcpCount {  // (b): poll[0] = instances still active (their indices appen
 
 // Per-kernel device timing with CUDA events recorded on the launching stream (hb_ocp_call.kernel_ms != NULL).
 // Events are only read back at the points where the driver synchronises anyway (convergence polls).
-enum { K_INIT = 0, K_EVAL, K_RICCATI, K_EXPAND, K_PREP, K_TRIAL, K_DECIDE, K_APPLY, K_COMMIT, K_COUNT_ACTIVE, K_STEP, K_NUM };
+enum { K_INIT = 0, K_EVAL, K_RICCATI, K_EXPAND, K_PREP, K_TRIAL, K_DECIDE, K_APPLY, K_COMMIT, K_COUNT_ACTIVE, K_STEP, K_RICFIX,
+       K_NUM };
 
 struct KernelTimer {
   bool on = false;
@@ -99,7 +100,7 @@ struct OcpModule {
   }
 
   // the sweep of one iteration, fastest version the problem admits (riccati_variant: see hb_ocp_call)
-  static int launch_riccati(const OcpArgs& a, int variant, cudaStream_t s) {
+  static int launch_riccati(const OcpArgs& a, int variant, cudaStream_t s, KernelTimer* tm = nullptr) {
     bool ric_done = false;
     if (variant >= 2) {
       int rc6 = -100;
@@ -115,7 +116,10 @@ struct OcpModule {
       }
       if (rc6 > 0) return rc6;
       ric_done = rc6 == 0;
-      if (ric_done) launch_1d<OcpRiccatiFix<P>>(a, a.n_instances(), s);   // instances flagged as non-convex (rare)
+      if (ric_done) {   // instances flagged as non-convex (rare): timed as its own kernel
+        if (tm) { tm->end(); tm->begin(K_RICFIX); }
+        launch_1d<OcpRiccatiFix<P>>(a, a.n_instances(), s);
+      }
     }
 #if HB_DEVICE_BUILD
     if constexpr (RiccatiTma2<P>::SUPPORTED) {
@@ -195,6 +199,7 @@ struct OcpModule {
     a.time0 = c->time0; a.dt = c->dt; a.warm = c->warm_start;
     a.convexify = c->regularization == 1 ? 1 : 0;
     a.convexify_eps = c->regularization_eps > 0.0 ? c->regularization_eps : 1e-4;
+    a.convexify_mu = c->regularization_mu;
     if (a.warm) a.mu_init = c->mu_init_warm;
     a.x0 = c->x0; a.sp = c->sp; a.sp_stride = c->sp_stride; a.tp = c->tp; a.tp_stride = c->tp_stride;
     a.uold = c->uold; a.uold_stride = c->uold_stride; a.ap = c->ap; a.ap_stride = c->ap_stride;
@@ -223,7 +228,10 @@ struct OcpModule {
     static thread_local KernelTimer tm;
     tm.on = c->kernel_ms != nullptr; tm.s = s; tm.ms = c->kernel_ms; tm.count = c->kernel_count; tm.launches = 0;
     tm.ms_it = c->kernel_ms_by_iter; tm.count_it = c->kernel_count_by_iter; tm.it = 0;
-    tm.begin(K_INIT); launch_2d<OcpInit<P>>(a, a.B, OcpInit<P>::ETOT, s); tm.end();
+    tm.begin(K_INIT);
+    if (c->warm_start && c->shift_warm_start) launch_2d<OcpShift<P>>(a, a.B, OcpShift<P>::PER, s);
+    launch_2d<OcpInit<P>>(a, a.B, OcpInit<P>::ETOT, s);
+    tm.end();
     // Host polling schedule: every check_every iterations, or - with a hint from the previous solve of the same closed
     // loop (first_check = iterations that one needed) - once after that many and then after every further iteration.
     // With compaction the first poll comes one iteration earlier: the last iterations of a solve belong to a few
@@ -254,7 +262,7 @@ struct OcpModule {
       tm.end();
       tm.begin(K_RICCATI);
       {
-        const int rcr = launch_riccati(a, c->riccati_variant, s);
+        const int rcr = launch_riccati(a, c->riccati_variant, s, &tm);
         if (rcr != 0) return rcr;
       }
       tm.end();

@@ -96,7 +96,8 @@ class OcpEngine:
               mu_min: Optional[float] = None, check_every: int = 4, stream=None, kernel_ms=None, kernel_count=None,
               riccati_variant: int = 2, warm_start: int = 0, mu_init_warm: float = 1e-4,
               eval_variant: int = 1, step_variant: int = 2, adaptive_poll: bool = True, compaction: bool = True,
-              regularization: int = 0, regularization_eps: float = 1e-4, kernel_ms_by_iter=None,
+              regularization: int = 0, regularization_eps: float = 1e-4, regularization_mu: float = 0., shift_warm_start: int = 0,
+              kernel_ms_by_iter=None,
               kernel_count_by_iter=None):
         """``x0``: CUDA tensor ``[B, nx]`` (scaled). Optional ``sp [B|1, N, nsp]``, ``tp``, ``uold``, ``ap`` tensors.
         Returns dict of device tensors: x [B,N+1,nx], u [B,N,nu], xc, lam, status, iters, stats."""
@@ -144,7 +145,8 @@ class OcpEngine:
             n_iterations_needed=C.pointer(needed),
             mu_init_warm=mu_init_warm, eval_variant=eval_variant, step_variant=step_variant,
             no_compaction=int(not compaction), regularization=int(regularization),
-            regularization_eps=float(regularization_eps),
+            regularization_eps=float(regularization_eps), regularization_mu=float(regularization_mu),
+            shift_warm_start=int(shift_warm_start),
             kernel_ms_by_iter=None if kernel_ms_by_iter is None else kernel_ms_by_iter.ctypes.data,
             kernel_count_by_iter=None if kernel_count_by_iter is None else kernel_count_by_iter.ctypes.data)
         _lib.check(lib.hb_ocp_solve(self._handle, C.byref(call)), 'hb_ocp_solve')

@@ -262,13 +262,13 @@ class LMPC(DynamicOptimization):
         B = x0t.shape[0]
         x0s = (x0t / c['xs_t']).contiguous()
         n, mx = c['n'], c['mx']
-        if c.get('B') != B:
+        if c.get('batch') != B:
             c['u'] = torch.empty(B, n, **f8)
             c['xp'] = torch.empty(B, mx, **f8)
             c['status'] = torch.zeros(B, dtype=torch.int32, device=dev)
             c['iters'] = torch.zeros(B, dtype=torch.int32, device=dev)
             c['work'] = torch.empty(lib.hb_lmpc_work_doubles(B, n, mx), **f8)
-            c['B'] = B
+            c['batch'] = B
         o = self._nlp_opts
         tol = float(o.get('ipopt.tol', o.get('tol', 1e-10)))
         rc = lib.hb_lmpc_solve(B, n, mx, nx, c['H_t'].data_ptr(), c['F_t'].data_ptr(), c['Gam_t'].data_ptr(),

@@ -202,7 +202,9 @@ class DynamicOptimization:
                     compaction=bool(int(o.get('b200.compaction', 1))),
                     adaptive_poll=bool(o.get('b200.adaptive_poll', True)),
                     regularization={'inertia': 0, 'mirror': 1}[str(o.get('b200.regularization', 'inertia'))],
-                    regularization_eps=float(o.get('b200.regularization_eps', 1e-4)))
+                    regularization_eps=float(o.get('b200.regularization_eps', 1e-4)),
+                    regularization_mu=float(o.get('b200.regularization_mu', 0.)),
+                    shift_warm_start=int(o.get('b200.shift_warm_start', 0)))
 
     def is_setup(self) -> bool:
         return self._nlp_setup_done

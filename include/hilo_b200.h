@@ -29,7 +29,7 @@ extern "C" {
 #endif
 
 /* ------------------------------------------------------------------------------------------------ library */
-#define HB_ABI_VERSION 3              /* bumps on every incompatible change of a struct or signature below */
+#define HB_ABI_VERSION 6              /* bumps on every incompatible change of a struct or signature below */
 int hb_version(void);                 /* HB_ABI_VERSION the library was built with; generated modules export the same
                                          number (hbm_abi_version) and hb_ocp_open / hb_est_open refuse a mismatch (-5) */
 const char* hb_last_error(void);      /* host string describing the last failure on this thread */
@@ -112,6 +112,13 @@ typedef struct hb_ocp_call {
                                1: additionally every reduced stage Hessian [Q S^T; S R] is convexified before the sweep
                                by mirroring its negative eigenvalues (|lambda|, floor regularization_eps)            */
   double regularization_eps;
+  double regularization_mu;         /* regularization == 1 acts only while the instance's barrier parameter is above this
+                                       value (far from the solution); below it the exact Hessian is kept and the inertia
+                                       correction alone guards the sweep (fast local convergence).  0: always           */
+  int shift_warm_start;             /* with warm_start = 1: the kept solution (primal variables, bound multipliers,
+                                       costates) is moved one stage towards the present before the solve (receding-
+                                       horizon shift; the last stage keeps its values).  0 (default): the previous
+                                       solution as it is, like the reference (mpc.py:725-726)                            */
   double* kernel_ms_by_iter;        /* host in/out [HB_OCP_TIMED_ITERS][HB_OCP_KERNELS] or NULL: kernel_ms split by the iteration
                                        index of the solve (last row = that index and beyond).  Iteration 0 of a solve is the
                                        one launch in which every instance of the batch is active: the roofline of a kernel
@@ -120,9 +127,9 @@ typedef struct hb_ocp_call {
 } hb_ocp_call;
 
 /* kernel indices of kernel_ms / kernel_count */
-#define HB_OCP_KERNELS 11
+#define HB_OCP_KERNELS 12
 #define HB_OCP_TIMED_ITERS 8
-#define HB_OCP_KERNEL_NAMES "init,eval,riccati,expand,prep,trial,decide,apply,commit,count,step"
+#define HB_OCP_KERNEL_NAMES "init,eval,riccati,expand,prep,trial,decide,apply,commit,count,step,ricfix"
 
 /* The Riccati sweep of one interior-point iteration alone (unit tests, profiling): the block-banded KKT system
  *   min sum_k 1/2 [dx;du]^T [Q S^T; S R] [dx;du] + [q;r]^T [dx;du] + terminal,  dx_{k+1} = A dx_k + B du_k + b,  dx_0 = 0

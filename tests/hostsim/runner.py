@@ -30,7 +30,7 @@ class OcpCall(C.Structure):
                 ('n_iterations_launched', _IP), ('n_kernel_launches', C.POINTER(C.c_longlong)),
                 ('kernel_ms', _DP), ('kernel_count', C.POINTER(C.c_longlong)), ('riccati_variant', C.c_int), ('warm_start', C.c_int), ('mu_init_warm', C.c_double), ('eval_variant', C.c_int), ('first_check', C.c_int),
                 ('n_iterations_needed', C.POINTER(C.c_int)), ('step_variant', C.c_int), ('no_compaction', C.c_int),
-                ('regularization', C.c_int), ('regularization_eps', C.c_double),
+                ('regularization', C.c_int), ('regularization_eps', C.c_double), ('regularization_mu', C.c_double), ('shift_warm_start', C.c_int),
                 ('kernel_ms_by_iter', C.c_void_p), ('kernel_count_by_iter', C.c_void_p)]
 
 
@@ -77,7 +77,8 @@ class HostOcp:
         self.lib.hbm_ocp_dims(C.byref(self.dims))
 
     def solve(self, x0, x, u, xc, xlb, xub, ulb, uub, dt, time0=0., sp=None, tp=None, uold=None, ap=None, tol=1e-8,
-              max_iter=200, n_alpha=8, mu_init=.1, riccati_variant=0, regularization=0, regularization_eps=1e-4):
+              max_iter=200, n_alpha=8, mu_init=.1, riccati_variant=0, regularization=0, regularization_eps=1e-4, regularization_mu=0., warm_start=0, mu_init_warm=1e-4,
+              shift_warm_start=0, work=None):
         d = self.dims
         B = x.shape[0]
         f8 = lambda a, shape: np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(shape))
@@ -104,7 +105,8 @@ class HostOcp:
         iters = np.zeros(B + 1, dtype=np.int32)
         stats = np.zeros((B, d.n_state))
         nwork = self.lib.hbm_ocp_work_doubles(B, n_alpha)
-        work = np.zeros(nwork)
+        if work is None:
+            work = np.zeros(nwork)   # pass the `work` of a previous solve back in for a warm start with multipliers
         launched = C.c_int(0)
         b = [f8(v, (-1,)) for v in (xlb, xub, ulb, uub)]
         call = OcpCall(B=B, n_alpha=n_alpha, max_iter=max_iter, check_every=1, tol=tol, acc_tol=1e-6, mu_init=mu_init,
@@ -114,7 +116,9 @@ class HostOcp:
                        lam=_dp(lam), status=status.ctypes.data_as(_IP), iters=iters.ctypes.data_as(_IP),
                        stats=_dp(stats), work=_dp(work), work_doubles=nwork, stream=None,
                        n_iterations_launched=C.pointer(launched), riccati_variant=riccati_variant,
-                       regularization=regularization, regularization_eps=regularization_eps)
+                       regularization=regularization, regularization_eps=regularization_eps,
+                       regularization_mu=regularization_mu, warm_start=warm_start, mu_init_warm=mu_init_warm,
+                       shift_warm_start=shift_warm_start)
         rc = self.lib.hbm_ocp_solve(C.byref(call))
         if rc != 0:
             raise RuntimeError(f"hbm_ocp_solve returned {rc}")

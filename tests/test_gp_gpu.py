@@ -85,6 +85,41 @@ def test_gp_inside_nmpc_matches_oracle(cuda_device):
     assert rel < 0.02 * (u_true.abs() / torch.tensor(us, device=cuda_device)).max().item() + 0.02
 
 
+def test_config3_gp_with_512_training_points_as_device_function(cuda_device):
+    """BASELINE config 3 at its stated GP size: 512 training points.  The posterior mean enters the model as ONE call
+    node; the generated node kernels evaluate it (value, gradient, Hessian) with a loop over the training table in
+    constant memory (csrc/gp_device.cuh) instead of 512 unrolled terms.  The device function must equal hb_gp_predict on
+    the same points, and the batched NMPC solve must equal the oracle's solve of the same flat NLP."""
+    import torch
+    from hilo_mpc_b200 import symbolic as sx
+    from hilo_mpc_b200.examples import cstr_gp_nmpc, cstr_initial_states, cstr_side_reaction_gp
+    from hilo_mpc_b200.library import cstr_side_reaction
+    from oracle.nmpc import FlatNlp
+    gp = cstr_side_reaction_gp(n_train=512)
+    xq = sx.sym('q', 2)
+    mean_sym, var_sym = gp.predict(xq)
+    assert var_sym is None and any(n.op.startswith('gp:') for n in sx.topo_sort(list(mean_sym)))
+    rng = np.random.default_rng(0)
+    Xq = np.vstack([rng.uniform(.8, 1.8, 100), rng.uniform(115., 135., 100)])
+    F = sx.Function('m', [('q', xq)], [('m', mean_sym)])
+    mean_dev, _ = gp.predict(Xq, mean_only=True)
+    np.testing.assert_allclose(np.asarray(F(Xq)).reshape(-1), mean_dev.reshape(-1), rtol=1e-9, atol=1e-9)
+    truth = cstr_side_reaction(Xq[0], Xq[1])
+    assert np.abs(mean_dev[0] - truth).max() < 0.02 * np.abs(truth).max()
+    nmpc = cstr_gp_nmpc(gp, N=10)
+    x0 = cstr_initial_states(32, seed=3)
+    nmpc.optimize(torch.tensor(x0, device=cuda_device))
+    assert (nmpc.solver_status_code == 1).all()
+    x_pred, u_pred, _ = nmpc.return_prediction()
+    xs, us = np.asarray(nmpc._xs_full), np.asarray(nmpc._us_full)
+    nlp = FlatNlp(nmpc.spec, exact_hessian=True)
+    for b in (0, 9, 31):
+        res, xo, uo = nlp.solve(x0[b] / xs, dt=nmpc.sampling_interval, finish_barrier=True)
+        assert res.status == 1
+        np.testing.assert_allclose(x_pred[b].cpu().numpy() / xs, xo.T, atol=2e-6)
+        np.testing.assert_allclose(u_pred[b].cpu().numpy() / us, uo.T, atol=2e-5)
+
+
 def test_gp_fit_model_reproduces_gpml_golden(cuda_device):
     """Hyper-parameter training: tests/test_GPs.py:833-849 - 20 points from the reference's LCG
     generator, default SE kernel and start values, fitted [noise_variance, length_scale, signal_variance] must equal the

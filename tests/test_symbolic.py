@@ -88,3 +88,45 @@ def test_c_source_compiles_and_matches():
         fv, fx = F(xv, uv)
         np.testing.assert_allclose(fo, fv, rtol=1e-14)
         np.testing.assert_allclose(jo.reshape(4, 4), fx, rtol=1e-13)
+
+
+def test_gp_call_node_derivatives_and_generated_c_code(tmp_path):
+    """A GP mean with many training points enters expressions as ONE call node (symbolic.gp_mean_node): derivatives map
+    mean -> gradient -> Hessian outputs of the same table loop.  Checks them against complex-step differentiation and the
+    emitted C (hb::gp_se_eval, csrc/gp_device.cuh, compiled for the host) against the NumPy evaluation."""
+    import ctypes as C
+    import os
+    import subprocess
+    rng = np.random.default_rng(0)
+    n, d = 300, 2
+    Xs, c, il = rng.normal(size=(n, d)), rng.normal(size=n), np.array([1 / .7, 1 / 15.])
+    gid = sx.register_gp_table(Xs, c, il)
+    x = sx.sym('x', 3)
+    m = sx.gp_mean_node(gid, [x[0] * 2. + x[2], x[1] + x[0]])
+    e = m * x[0] + sx.sin(m) + x[2] ** 2
+    g, H = sx.gradient(e, x), sx.hessian(e, x)
+    F = sx.Function('f', [('x', x)], [('e', [e]), ('g', g), ('H', H)])
+    pt = np.array([.3, -.2, .1])
+    ev, gv, Hv = F(pt)
+    gc = np.array([F(pt + 1e-30j * np.eye(3)[j])[0].imag / 1e-30 for j in range(3)]).reshape(-1)
+    Hc = np.array([F(pt + 1e-30j * np.eye(3)[j])[1].imag / 1e-30 for j in range(3)])
+    np.testing.assert_allclose(gv, gc, rtol=1e-11, atol=1e-12)
+    np.testing.assert_allclose(Hv, Hc, rtol=1e-10, atol=1e-11)
+    # one table, found from the expression; a second mean node at another query gets its own call
+    assert sx.gp_tables_used(np.array([e], dtype=object)) == [gid]
+    csrc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'hilo_mpc_b200', 'csrc')
+    src = '\n'.join(['#define HB_HOSTSIM', '#include "ocp_kernels.cuh"', sx.gp_tables_c_source([gid]),
+                     'extern "C" {', F.c_source(qualifiers=''), '}'])
+    assert src.count('gp_se_eval<2, 2>') == 1          # value, gradient and Hessian share ONE loop over the table
+    cu = tmp_path / 'gp_fun.cpp'
+    cu.write_text(src)
+    so = tmp_path / 'gp_fun.so'
+    subprocess.run(['g++', '-O1', '-std=c++17', '-shared', '-fPIC', '-DHB_HOSTSIM', '-I', csrc, str(cu), '-o', str(so)],
+                   check=True)
+    lib = C.CDLL(str(so))
+    out_e, out_g, out_H = np.zeros(1), np.zeros(3), np.zeros(9)
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    lib.f(dp(pt), dp(out_e), dp(out_g), dp(out_H))
+    np.testing.assert_allclose(out_e[0], ev, rtol=1e-13)
+    np.testing.assert_allclose(out_g, gv, rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(out_H.reshape(3, 3), Hv, rtol=1e-11, atol=1e-12)

@@ -1,0 +1,20 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 300 python -m pytest tests/test_lmpc_condensed.py -m gpu -q --timeout 200 -x 2>&1 | grep -E "^E |Error|passed|failed" | head -20
+i=0
+for v in "--config 5 --batch 1024 --opt b200.shift_warm_start=1" "--config 5 --batch 1024 --opt b200.shift_warm_start=1 --warm-mu 1e-8" "--config 4 --opt b200.shift_warm_start=1" "--config 4" "--config 2 --opt b200.shift_warm_start=1"; do
+  timeout 600 python bench.py --steps 20 --no-cpu-baseline --no-default-options --no-gp $v > gpurun_out/bench_s$i.json 2> gpurun_out/bench_s$i.err
+  echo "variant $i [$v] rc=$?"
+  i=$((i+1))
+done
+python - <<'PY'
+import json,glob
+for f in sorted(glob.glob('gpurun_out/bench_s?.json')):
+    try:
+        d=json.loads(open(f).read().strip().splitlines()[-1])
+        c=d['config']
+        print(f, 'value %.0f'%d['value'], 'e2e %.0f'%d['e2e']['value'], 'ms/step %.2f'%d['ms_per_step'], 'it %.2f max %d'%(c['ipm_iterations_mean'], c['ipm_iterations_max']), 'launched %.1f'%c['ipm_iterations_launched_per_step_mean'],
+              'opt %.3f acc %.3f'%(c['status_optimal_frac'], c['status_acceptable_frac']), {k:round(v['avg_us'],1) for k,v in d.get('kernels',{}).items()})
+    except Exception as e:
+        print(f,'ERR',e, open(f.replace('.json','.err')).read()[-400:])
+PY
