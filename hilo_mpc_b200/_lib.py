@@ -85,7 +85,7 @@ def load() -> C.CDLL:
     return lib
 
 
-ABI_VERSION = 6   # HB_ABI_VERSION of include/hilo_b200.h this binding was written against
+ABI_VERSION = 7   # HB_ABI_VERSION of include/hilo_b200.h this binding was written against
 
 
 def _register_optional(lib: C.CDLL) -> None:

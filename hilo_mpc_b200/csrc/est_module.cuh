@@ -1,6 +1,7 @@
 // C entry points of one generated estimator / simulation module (see est_kernels.cuh).
 #pragma once
 #include "est_kernels.cuh"
+#include "est_lanes.cuh"
 #include "../../include/hilo_b200.h"
 
 namespace hb {
@@ -54,6 +55,14 @@ struct EstModule {
   static int ukf(const hb_est_call* c) {
     EstArgs a; if (!fill(c, a)) return -1;
     if (a.status == nullptr || a.P == nullptr || a.X == nullptr) return -4;
+#if HB_DEVICE_BUILD
+    if constexpr (UkfLanes<E>::SUPPORTED) {   // one lane per sigma point (est_lanes.cuh); variant 0 keeps one thread per filter
+      if (c->variant != 0) {
+        cudaError_t e = launch_ukf_lanes<E>(a, (cudaStream_t)c->stream);
+        return e == cudaSuccess ? finish() : (int)e;
+      }
+    }
+#endif
     launch_1d<UkfStep<E>>(a, a.B, (cudaStream_t)c->stream); return finish();
   }
   static int pf(const hb_est_call* c) {

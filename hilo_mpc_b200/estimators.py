@@ -268,6 +268,7 @@ class UnscentedKalmanFilter(_KalmanFilter):
         self._alpha = self._beta = self._kappa = None
         self.alpha, self.beta, self.kappa = alpha, beta, kappa
         self._X = None
+        self.kernel_variant = 1   # 1: one lane per sigma point (csrc/est_lanes.cuh), 0: one thread per filter
 
     @property
     def alpha(self):
@@ -301,7 +302,7 @@ class UnscentedKalmanFilter(_KalmanFilter):
         ns = 2 * self._n_x + 1
         if self._X is None or self._X.shape[0] != B:
             self._X = torch.zeros(B, ns, self._n_x, dtype=torch.float64, device=eng.device)
-        return dict(X=self._X, alpha=self._alpha, beta=self._beta, kappa=self._kappa)
+        return dict(X=self._X, alpha=self._alpha, beta=self._beta, kappa=self._kappa, variant=self.kernel_variant)
 
     def _result_matrix(self):  # kf.py:549-553: [x_pred | P_pred | X]
         return np.column_stack([self._x[0].cpu().numpy(), self._P[0].cpu().numpy(), self._X[0].cpu().numpy().T])

@@ -270,7 +270,7 @@ class LMPC(DynamicOptimization):
             c['work'] = torch.empty(lib.hb_lmpc_work_doubles(B, n, mx), **f8)
             c['batch'] = B
         o = self._nlp_opts
-        tol = float(o.get('ipopt.tol', o.get('tol', 1e-10)))
+        tol = float(o.get('ipopt.tol', o.get('tol', 1e-12)))   # relative KKT tolerance of the dense-QP kernel
         rc = lib.hb_lmpc_solve(B, n, mx, nx, c['H_t'].data_ptr(), c['F_t'].data_ptr(), c['Gam_t'].data_ptr(),
                                c['Phi_t'].data_ptr(), c['ulb_t'].data_ptr(), c['uub_t'].data_ptr(), c['xlb_t'].data_ptr(),
                                c['xub_t'].data_ptr(), x0s.data_ptr(), c['u'].data_ptr(), c['xp'].data_ptr(),

@@ -513,14 +513,14 @@ class NMPC(DynamicOptimization):
     def optimize(self, x0, cp=None, tvp=None, v0=None, runs=0, fix_x0=True, **kwargs):
         if not self._nlp_setup_done:
             raise RuntimeError("The NMPC is not set up. Run NMPC.setup() before optimizing.")
-        if runs:
-            raise NotImplementedError("Random multi-start (runs > 0) is not supported by the B200 engine; batch the "
-                                      "initial guesses instead.")
-        if not fix_x0:
-            raise NotImplementedError("fix_x0=False is not supported by the B200 engine yet")
+        if not isinstance(runs, (int, np.integer)) or runs < 0:
+            raise ValueError("The number of multi-start runs must be a non-negative integer")
+        if not fix_x0 and ('x0_lb' in kwargs or 'x0_ub' in kwargs):
+            raise NotImplementedError("fix_x0=False with bounds on the initial state other than the state bounds "
+                                      "(x0_lb / x0_ub) is not supported by the B200 engine yet")
         from . import _lib
         torch = _lib.require_cuda()
-        eng = self._engine
+        eng = self._engine if fix_x0 else self._free_x0_engine()
         eng._open()
         dev = eng._device
         s = self._spec
@@ -568,7 +568,12 @@ class NMPC(DynamicOptimization):
             eng._alloc(B, self._solver_numbers()['n_alpha'])
             eng.reset_guess(v0)
         num = self._solver_numbers()
-        out = eng.solve(x0s, dt=self._sampling_interval, time0=self._time, sp=sp, tp=tp, uold=uold, **num)
+        if runs or not fix_x0:
+            eng._alloc(B, num['n_alpha'])
+        if not fix_x0:   # x_0 is a decision variable inside the state bounds; the measured state is only its initial guess
+            eng._t['x'][:, 0, :] = x0s
+        solve = lambda: eng.solve(x0s, dt=self._sampling_interval, time0=self._time, sp=sp, tp=tp, uold=uold, **num)
+        out = solve() if not runs else self._multi_start(eng, solve, int(runs), float(kwargs.get('pert_factor', .1)), torch)
         self._last = out
         if s.nuold:
             self._uold = out['u'][:, 0, self._du_ind].clone()  # next call's u_old (mpc.py:488-493)
@@ -588,6 +593,64 @@ class NMPC(DynamicOptimization):
             return u_np
         self._solver_status_code = out['status']
         return u0 if is_tensor else u0.detach().cpu().numpy()
+
+    def _free_x0_engine(self):
+        """Second generated module of the same problem with a free initial state (``optimize(..., fix_x0=False)``,
+        mpc.py:803-807), built on first use."""
+        if getattr(self, '_engine_free', None) is None:
+            import copy
+            from .engine import OcpEngine
+            spec = copy.copy(self._spec)
+            spec.fixed_x0 = False
+            spec.name = self._spec.name + '_freex0'
+            self._engine_free = OcpEngine(spec, build=getattr(self, '_build_module', True))
+        return self._engine_free
+
+    def _multi_start(self, eng, solve, runs, pert_factor, torch):
+        """``runs`` solves from randomly perturbed starting points, the best converged one per instance is kept
+        (mpc.py:728-740): first from the current guess ``v0``, then from ``clip(v0 + v0 (1 - 2 rand) pert_factor, lb, ub)``
+        with ``rand`` drawn from the legacy NumPy RNG over the flat decision vector ``[x_0..x_N | u | X]`` of each instance."""
+        t = eng._t
+        B = t['x'].shape[0]
+        keys = ('x', 'u', 'xc') if eng.dims.nc else ('x', 'u')
+        v0 = {k: t[k].clone() for k in keys}
+        s = self._spec
+        f8 = dict(dtype=torch.float64, device=t['x'].device)
+        from .engine import _finite
+        lb = {'x': torch.tensor(_finite(s.x_lb), **f8), 'u': torch.tensor(_finite(s.u_lb), **f8)}
+        ub = {'x': torch.tensor(_finite(s.x_ub), **f8), 'u': torch.tensor(_finite(s.u_ub), **f8)}
+        if 'xc' in keys:
+            lb['xc'], ub['xc'] = lb['x'].repeat(s.degree), ub['x'].repeat(s.degree)
+        best, best_f = None, torch.full((B,), float('inf'), **f8)
+        sizes = [int(np.prod(v0[k].shape[1:])) for k in keys]
+        for r in range(runs):
+            eng._solved_once = False          # every run is a fresh start of the solver from the given point
+            out = solve()
+            f = out['stats'][:, 13]           # ST_OBJ in csrc/ocp_kernels.cuh
+            ok = ((out['status'] == 1) | (out['status'] == 2)) & (f < best_f)
+            if best is None:
+                best = {k: out[k].clone() for k in ('x', 'u', 'lam', 'status', 'iters', 'stats')}
+                if out.get('xc') is not None:
+                    best['xc'] = out['xc'].clone()
+                best_f = torch.where(ok, f, best_f)
+            elif ok.any():
+                for k, v in best.items():
+                    m = ok.reshape((-1,) + (1,) * (v.dim() - 1))
+                    best[k] = torch.where(m, out[k], v)
+                best_f = torch.where(ok, f, best_f)
+            if r + 1 < runs:
+                rnd = np.stack([np.random.rand(sum(sizes)) for _ in range(B)])
+                pos = 0
+                for k, n in zip(keys, sizes):
+                    fac = torch.tensor(1. - 2. * rnd[:, pos:pos + n], **f8).reshape(v0[k].shape)
+                    pos += n
+                    t[k].copy_(torch.minimum(torch.maximum(v0[k] + v0[k] * fac * pert_factor, lb[k]), ub[k]))
+        for k in keys:                        # the kept solution is the next warm start (mpc.py:737-738)
+            t[k].copy_(best[k])
+        t['lam'].copy_(best['lam'])
+        t['status'].copy_(best['status'])
+        best.setdefault('xc', None)
+        return best
 
     def return_prediction(self):
         """``(x_pred [nx, N+1], u_pred [nu, N], None)`` for a single instance, batched tensors otherwise

@@ -29,7 +29,7 @@ extern "C" {
 #endif
 
 /* ------------------------------------------------------------------------------------------------ library */
-#define HB_ABI_VERSION 6              /* bumps on every incompatible change of a struct or signature below */
+#define HB_ABI_VERSION 7              /* bumps on every incompatible change of a struct or signature below */
 int hb_version(void);                 /* HB_ABI_VERSION the library was built with; generated modules export the same
                                          number (hbm_abi_version) and hb_ocp_open / hb_est_open refuse a mismatch (-5) */
 const char* hb_last_error(void);      /* host string describing the last failure on this thread */
@@ -195,6 +195,8 @@ typedef struct hb_est_call {
   size_t work_doubles;
   int* status;               /* out [B]: 0 ok, -1 numerical failure                                               */
   void* stream;
+  int variant;               /* UKF: 1 (default of the Python shell) one lane per sigma point, reductions by warp shuffles;
+                                0 one thread per filter                                                           */
 } hb_est_call;
 
 typedef struct hb_est* hb_est_t;

@@ -302,3 +302,41 @@ def test_sweep_entry_point_on_the_device(cuda_device):
             dx, du = riccati_reference(A[7], Bm[7], b[7], Q[7], S[7], R[7], q[7], r[7], QN[7], qN[7])
             np.testing.assert_allclose(out['dx'][7].cpu().numpy(), dx, atol=1e-10)
             np.testing.assert_allclose(out['du'][7].cpu().numpy(), du, atol=1e-10)
+
+
+def test_multi_start_and_free_initial_state(cuda_device):
+    """``optimize(x0, runs=r)`` (mpc.py:728-740): r solves from randomly perturbed starting points (legacy NumPy RNG), the
+    best converged one is kept - on the CSTR every start reaches the same minimiser.  ``fix_x0=False`` (mpc.py:803-807):
+    x_0 becomes a decision variable inside the state bounds, compared with the oracle on the same flat NLP."""
+    import copy
+    import torch
+    from hilo_mpc_b200.examples import cstr_initial_states, cstr_nmpc
+    from oracle.nmpc import FlatNlp
+    x0 = cstr_initial_states(6, seed=11)
+    x0t = torch.tensor(x0, device=cuda_device)
+    base = cstr_nmpc(N=10)
+    u_ref = base.optimize(x0t).clone()
+    nmpc = cstr_nmpc(N=10)
+    np.random.seed(5)
+    u_ms = nmpc.optimize(x0t, runs=3)
+    assert (nmpc.solver_status_code == 1).all()
+    assert np.random.rand() != np.random.RandomState(5).rand()      # the legacy global RNG was consumed
+    assert (u_ms - u_ref).abs().max().item() < 1e-5 * u_ref.abs().max().item()
+    # free initial state
+    free = cstr_nmpc(N=10)
+    u_free = free.optimize(x0t, fix_x0=False)
+    assert (free.solver_status_code == 1).all()
+    out = free._last
+    assert (out['stats'][:, 13] <= base._last['stats'][:, 13] + 1e-9).all()   # a relaxation of the pinned problem
+    spec = copy.copy(free.spec)
+    spec.fixed_x0 = False
+    nlp = FlatNlp(spec, exact_hessian=True)
+    xs, us = np.asarray(free._xs_full), np.asarray(free._us_full)
+    for b in (0, 5):
+        lb, ub, v0 = nlp.bounds_and_guess(None)
+        v0[nlp.x_ind[0]] = x0[b] / xs
+        res, xo, uo = nlp.solve(None, v0=v0, dt=free.sampling_interval, finish_barrier=True)
+        assert res.status == 1
+        np.testing.assert_allclose(out['x'][b].cpu().numpy(), xo.T, atol=2e-6)
+        np.testing.assert_allclose(out['u'][b].cpu().numpy(), uo.T, atol=2e-5)
+    assert u_free.shape == (6, 2)
