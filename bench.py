@@ -494,14 +494,25 @@ class NmpcLoop:
         self.nmpc._last = None
         self.nmpc._time = 0.
         self.x_cur = self.x0
+        self.num = self.nmpc._solver_numbers()
+        nth = self.nmpc.spec.nx - self.nx0
+        self.theta = self.torch.zeros(self.B, max(nth, 0), dtype=self.torch.float64, device=self.dev)
 
     def step_device(self, k, timing=False):
+        """Device-resident step: the engine call of NMPC.optimize (hb_ocp_solve through OcpEngine.solve) on tensors that
+        never leave the device; the path variable of config 5 is carried like NMPC.optimize does (mpc.py:1173-1204)."""
+        torch, nmpc = self.torch, self.nmpc
+        xs, _ = nmpc._scaling_tensors(torch, self.dev)
+        x = self.x_cur
+        if nmpc.spec.nx > self.nx0:
+            x = torch.cat([x, self.theta], dim=1)
         self._timing = timing
-        self.nmpc.optimize(self.x_cur)                      # device tensor in, device tensor out
+        out = self.eng.solve(x / xs, dt=nmpc.sampling_interval, time0=0., **self.num)
         self._timing = False
-        out = self.nmpc._last
-        xs, _ = self.nmpc._scaling_tensors(self.torch, self.dev)
+        nmpc._last = out
         self.x_cur = out['x'][:, 1, :self.nx0] * xs[:self.nx0] + self.noise[k]
+        if nmpc.spec.nx > self.nx0:
+            self.theta = out['x'][:, 1, self.nx0:] * xs[self.nx0:]
         return out
 
     def start_e2e(self):

@@ -44,6 +44,9 @@ class ANN:
         self._bias: Optional[List[np.ndarray]] = None
         self._in_mean = self._in_scale = self._out_mean = self._out_scale = None
 
+    symbolic_mode = 'call'        # 'call': single-hidden-layer networks as call nodes; 'unroll': plain expression graph
+    call_node_min_hidden = 16     # smaller networks are cheaper unrolled
+
     def add_layers(self, *layers):
         for layer in layers:
             self._layers.extend(layer if isinstance(layer, (list, tuple)) else [layer])
@@ -96,6 +99,20 @@ class ANN:
             raise RuntimeError("The network has no weights yet: call set_weights() or ANN.from_torch()")
         symbolic = sx.is_symbolic(X)
         h = sx.as_vector(X) if symbolic else np.atleast_2d(np.asarray(X, dtype=float))
+        if symbolic and self.symbolic_mode == 'call' and len(self._layers) == 1 and \
+                self._layers[0].activation.lower() in ('tanh', 'sigmoid', 'logistic') and \
+                self._weights[0].shape[0] >= self.call_node_min_hidden:
+            # one hidden layer: the network enters the expression graph as call nodes (a loop over the hidden units in
+            # the generated device code, csrc/gp_device.cuh::mlp1_eval) with the z-score scalings folded into the weights
+            W1, b1, W2, b2 = self._weights[0], self._bias[0], self._weights[1], self._bias[1]
+            if self._in_mean is not None:
+                b1 = b1 - W1 @ (self._in_mean / self._in_scale)
+                W1 = W1 / self._in_scale[None, :]
+            if self._out_mean is not None:
+                W2 = W2 * self._out_scale[:, None]
+                b2 = b2 * self._out_scale + self._out_mean
+            mid = sx.register_mlp_table(W1, b1, W2, b2, self._layers[0].activation.lower())
+            return sx.mlp_output_nodes(mid, h)
         if symbolic:
             if self._in_mean is not None:
                 h = (h - self._in_mean) / self._in_scale

@@ -63,4 +63,66 @@ HB_HD void gp_se_eval(const double* __restrict__ tab, int n, const double* __res
       for (int l = 0; l <= j; ++l) out[1 + D + j * (j + 1) / 2 + l] = H[j * (j + 1) / 2 + l] * inv_ls[j] * inv_ls[l];
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// One-hidden-layer perceptron  y = W2 act(W1 z + b1) + b2  (the graph of hilo_mpc/util/machine_learning.py:521-578 with the
+// z-score scaling of inputs and outputs folded into the weights) as a device function: value, Jacobian and the second
+// derivatives of every output in ONE loop over the hidden units.  The fully unrolled expression of a 1 x 32 network and
+// its derivatives is ~20 000 SASS instructions per node kernel (333 KB of straight-line code: 37 % of the warp samples
+// stalled on instruction fetch, profiles/ncu_evq_c5_r2_summary.csv); the loop is a few hundred.
+// tab = [NH][NZ + 1] rows (W1[j][:], b1[j]) | [NO][NH] W2 | [NO] b2, in constant memory of the generated module.
+// out = [y (NO) | J row-major (NO x NZ) | for every output the lower triangle of its Hessian (NO x NZ (NZ + 1) / 2)].
+// ACT: 0 tanh, 1 logistic sigmoid.
+template <int NZ, int NH, int NO, int ORDER, int ACT>
+HB_HD void mlp1_eval(const double* __restrict__ tab, const double* z, double* out) {
+  constexpr int NT = NZ * (NZ + 1) / 2;
+  constexpr int NOUT = NO + (ORDER >= 1 ? NO * NZ : 0) + (ORDER >= 2 ? NO * NT : 0);
+  const double* W2 = tab + NH * (NZ + 1);
+  const double* b2 = W2 + NO * NH;
+  for (int e = 0; e < NOUT; ++e) out[e] = 0.0;
+  for (int o = 0; o < NO; ++o) out[o] = b2[o];
+  for (int j = 0; j < NH; ++j) {
+    const double* w1 = tab + j * (NZ + 1);
+    double act = w1[NZ];
+#if HB_DEVICE_BUILD
+#pragma unroll
+#endif
+    for (int i = 0; i < NZ; ++i) act += w1[i] * z[i];
+    double h, d1, d2;
+    if (ACT == 0) { h = tanh(act); d1 = 1.0 - h * h; d2 = -2.0 * h * d1; }
+    else { h = 1.0 / (1.0 + exp(-act)); d1 = h * (1.0 - h); d2 = d1 * (1.0 - 2.0 * h); }
+    double ww[ORDER >= 2 ? NT : 1];
+    if (ORDER >= 2) {
+#if HB_DEVICE_BUILD
+#pragma unroll
+#endif
+      for (int i = 0; i < NZ; ++i)
+#if HB_DEVICE_BUILD
+#pragma unroll
+#endif
+        for (int l = 0; l <= i; ++l) ww[i * (i + 1) / 2 + l] = w1[i] * w1[l];
+    }
+#if HB_DEVICE_BUILD
+#pragma unroll
+#endif
+    for (int o = 0; o < NO; ++o) {
+      const double w = W2[o * NH + j];
+      out[o] += w * h;
+      if (ORDER >= 1) {
+        const double wd = w * d1;
+#if HB_DEVICE_BUILD
+#pragma unroll
+#endif
+        for (int i = 0; i < NZ; ++i) out[NO + o * NZ + i] += wd * w1[i];
+      }
+      if (ORDER >= 2) {
+        const double wd2 = w * d2;
+#if HB_DEVICE_BUILD
+#pragma unroll
+#endif
+        for (int e = 0; e < NT; ++e) out[NO + NO * NZ + o * NT + e] += wd2 * ww[e];
+      }
+    }
+  }
+}
+
 }  // namespace hb

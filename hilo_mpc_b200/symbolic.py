@@ -362,6 +362,65 @@ def gp_mean_node(gid: str, xq) -> 'Expr':
     return Expr(f'gp:{gid}:m', args)
 
 
+MLP_TABLES: Dict[str, dict] = {}
+
+
+def register_mlp_table(W1, b1, W2, b2, activation: str) -> str:
+    """One-hidden-layer perceptron ``y = W2 act(W1 z + b1) + b2`` (scalings already folded in); ``activation`` 'tanh' or
+    'sigmoid'.  Returns the table id."""
+    import hashlib
+    W1, b1, W2, b2 = (np.ascontiguousarray(v, dtype=float) for v in (W1, b1, W2, b2))
+    act = {'tanh': 0, 'sigmoid': 1, 'logistic': 1}[activation]
+    mid = hashlib.sha256(W1.tobytes() + b1.tobytes() + W2.tobytes() + b2.tobytes() + bytes([act])).hexdigest()[:10]
+    MLP_TABLES[mid] = dict(W1=W1, b1=b1.reshape(-1), W2=W2, b2=b2.reshape(-1), act=act, nz=W1.shape[1], nh=W1.shape[0],
+                           no=W2.shape[0])
+    return mid
+
+
+def mlp_output_nodes(mid: str, z) -> np.ndarray:
+    args = tuple(Expr.wrap(v) for v in as_vector(z))
+    t = MLP_TABLES[mid]
+    if len(args) != t['nz']:
+        raise ValueError("mlp_output_nodes: dimension of the input does not match the table")
+    return np.array([Expr(f'mlp:{mid}:y{o}', args) for o in range(t['no'])], dtype=object)
+
+
+def _mlp_out_index(what: str, t: dict) -> int:
+    nz, no = t['nz'], t['no']
+    nt = nz * (nz + 1) // 2
+    if what[0] == 'y':
+        return int(what[1:])
+    if what[0] == 'j':
+        o, i = (int(v) for v in what[1:].split('_'))
+        return no + o * nz + i
+    o, i, l = (int(v) for v in what[1:].split('_'))
+    return no + no * nz + o * nt + i * (i + 1) // 2 + l
+
+
+def _mlp_numpy(mid: str, order: int, *z):
+    """Numeric evaluation of one MLP group: list of outputs in the order of ``hb::mlp1_eval``."""
+    t = MLP_TABLES[mid]
+    nz, nh, no = t['nz'], t['nh'], t['no']
+    zz = [np.asarray(v) for v in z]
+    shape = np.broadcast(*zz).shape
+    a = sum(zz[i][..., None] * t['W1'][:, i] for i in range(nz)) + t['b1']          # (..., nh)
+    if t['act'] == 0:
+        h = np.tanh(a); d1 = 1. - h * h; d2 = -2. * h * d1
+    else:
+        h = 1. / (1. + np.exp(-a)); d1 = h * (1. - h); d2 = d1 * (1. - 2. * h)
+    out = [(h * t['W2'][o]).sum(axis=-1) + t['b2'][o] for o in range(no)]
+    if order >= 1:
+        for o in range(no):
+            for i in range(nz):
+                out.append((d1 * t['W2'][o] * t['W1'][:, i]).sum(axis=-1))
+    if order >= 2:
+        for o in range(no):
+            for i in range(nz):
+                for l in range(i + 1):
+                    out.append((d2 * t['W2'][o] * t['W1'][:, i] * t['W1'][:, l]).sum(axis=-1))
+    return [np.broadcast_to(v, shape) for v in out]
+
+
 def _gp_parts(op: str):
     _, gid, what = op.split(':')
     return gid, what
@@ -508,7 +567,7 @@ def _rebuild(op: str, args: tuple) -> Expr:
         return _pow(*args)
     if op == 'neg':
         return _neg(*args)
-    if op in ('atan2', 'fmin', 'fmax') or op.startswith('gp:'):
+    if op in ('atan2', 'fmin', 'fmax') or op.startswith('gp:') or op.startswith('mlp:'):
         return Expr(op, args)
     return _unary(op, args[0])
 
@@ -571,6 +630,22 @@ def _deriv_node(node: Expr, d: List[Optional[Expr]]) -> Optional[Expr]:
         return t
     if op in ('fmin', 'fmax'):
         raise NotImplementedError("fmin/fmax are not differentiable in this layer")
+    if op.startswith('mlp:'):
+        mid, what = _gp_parts(op)
+        t = None
+        for i, di in enumerate(d):
+            if di is None:
+                continue
+            if what[0] == 'y':
+                part = Expr(f'mlp:{mid}:j{what[1:]}_{i}', a)
+            elif what[0] == 'j':
+                o, i0 = (int(v) for v in what[1:].split('_'))
+                part = Expr(f'mlp:{mid}:h{o}_{max(i0, i)}_{min(i0, i)}', a)
+            else:
+                raise NotImplementedError("Third derivatives of an MLP call node are not available")
+            term = _mul(part, di)
+            t = term if t is None else _add(t, term)
+        return t
     if op.startswith('gp:'):
         gid, what = _gp_parts(op)
         t = None
@@ -721,6 +796,27 @@ def _emit(outputs: List[Expr], inputs: Dict[int, str], lang: str, tmp: str = 't'
             continue
         a = [names[x.id] for x in node.args]
         op = node.op
+        if op.startswith('mlp:'):
+            mid, what = _gp_parts(op)
+            key = ('mlp', mid) + tuple(x.id for x in node.args)
+            t = MLP_TABLES[mid]
+            if key not in gp_groups:
+                order = 0
+                for other in order_nodes:
+                    if other.op.startswith(f'mlp:{mid}:') and tuple(x.id for x in other.args) == key[2:]:
+                        w2 = _gp_parts(other.op)[1]
+                        order = max(order, {'y': 0, 'j': 1, 'h': 2}[w2[0]])
+                nz, nh, no = t['nz'], t['nh'], t['no']
+                var = f'{tmp}mlp{len(gp_groups)}'
+                if lang == 'c':
+                    nout = no + (no * nz if order >= 1 else 0) + (no * nz * (nz + 1) // 2 if order >= 2 else 0)
+                    lines.append(f'double {var}[{nout}]; {{ const double {var}z[{nz}] = {{{", ".join(a)}}}; '
+                                 f'hb::mlp1_eval<{nz}, {nh}, {no}, {order}, {t["act"]}>(hb_mlp_tab_{mid}, {var}z, {var}); }}')
+                else:
+                    lines.append(f'{var} = _mlp_numpy({mid!r}, {order}, {", ".join(a)})')
+                gp_groups[key] = var
+            names[node.id] = f'{gp_groups[key]}[{_mlp_out_index(what, t)}]'
+            continue
         if op.startswith('gp:'):
             gid, what = _gp_parts(op)
             key = (gid,) + tuple(x.id for x in node.args)
@@ -808,7 +904,7 @@ class Function:
             rets.append('[' + ', '.join(outs[pos:pos + len(vec)]) + ']')
             pos += len(vec)
         src.append('    return (' + ', '.join(rets) + ',)')
-        ns = {'np': np, '_gp_numpy': _gp_numpy}
+        ns = {'np': np, '_gp_numpy': _gp_numpy, '_mlp_numpy': _mlp_numpy}
         exec('\n'.join(src), ns)
         return ns[self.name]
 
@@ -871,11 +967,12 @@ class Function:
 
 
 def gp_tables_used(exprs) -> List[str]:
-    """Ids of the GP tables referenced by ``exprs`` (in first-use order)."""
+    """Ids of the GP / MLP tables referenced by ``exprs`` (in first-use order; MLP ids carry the prefix 'mlp:')."""
     ids: List[str] = []
     for node in topo_sort(as_vector(exprs)):
-        if node.op.startswith('gp:'):
+        if node.op.startswith('gp:') or node.op.startswith('mlp:'):
             gid = _gp_parts(node.op)[0]
+            gid = ('mlp:' + gid) if node.op.startswith('mlp:') else gid
             if gid not in ids:
                 ids.append(gid)
     return ids
@@ -885,6 +982,13 @@ def gp_tables_c_source(ids: Sequence[str]) -> str:
     """Definitions of the training tables for a generated module (device constants + host copies for the CPU logic build)."""
     out = []
     for gid in ids:
+        if gid.startswith('mlp:'):
+            t = MLP_TABLES[gid[4:]]
+            rows = np.concatenate([np.concatenate([t['W1'], t['b1'][:, None]], axis=1).reshape(-1), t['W2'].reshape(-1),
+                                   t['b2']])
+            body = ', '.join(_c_const(float(v)) for v in rows)
+            out.append(f'HB_GP_TABLE double hb_mlp_tab_{gid[4:]}[{rows.size}] = {{{body}}};')
+            continue
         t = GP_TABLES[gid]
         rows = np.concatenate([t['Xs'], t['c'][:, None]], axis=1).reshape(-1)
         body = ', '.join(_c_const(float(v)) for v in rows)

@@ -130,3 +130,53 @@ def test_gp_call_node_derivatives_and_generated_c_code(tmp_path):
     np.testing.assert_allclose(out_e[0], ev, rtol=1e-13)
     np.testing.assert_allclose(out_g, gv, rtol=1e-12, atol=1e-13)
     np.testing.assert_allclose(out_H.reshape(3, 3), Hv, rtol=1e-11, atol=1e-12)
+
+
+def test_mlp_call_node_equals_the_unrolled_graph_and_its_generated_c_code(tmp_path):
+    """A one-hidden-layer network enters expressions as call nodes (value -> Jacobian -> per-output Hessian outputs of one
+    loop over the hidden units, csrc/gp_device.cuh::mlp1_eval).  Value, Jacobian and the multiplier-contracted Hessian
+    must equal those of the fully unrolled graph (machine_learning.py:521-578 restated), in NumPy and in the emitted C."""
+    import ctypes as C
+    import os
+    import subprocess
+    from hilo_mpc_b200.ann import ANN, Layer
+    rng = np.random.default_rng(3)
+    nz, nh, no = 5, 20, 4
+    net = ANN([f'z{i}' for i in range(nz)], [f'y{i}' for i in range(no)])
+    net.add_layers(Layer.dense(nh, 'tanh'))
+    net.setup()
+    net.set_weights([rng.normal(size=(nh, nz)), rng.normal(size=(no, nh))], [rng.normal(size=nh), rng.normal(size=no)],
+                    input_scaling=(rng.normal(size=nz), rng.uniform(.5, 2., nz)),
+                    output_scaling=(rng.normal(size=no), rng.uniform(.5, 2., no)))
+    z, lam = sx.sym('z', nz), sx.sym('l', no)
+    funs = {}
+    for mode in ('call', 'unroll'):
+        net.symbolic_mode = mode
+        y = net.predict(sx.sin(z) * 2. + z)          # composed with an inner map: chain rule through the node
+        funs[mode] = sx.Function('f', [('z', z), ('l', lam)],
+                                 [('y', y), ('J', sx.jacobian(y, z)), ('H', sx.hessian(sx.dot(lam, y), z))])
+    assert funs['call'].n_nodes() < funs['unroll'].n_nodes() / 5
+    zv, lv = rng.normal(size=nz), rng.normal(size=no)
+    ref = funs['unroll'](zv, lv)
+    out = funs['call'](zv, lv)
+    for a, b in zip(out, ref):
+        np.testing.assert_allclose(a, b, rtol=1e-11, atol=1e-12)
+    np.testing.assert_allclose(np.asarray(ref[0]).reshape(-1), net.predict((np.sin(zv) * 2. + zv)[:, None])[:, 0], rtol=1e-12)
+    csrc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'hilo_mpc_b200', 'csrc')
+    ids = sx.gp_tables_used(np.concatenate([o for o in funs['call'].outputs]))
+    assert len(ids) == 1 and ids[0].startswith('mlp:')
+    src = '\n'.join(['#define HB_HOSTSIM', '#include "ocp_kernels.cuh"', sx.gp_tables_c_source(ids), 'extern "C" {',
+                     funs['call'].c_source(qualifiers=''), '}'])
+    assert src.count('mlp1_eval<') == 1
+    cu = tmp_path / 'mlp_fun.cpp'
+    cu.write_text(src)
+    so = tmp_path / 'mlp_fun.so'
+    subprocess.run(['g++', '-O1', '-std=c++17', '-shared', '-fPIC', '-DHB_HOSTSIM', '-I', csrc, str(cu), '-o', str(so)],
+                   check=True)
+    lib = C.CDLL(str(so))
+    o_y, o_J, o_H = np.zeros(no), np.zeros(no * nz), np.zeros(nz * nz)
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    lib.f(dp(zv), dp(lv), dp(o_y), dp(o_J), dp(o_H))
+    np.testing.assert_allclose(o_y, np.asarray(ref[0]).reshape(-1), rtol=1e-12)
+    np.testing.assert_allclose(o_J.reshape(no, nz), ref[1], rtol=1e-11, atol=1e-12)
+    np.testing.assert_allclose(o_H.reshape(nz, nz), ref[2], rtol=1e-10, atol=1e-11)
