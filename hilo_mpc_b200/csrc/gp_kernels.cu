@@ -12,6 +12,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 
 #include "../../include/hilo_b200.h"
 
@@ -241,6 +242,151 @@ __global__ void predict_reduce_kernel(int n, int M, const double* __restrict__ K
   if (var != nullptr) var[m] = sf2 + noise - vv;
 }
 
+// ------------------------------------------------------------------------------------------------ fused prediction
+// mean and variance of QT = 32 query points per CTA without materialising K* or V = L^-1 K* in HBM (the unfused path
+// writes and re-reads 2 x n x M doubles: 537 MB for n = 512, M = 65536):
+//   1. the cross-covariance tile Ks [n][QT] is built in shared memory (one exp per entry) together with the mean
+//      sum_i alpha_i Ks[i][q];
+//   2. V = Linv Ks row tile by row tile (32 rows) on the fp64 tensor pipe: A = Linv tile [32][16] per k-step, staged
+//      through a double-buffered cp.async ring (Linv is L2 resident: n^2 / 2 doubles), B = the resident Ks; the K loop of
+//      a row tile stops at its diagonal block (Linv is lower triangular);
+//   3. the epilogue of a row tile squares its accumulators and adds them to the per-query sum ||V[:, q]||^2 - V itself is
+//      never stored.
+// 8 warps (one CTA per SM: the Ks tile of n = 512 takes 135 KB), warp w owns the 8 x 16 part (rows 8 (w >> 1), columns
+// 16 (w & 1)) of the 32 x 32 output tile = 2 independent DMMA accumulators; n a multiple of 32 (else the unfused path).
+constexpr int QT = 32, FK = 16, FT = 256;
+constexpr int KS_LD = QT + 1;   // odd leading dimension: conflict-free B-operand loads (rows k..k+3, 8 columns)
+
+__device__ __forceinline__ void cp_async16_gp(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+
+__global__ void __launch_bounds__(FT) gp_predict_fused_kernel(int kind, int n, int d, int M, const double* __restrict__ X,
+                                                              const double* __restrict__ Xq, const double* __restrict__ ls,
+                                                              double sf2, double noise, double prior,
+                                                              const double* __restrict__ Linv, const double* __restrict__ alpha,
+                                                              double* __restrict__ mean, double* __restrict__ var) {
+  extern __shared__ __align__(16) double sm[];
+  constexpr int ALD = FK + 2;                        // A-tile row stride: 16-byte aligned chunks
+  double* Ks = sm;                                   // [n][KS_LD]
+  double* As = Ks + (size_t)n * KS_LD;               // [2][32][ALD]
+  double* colsum = As + 2 * 32 * ALD;                // [QT] sum of squares, [QT] mean
+  double* musum = colsum + QT;
+  const int q0 = blockIdx.x * QT, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid < QT) { colsum[tid] = 0.0; musum[tid] = 0.0; }
+  __syncthreads();
+  // ---- 1. cross covariance tile + mean: thread (q = tid % 32, rows tid / 32, +8, ...)
+  {
+    const int q = tid & 31, gq = q0 + q;
+    double xq[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) xq[k] = (k < d && gq < M) ? Xq[(size_t)k * M + gq] / ls[k] : 0.0;
+    double mu = 0.0;
+    for (int i = tid >> 5; i < n; i += FT / 32) {
+      double d2 = 0.0;
+#pragma unroll
+      for (int k = 0; k < 16; ++k)
+        if (k < d) { const double r = X[(size_t)k * n + i] / ls[k] - xq[k]; d2 += r * r; }
+      double v;
+      if (kind == 0) v = sf2 * exp(-0.5 * d2);
+      else {
+        const double r = sqrt(d2);
+        if (kind == 1) v = sf2 * exp(-r);
+        else if (kind == 2) { const double t = 1.7320508075688772 * r; v = sf2 * (1.0 + t) * exp(-t); }
+        else { const double t = 2.23606797749979 * r; v = sf2 * (1.0 + t + t * t * (1.0 / 3.0)) * exp(-t); }
+      }
+      if (gq >= M) v = 0.0;
+      Ks[(size_t)i * KS_LD + q] = v;
+      mu += v * alpha[i];
+    }
+    atomicAdd(&musum[q], mu);
+  }
+  __syncthreads();
+  if (var != nullptr) {
+    const int wm = (warp >> 1) * 8, wn = (warp & 1) * 16;
+    auto load_stage = [&](int buf, int tm, int k0) {   // 32 rows x 16 doubles = 256 chunks of 16 bytes, one per thread
+      const int r = tid >> 3, cc = (tid & 7) * 2;
+      cp_async16_gp(As + (size_t)buf * 32 * ALD + r * ALD + cc, Linv + (size_t)(tm + r) * n + k0 + cc);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    double csq[2][2] = {{0.0, 0.0}, {0.0, 0.0}};   // partial sums of squares of this thread's columns (ni, e)
+    for (int tm = 0; tm < n; tm += 32) {
+      double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+      const int nk = (tm + 32) / FK;      // k-steps up to the diagonal block
+      load_stage(0, tm, 0);
+      for (int ks = 0; ks < nk; ++ks) {
+        if (ks + 1 < nk) load_stage((ks + 1) & 1, tm, (ks + 1) * FK);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncthreads();
+        const double* A0 = As + (size_t)(ks & 1) * 32 * ALD;
+        const int k0 = ks * FK;
+#pragma unroll
+        for (int kk = 0; kk < FK; kk += 4) {
+          const double a = A0[(wm + (lane >> 2)) * ALD + kk + (lane & 3)];
+#pragma unroll
+          for (int ni = 0; ni < 2; ++ni) {
+            const double b = Ks[(size_t)(k0 + kk + (lane & 3)) * KS_LD + wn + ni * 8 + (lane >> 2)];
+            dmma(acc[ni][0], acc[ni][1], a, b);
+          }
+        }
+        __syncthreads();
+      }
+#pragma unroll
+      for (int ni = 0; ni < 2; ++ni) {
+        csq[ni][0] += acc[ni][0] * acc[ni][0];
+        csq[ni][1] += acc[ni][1] * acc[ni][1];
+      }
+    }
+    // column c = wn + ni * 8 + 2 * (lane & 3) + e is shared by the 8 lanes with equal (lane & 3): reduce over lane >> 2
+#pragma unroll
+    for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        double v = csq[ni][e];
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        if ((lane >> 2) == 0) atomicAdd(&colsum[wn + ni * 8 + 2 * (lane & 3) + e], v);
+      }
+    __syncthreads();
+  }
+  if (tid < QT && q0 + tid < M) {
+    mean[q0 + tid] = prior + musum[tid];
+    if (var != nullptr) var[q0 + tid] = sf2 + noise - colsum[tid];
+  }
+}
+
+// mean only: one thread per query point walks the training set (every thread of a warp reads the same training row: one
+// broadcast per load); nothing but Xq and the means touches HBM
+__global__ void __launch_bounds__(128) gp_mean_only_kernel(int kind, int n, int d, int M, const double* __restrict__ X,
+                                                           const double* __restrict__ Xq, const double* __restrict__ ls,
+                                                           double sf2, double prior, const double* __restrict__ alpha,
+                                                           double* __restrict__ mean) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  double xq[16], il[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) { il[k] = k < d ? 1.0 / ls[k] : 0.0; xq[k] = k < d ? Xq[(size_t)k * M + m] * il[k] : 0.0; }
+  double mu = 0.0;
+  for (int i = 0; i < n; ++i) {
+    double d2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+      if (k < d) { const double r = __ldg(X + (size_t)k * n + i) * il[k] - xq[k]; d2 += r * r; }
+    double v;
+    if (kind == 0) v = exp(-0.5 * d2);
+    else {
+      const double r = sqrt(d2);
+      if (kind == 1) v = exp(-r);
+      else if (kind == 2) { const double t = 1.7320508075688772 * r; v = (1.0 + t) * exp(-t); }
+      else { const double t = 2.23606797749979 * r; v = (1.0 + t + t * t * (1.0 / 3.0)) * exp(-t); }
+    }
+    mu += v * __ldg(alpha + i);
+  }
+  mean[m] = prior + sf2 * mu;
+}
+
 }  // namespace
 
 extern "C" {
@@ -308,6 +454,24 @@ int hb_gp_predict_kernel(int kind, int n, int d, int M, const double* X, const d
   if (n <= 0 || d <= 0 || M <= 0 || !X || !Xq || !length_scales || !alpha || !mean || !work) return -1;
   if (var != nullptr && Linv == nullptr) return -1;
   cudaStream_t s = (cudaStream_t)stream;
+  {  // fused path: no K* / V in HBM (n a multiple of 32, d <= 16, the tile fits shared memory)
+    const size_t smem = ((size_t)n * KS_LD + 2 * 32 * (FK + 2) + 2 * QT) * sizeof(double);
+    static bool fused_off = getenv("HB_GP_UNFUSED") != nullptr;
+    if (!fused_off && var == nullptr && d <= 16) {
+      gp_mean_only_kernel<<<(M + 127) / 128, 128, 0, s>>>(kind, n, d, M, X, Xq, length_scales, signal_variance, prior_mean,
+                                                          alpha, mean);
+      cudaError_t e = cudaGetLastError();
+      return e == cudaSuccess ? 0 : (int)e;
+    }
+    if (!fused_off && n % 32 == 0 && d <= 16 && smem <= 200 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(gp_predict_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      gp_predict_fused_kernel<<<(M + QT - 1) / QT, FT, smem, s>>>(kind, n, d, M, X, Xq, length_scales, signal_variance,
+                                                                   noise_variance, prior_mean, Linv, alpha, mean, var);
+      e = cudaGetLastError();
+      return e == cudaSuccess ? 0 : (int)e;
+    }
+  }
   double* Ks = work;                  // [n][M] cross covariance
   double* V = work + (size_t)n * M;   // [n][M] L^-1 K*
   dim3 grid((M + 127) / 128, n);

@@ -100,7 +100,10 @@ struct OcpModule {
   }
 
   // the sweep of one iteration, fastest version the problem admits (riccati_variant: see hb_ocp_call)
-  static int launch_riccati(const OcpArgs& a, int variant, cudaStream_t s, KernelTimer* tm = nullptr) {
+  // fix_in_step: the step kernel that follows redoes flagged (non-convex) instances itself (step_quad.cuh), so the
+  // separate fix-up launch is skipped
+  static int launch_riccati(const OcpArgs& a, int variant, cudaStream_t s, KernelTimer* tm = nullptr,
+                            bool fix_in_step = false) {
     bool ric_done = false;
     if (variant >= 2) {
       int rc6 = -100;
@@ -116,7 +119,7 @@ struct OcpModule {
       }
       if (rc6 > 0) return rc6;
       ric_done = rc6 == 0;
-      if (ric_done) {   // instances flagged as non-convex (rare): timed as its own kernel
+      if (ric_done && !fix_in_step) {   // instances flagged as non-convex (rare): timed as its own kernel
         if (tm) { tm->end(); tm->begin(K_RICFIX); }
         launch_1d<OcpRiccatiFix<P>>(a, a.n_instances(), s);
       }
@@ -262,7 +265,9 @@ struct OcpModule {
       tm.end();
       tm.begin(K_RICCATI);
       {
-        const int rcr = launch_riccati(a, c->riccati_variant, s, &tm);
+        // (folding the fix-up of flagged instances into the step kernel was measured: its cold call costs step_quad
+        //  45 us per launch in spills - the 3 us launch stays)
+        const int rcr = launch_riccati(a, c->riccati_variant, s, &tm, false);
         if (rcr != 0) return rcr;
       }
       tm.end();

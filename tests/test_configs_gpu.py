@@ -149,3 +149,41 @@ def test_config5_path_following_with_mlp_dynamics_full_size(cuda_device):
         assert r.status == 1
         np.testing.assert_allclose(xb, xo.T, atol=5e-5)
         np.testing.assert_allclose(ub, uo.T, atol=5e-5)
+
+
+def test_nonconvex_instances_of_the_warp_sweep_are_redone_with_inertia_correction(cuda_device):
+    """Pendulum swing-up (nx=2, nu=1: the warp-per-instance tensor-pipe sweep): far from the solution the exact Lagrangian
+    Hessian is indefinite, the sweep flags the instance (ST_ICREQ) and the step kernel (step_variant 2) or the fix-up
+    kernel (step_variant 0) redoes it with IPOPT's inertia correction.  Both routes must reach the same KKT points."""
+    import torch
+    from hilo_mpc_b200 import NMPC
+    from hilo_mpc_b200 import symbolic as sx
+    from hilo_mpc_b200.model import Model
+    res = []
+    for variant in (2, 0):
+        model = Model(name='pendulum')
+        x = model.set_dynamical_states(['th', 'om'])
+        u = model.set_inputs(['tau'])
+        model.set_dynamical_equations([x[1], -sx.sin(x[0]) - .1 * x[1] + u[0]])
+        model.setup(dt=.1)
+        nmpc = NMPC(model)
+        nmpc.horizon = 20
+        nmpc.quad_stage_cost.add_states(names=['th', 'om'], ref=[np.pi, 0.], weights=[10., 1.])
+        nmpc.quad_stage_cost.add_inputs(names=['tau'], weights=[.1])
+        nmpc.quad_terminal_cost.add_states(names=['th', 'om'], ref=[np.pi, 0.], weights=[100., 10.])
+        nmpc.set_box_constraints(x_lb=[-10., -10.], x_ub=[10., 10.], u_lb=[-3.], u_ub=[3.])
+        nmpc.set_initial_guess(x_guess=[0., 0.], u_guess=[0.])
+        nmpc.set_solver_opts({'b200.step_variant': variant, 'ipopt.max_iter': 500})
+        nmpc.setup()
+        rng = np.random.default_rng(0)
+        x0 = np.column_stack([rng.uniform(-.5, .5, 64), rng.uniform(-.5, .5, 64)])
+        nmpc.optimize(torch.tensor(x0, device=cuda_device))
+        assert nmpc.engine.dims.frag == 1
+        st = nmpc.solver_status_code
+        out = nmpc._last
+        res.append((st.clone(), out['x'].clone(), out['stats'][:, 20].clone()))   # ST_DW: last inertia correction used
+    ok = (res[0][0] == 1) & (res[1][0] == 1)
+    assert ok.float().mean().item() > .9
+    assert (res[0][2] > 0).any() and (res[1][2] > 0).any()     # the correction was needed: the non-convex path was taken
+    same = ((res[0][1] - res[1][1]).abs().flatten(1).max(dim=1).values < 1e-6) & ok
+    assert same.float().mean().item() > .8

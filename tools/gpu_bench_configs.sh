@@ -2,7 +2,7 @@
 # bench lines of the BASELINE configurations on one GPU; logs under gpurun_out/
 mkdir -p gpurun_out
 for c in ${CONFIGS:-2 4 5 3}; do
-  timeout ${BENCH_TIMEOUT:-900} python bench.py --config $c ${BENCH_ARGS} > gpurun_out/bench_c$c.json 2> gpurun_out/bench_c$c.err
+  timeout -k 10 ${BENCH_TIMEOUT:-900} python bench.py --config $c ${BENCH_ARGS} > gpurun_out/bench_c$c.json 2> gpurun_out/bench_c$c.err
   echo "config $c rc=$?"; tail -2 gpurun_out/bench_c$c.err
 done
 python - <<'PY'

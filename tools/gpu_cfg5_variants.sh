@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 i=0
 for v in "" "--opt b200.eval_variant=0" "--opt b200.regularization_mu=0" "--warm-mu 1e-4" "--warm-mu 1e-8" "--opt b200.eval_variant=0 --opt b200.step_variant=1"; do
-  timeout 600 python bench.py --config 5 --batch 1024 --steps 10 --no-cpu-baseline --no-default-options $v > gpurun_out/bench_v$i.json 2> gpurun_out/bench_v$i.err
+  timeout -k 10 600 python bench.py --config 5 --batch 1024 --steps 10 --no-cpu-baseline --no-default-options $v > gpurun_out/bench_v$i.json 2> gpurun_out/bench_v$i.err
   echo "variant $i [$v] rc=$?"
   i=$((i+1))
 done

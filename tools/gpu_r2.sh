@@ -1,10 +1,10 @@
 #!/bin/bash
 # round-2 GPU check: smoke, GPU tests (per-test timeouts), default bench; logs under gpurun_out/
 mkdir -p gpurun_out
-timeout 180 python -u -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log
-timeout 900 python -u -m pytest tests -m gpu -q --timeout 300 --deselect tests/test_gp_gpu.py ${PYTEST_ARGS} > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log; tail -25 gpurun_out/pytest_gpu.log
-timeout 300 python -u -m pytest tests/test_gp_gpu.py -m gpu -q --timeout 60 > gpurun_out/pytest_gp.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gp.log; tail -3 gpurun_out/pytest_gp.log
-timeout 400 python bench.py ${BENCH_ARGS} > gpurun_out/bench_r2.json 2> gpurun_out/bench_r2.err; tail -3 gpurun_out/bench_r2.err
+timeout -k 10 180 python -u -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log
+timeout -k 10 900 python -u -m pytest tests -m gpu -q --timeout -k 10 300 --deselect tests/test_gp_gpu.py ${PYTEST_ARGS} > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log; tail -25 gpurun_out/pytest_gpu.log
+timeout -k 10 300 python -u -m pytest tests/test_gp_gpu.py -m gpu -q --timeout -k 10 60 > gpurun_out/pytest_gp.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gp.log; tail -3 gpurun_out/pytest_gp.log
+timeout -k 10 400 python bench.py ${BENCH_ARGS} > gpurun_out/bench_r2.json 2> gpurun_out/bench_r2.err; tail -3 gpurun_out/bench_r2.err
 python - <<'PY'
 import json
 try:

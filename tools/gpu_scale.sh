@@ -4,9 +4,9 @@ N=${1:-2}; CFGS=${2:-"2 4 5"}
 mkdir -p gpurun_out
 for c in $CFGS; do
   if [ "$N" = "1" ]; then
-    timeout 900 python bench.py --config $c --gpus 1 --steps ${STEPS:-40} --no-cpu-baseline --no-gp > gpurun_out/scale_c${c}_n$N.json 2> gpurun_out/scale_c${c}_n$N.err
+    timeout -k 10 900 python bench.py --config $c --gpus 1 --steps ${STEPS:-40} --no-cpu-baseline --no-gp > gpurun_out/scale_c${c}_n$N.json 2> gpurun_out/scale_c${c}_n$N.err
   else
-    timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500 + c)) bench.py --config $c --gpus $N --steps ${STEPS:-40} --no-cpu-baseline --no-gp > gpurun_out/scale_c${c}_n$N.json 2> gpurun_out/scale_c${c}_n$N.err
+    timeout -k 10 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500 + c)) bench.py --config $c --gpus $N --steps ${STEPS:-40} --no-cpu-baseline --no-gp > gpurun_out/scale_c${c}_n$N.json 2> gpurun_out/scale_c${c}_n$N.err
   fi
   echo "config $c N=$N rc=$?"; tail -1 gpurun_out/scale_c${c}_n$N.json | python -c "
 import sys, json

@@ -1,9 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_lmpc_condensed.py -m gpu -q --timeout 200 -x 2>&1 | grep -E "^E |Error|passed|failed" | head -20
+timeout -k 10 300 python -m pytest tests/test_lmpc_condensed.py -m gpu -q --timeout -k 10 200 -x 2>&1 | grep -E "^E |Error|passed|failed" | head -20
 i=0
 for v in "--config 5 --batch 1024 --opt b200.shift_warm_start=1" "--config 5 --batch 1024 --opt b200.shift_warm_start=1 --warm-mu 1e-8" "--config 4 --opt b200.shift_warm_start=1" "--config 4" "--config 2 --opt b200.shift_warm_start=1"; do
-  timeout 600 python bench.py --steps 20 --no-cpu-baseline --no-default-options --no-gp $v > gpurun_out/bench_s$i.json 2> gpurun_out/bench_s$i.err
+  timeout -k 10 600 python bench.py --steps 20 --no-cpu-baseline --no-default-options --no-gp $v > gpurun_out/bench_s$i.json 2> gpurun_out/bench_s$i.err
   echo "variant $i [$v] rc=$?"
   i=$((i+1))
 done
