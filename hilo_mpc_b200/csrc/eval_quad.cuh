@@ -72,7 +72,7 @@ struct EvalQuad {
   static HB_HD constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }   // j <= i
   static constexpr int NRED = (NTRI + 2 * NE) | 1;
   static constexpr int FT = (((D * FSZ > NC * (NE + 1)) ? D * FSZ : NC * (NE + 1)) + 1) & ~1;   // even: PB holds 128-bit words
-  static constexpr int PBN = (4 * ((W + 1) & ~1) > NC) ? 4 * ((W + 1) & ~1) : NC;   // 2 buffers x 2 pivot rows
+  static constexpr int PBN = (2 * ((W + 1) & ~1) > NC) ? 2 * ((W + 1) & ~1) : NC;   // 2 pivot-row buffers
   static constexpr int A1 = FT + PBN + D * LSZ, A2 = LPN * NRED;
   static constexpr int NCSZ = NODECOST ? (NX + NU + NX * NX + NU * NX + NU * NU) : 0;  // gx | gu | Qn | Sn | Rn of the node cost
   static constexpr int oF = 0, oT = 0, oPB = FT, oNU = oPB, oL = oPB + PBN, oRED = 0,
@@ -117,8 +117,9 @@ struct EvalQuad {
     for (int bk = 0; bk < NB2; ++bk) {
       const int c = 2 * bk;
       const int po0 = c % LPN, plr0 = c / LPN, po1 = (c + 1) % LPN, plr1 = (c + 1) / LPN;
-      // both rows are published from column c (even) on: rows c and c + 1 side by side, double-buffered over the rounds
-      double* prow = pb + (bk & 1) * 2 * PS;
+      // both rows are published from column c (even) on, side by side in the two row buffers; the barrier after the
+      // reads frees them for the next round
+      double* prow = pb;
       if (q == po0) {
 #pragma unroll
         for (int j = c; j < NCOLS; j += 2)
@@ -137,6 +138,7 @@ struct EvalQuad {
         const double2 t1 = *reinterpret_cast<const double2*>(prow + PS + j);
         p0[j] = t0.x; p0[j + 1] = t0.y; p1[j] = t1.x; p1[j + 1] = t1.y;
       }
+      __syncwarp();
       // inverse of the pivot block [a b; cc d] (rows c, c + 1; columns c, c + 1)
       const double a = p0[c], b = p0[c + 1], cc = p1[c], d = p1[c + 1];
       const double det = a * d - b * cc;
@@ -161,7 +163,7 @@ struct EvalQuad {
     if constexpr (NPIV % 2 == 1) {         // odd last pivot: one scalar step, its row normalised on the spot
       constexpr int c = NPIV - 1;
       const int po = c % LPN, plr = c / LPN;
-      double* prow = pb + (NB2 & 1) * 2 * PS;
+      double* prow = pb;
       constexpr int j0 = c & ~1;
       if (q == po) {
 #pragma unroll

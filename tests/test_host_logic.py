@@ -74,3 +74,48 @@ def test_control_loop_checks_and_fails_loudly_without_gpu():
     if not torch.cuda.is_available():
         with pytest.raises(EngineUnavailable):
             loop.run(1, x0=np.zeros((2, 4)))
+
+
+def test_control_loop_hands_only_constant_parameters_to_the_controller():
+    """Plant parameters that the controller treats as time-varying must not reach ``cp`` (reference
+    control_loop.py:357-362); a ``cp`` of the wrong length is an error, not a silent batch."""
+    import torch
+    from hilo_mpc_b200 import Model
+
+    plant = Model(name='two_par')
+    x = plant.set_dynamical_states(['a'])
+    u = plant.set_inputs(['u'])
+    p = plant.set_parameters(['k', 'w'])
+    plant.set_dynamical_equations([-p[0] * x[0] + p[1] * u[0]])
+    plant.setup(dt=.1)
+
+    class Recorder:
+        _model = plant
+        _tvp_names = ['w']
+
+        def optimize(self, x0, cp=None, **kwargs):
+            self.cp = cp
+            return torch.zeros(x0.shape[0], 1, dtype=torch.float64)
+
+    ctrl = Recorder()
+    loop = SimpleControlLoop(plant, ctrl)
+    loop._control(torch.zeros(3, 1, dtype=torch.float64), [2., 5.], {})
+    assert [float(v) for v in ctrl.cp] == [2.]
+    ctrl._tvp_names = []
+    loop._control(torch.zeros(3, 1, dtype=torch.float64), [2., 5.], {})
+    assert [float(v) for v in np.asarray(ctrl.cp).reshape(-1)] == [2., 5.]
+
+    # NMPC side: the alias the reference's loop reads exists, and a cp of the wrong size is rejected
+    from hilo_mpc_b200 import NMPC
+    nmpc = NMPC(plant)
+    nmpc.horizon = 4
+    nmpc.quad_stage_cost.add_states(names=['a'], weights=[1.], ref=[0.])
+    nmpc.set_time_varying_parameters(['w'], values={'w': [1., 2., 3.]})
+    nmpc._build_module = False
+    nmpc.setup()
+    assert list(nmpc._time_varying_parameters) == ['w'] == list(nmpc._tvp_names)
+    with pytest.raises(ValueError):
+        nmpc._stage_parameters([1., 2., 3.], None, None, torch, torch.device('cpu'), 2)
+    sp = nmpc._stage_parameters([7.], None, None, torch, torch.device('cpu'), 2)
+    assert sp.shape[-1] == 2 and sp.shape[-2] == 4                    # per stage: [w_k, k]
+    assert np.allclose(sp.reshape(-1, 4, 2)[0].numpy(), [[1., 7.], [2., 7.], [3., 7.], [1., 7.]])
