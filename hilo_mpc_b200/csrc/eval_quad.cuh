@@ -39,6 +39,14 @@ struct OcpEvalTail {
 
 #if HB_DEVICE_BUILD
 
+// tuning knobs of the 8-lanes-per-node variant (see NCOPY and the launch bounds)
+#ifndef HB_EVQ_PAIRRED
+#define HB_EVQ_PAIRRED 1
+#endif
+#ifndef HB_EVQ_MINB8
+#define HB_EVQ_MINB8 2
+#endif
+
 template <class P>
 struct EvalQuad {
   using T = OcpT<P>;
@@ -73,7 +81,11 @@ struct EvalQuad {
   static constexpr int NRED = (NTRI + 2 * NE) | 1;
   static constexpr int FT = (((D * FSZ > NC * (NE + 1)) ? D * FSZ : NC * (NE + 1)) + 1) & ~1;   // even: PB holds 128-bit words
   static constexpr int PBN = (2 * ((W + 1) & ~1) > NC) ? 2 * ((W + 1) & ~1) : NC;   // 2 pivot-row buffers
-  static constexpr int A1 = FT + PBN + D * LSZ, A2 = LPN * NRED;
+  // copies of the partial sums that meet in shared memory: with 8 lanes per node the lanes q and q ^ 4 add theirs by a
+  // shuffle first (HB_EVQ_PAIRRED, default on), which takes the reduction area below the size of [F/T | PB | L] and
+  // the CTA under a third of the SM's shared memory
+  static constexpr int NCOPY = (LPN == 8 && HB_EVQ_PAIRRED) ? 4 : LPN;
+  static constexpr int A1 = FT + PBN + D * LSZ, A2 = NCOPY * NRED;
   static constexpr int NCSZ = NODECOST ? (NX + NU + NX * NX + NU * NX + NU * NU) : 0;  // gx | gu | Qn | Sn | Rn of the node cost
   static constexpr int oF = 0, oT = 0, oPB = FT, oNU = oPB, oL = oPB + PBN, oRED = 0,
                        oSUM = (A1 > A2 ? A1 : A2),                       // sum_i lu_i [NU] | sum_i luu_i [NU*NU]
@@ -618,7 +630,13 @@ struct EvalQuad {
       }
     }
     __syncwarp();   // every lane is done with F / T / PB / L: the area becomes the reduction buffer
-    {
+    if constexpr (NCOPY < LPN) {
+#pragma unroll
+      for (int e = 0; e < NTRI; ++e) Pt[e] += qshfl_xor(Pt[e], NCOPY);
+#pragma unroll
+      for (int ii = 0; ii < NE; ++ii) { gq[ii] += qshfl_xor(gq[ii], NCOPY); gbp[ii] += qshfl_xor(gbp[ii], NCOPY); }
+    }
+    if (q < NCOPY) {
       double* red = S + oRED + q * NRED;
 #pragma unroll
       for (int e = 0; e < NTRI; ++e) red[e] = Pt[e];
@@ -630,7 +648,7 @@ struct EvalQuad {
     auto rsum = [&](int e) {   // sum of entry e over the lanes' copies
       double v = S[oRED + e];
 #pragma unroll
-      for (int c = 1; c < LPN; ++c) v += S[oRED + c * NRED + e];
+      for (int c = 1; c < NCOPY; ++c) v += S[oRED + c * NRED + e];
       return v;
     };
 #pragma unroll
@@ -695,7 +713,7 @@ struct EvalQuad {
 };
 
 template <class P>
-__global__ void __launch_bounds__(128, EvalQuad<P>::LPN == 4 ? 3 : 2) eval_quad_kernel(OcpArgs a) { EvalQuad<P>::run(a); }
+__global__ void __launch_bounds__(128, EvalQuad<P>::LPN == 4 ? 3 : HB_EVQ_MINB8) eval_quad_kernel(OcpArgs a) { EvalQuad<P>::run(a); }
 
 template <class P>
 inline cudaError_t launch_eval_quad(const OcpArgs& a, cudaStream_t s) {
