@@ -366,11 +366,24 @@ struct StepQuad {
   }
 };
 
-#ifndef HB_STEPQ_MINB
-#define HB_STEPQ_MINB 2   // CTAs per SM the register allocation aims at
+// CTAs per SM the register allocation aims at.  The kernel waits on global loads (44 % of its warp samples), so warps
+// per SM matter, but under about HB_STEPQ_REGS registers per thread the spills cost more than the extra warps bring
+// (measured: 224-thread CTAs 226 us at 128 registers / 275 us at 80; 128-thread CTAs 332 us at 255 / 259 us at 168):
+// as many CTAs as still leave that many registers.
+#ifndef HB_STEPQ_REGS
+#define HB_STEPQ_REGS 128
 #endif
 template <class P>
-__global__ void __launch_bounds__(StepQuad<P>::THREADS, HB_STEPQ_MINB) step_quad_kernel(const OcpArgs a) { StepQuad<P>::run(a); }
+struct StepQuadLaunch {
+#ifdef HB_STEPQ_MINB
+  static constexpr int MINB = HB_STEPQ_MINB;
+#else
+  static constexpr int FIT = 65536 / (HB_STEPQ_REGS * StepQuad<P>::THREADS);
+  static constexpr int MINB = FIT < 2 ? 2 : (FIT > 8 ? 8 : FIT);
+#endif
+};
+template <class P>
+__global__ void __launch_bounds__(StepQuad<P>::THREADS, StepQuadLaunch<P>::MINB) step_quad_kernel(const OcpArgs a) { StepQuad<P>::run(a); }
 
 template <class P>
 inline cudaError_t launch_step_quad(const OcpArgs& a, cudaStream_t s) {
