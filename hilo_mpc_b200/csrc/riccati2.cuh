@@ -461,8 +461,11 @@ struct RiccatiTma2 {
   }
 };
 
+#ifndef HB_RIC2_MINB
+#define HB_RIC2_MINB 2   // CTAs per SM the register allocation aims at
+#endif
 template <class P>
-__global__ void __launch_bounds__(RiccatiTma2<P>::THREADS, 2) riccati_tma2_kernel(OcpArgs a) { RiccatiTma2<P>::run(a); }
+__global__ void __launch_bounds__(RiccatiTma2<P>::THREADS, HB_RIC2_MINB) riccati_tma2_kernel(OcpArgs a) { RiccatiTma2<P>::run(a); }
 
 template <class P>
 inline cudaError_t launch_riccati_tma2(const OcpArgs& a, cudaStream_t s) {
