@@ -131,5 +131,118 @@ inline cudaError_t launch_ukf_lanes(const EstArgs& a, cudaStream_t s) {
   return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Particle filter, warp-level version: one WARP per filter, its particles on the lanes (particle k on lane k % 32).
+//
+// The one-thread-per-filter kernel (PfStep) walks the n_s particles of a filter in sequence - n_s x substeps x 4
+// right-hand-side evaluations per thread, and 16384 filters are 3.5 warps per SM.  Here the propagations, likelihoods,
+// the binary searches of the resampling and the gather run side by side; what the reference computes as a SEQUENCE
+// (normalisation sum, cumulative sum of the weights, sample mean and covariance: the order fixes the rounding, and the
+// resampling indices must equal numpy's bit for bit) stays a sequence, walked by one lane per output - weights: lane 0,
+// mean: lane i < nx, covariance: lane (i, j) - over data the warp has just written (L1-resident).  The results are
+// therefore identical to PfStep's, bit for bit.
+template <class E>
+struct PfLanes {
+  static constexpr int NX = E::NX, NY = E::NYE;
+
+  static __device__ void run(const EstArgs& a) {
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = gt >> 5, lane = gt & 31;
+    if (b >= a.B) return;                       // whole warps only: no shuffle / barrier partner is lost
+    const double* u = a.u + (long long)b * a.u_stride;
+    const double* p = a.p + (long long)b * a.p_stride;
+    const int ns = a.n_particles;
+    double* Xg = a.X + (long long)b * ns * NX;
+    double* Xs = a.Xs + (long long)b * ns * NX;
+    double* q = a.q + (long long)b * ns;
+    double* Ys = a.Ys + (long long)b * ns;
+    double* cdf = a.cdf + (long long)b * ns;
+    long long* idx = a.idx + (long long)b * ns;
+    const double* unif = a.unif + (long long)b * ns;
+    const double yv = a.y[(long long)b * NY];
+    const double sigma = sqrt(a.R[0]);          // univariate likelihood (pf.py:158)
+    // ---- 1. propagate, add the noise, likelihood (parallel over the particles)
+    for (int k = lane; k < ns; k += 32) {
+      double xn[NX], yk[NY];
+      est_propagate<E>(Xg + k * NX, u, p, a.t0, a.dt, a.substeps, xn);
+      E::hE(xn, u, p, yk);
+#pragma unroll
+      for (int i = 0; i < NX; ++i) Xs[k * NX + i] = xn[i] + a.w[((long long)b * ns + k) * NX + i];
+      const double Y = yk[0] + a.v[((long long)b * ns + k) * NY];
+      const double r = (Y - yv) / sigma;
+      q[k] = exp(-0.5 * r * r) / (sqrt(2.0 * M_PI) * sigma);
+      Ys[k] = Y;
+    }
+    __syncwarp();
+    // ---- 2. weights: q / sum(q), cdf = cumsum(q) / cdf[-1]  (the two running sums in particle order)
+    double qsum = 0.0;
+    if (lane == 0)
+      for (int k = 0; k < ns; ++k) qsum += q[k];
+    qsum = __shfl_sync(0xffffffffu, qsum, 0);
+    for (int k = lane; k < ns; k += 32) q[k] /= qsum;
+    __syncwarp();
+    double last = 0.0;
+    if (lane == 0) {
+      double sacc = 0.0;
+      for (int k = 0; k < ns; ++k) { sacc += q[k]; cdf[k] = sacc; }
+      last = sacc;
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    __syncwarp();
+    for (int k = lane; k < ns; k += 32) cdf[k] /= last;
+    __syncwarp();
+    // ---- 3. resampling indices: searchsorted(cdf, u, side='right'), one search per lane
+    for (int k = lane; k < ns; k += 32) {
+      const double uu = unif[k];
+      int lo = 0, hi = ns;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (cdf[mid] <= uu) lo = mid + 1; else hi = mid;
+      }
+      idx[k] = lo;
+    }
+    __syncwarp();
+    // ---- 4. gather the survivors
+    for (int k = lane; k < ns; k += 32) {
+      const long long src = idx[k];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) Xg[k * NX + i] = Xs[src * NX + i];
+    }
+    __syncwarp();
+    // ---- 5. moments, each output a sequence over the particles like the reference's sum2 / np.cov
+    for (int i = lane; i < NX; i += 32) {
+      double sacc = 0.0;
+      for (int k = 0; k < ns; ++k) sacc += Xg[k * NX + i];
+      a.x[(long long)b * NX + i] = sacc / ns;
+    }
+    __syncwarp();
+    for (int e = lane; e < NX * NX; e += 32) {
+      const int i = e / NX, j = e % NX;
+      const double mi = a.x[(long long)b * NX + i], mj = a.x[(long long)b * NX + j];
+      double sacc = 0.0;
+      for (int k = 0; k < ns; ++k) sacc += (Xg[k * NX + i] - mi) * (Xg[k * NX + j] - mj);
+      a.P[(long long)b * NX * NX + e] = sacc / (ns - 1);
+    }
+    if (lane == 0) {
+      if (a.y_pred != nullptr) {                // pf.py:419-420: mean of the resampled noisy measurements
+        double ym = 0.0;
+        for (int k = 0; k < ns; ++k) ym += Ys[idx[k]];
+        a.y_pred[(long long)b * NY] = ym / ns;
+      }
+      a.status[b] = 0;
+    }
+  }
+};
+
+template <class E>
+__global__ void __launch_bounds__(128) pf_lanes_kernel(EstArgs a) { PfLanes<E>::run(a); }
+
+template <class E>
+inline cudaError_t launch_pf_lanes(const EstArgs& a, cudaStream_t s) {
+  const long long threads = (long long)a.B * 32;
+  pf_lanes_kernel<E><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
 #endif  // HB_DEVICE_BUILD
 }  // namespace hb

@@ -69,6 +69,12 @@ struct EstModule {
     EstArgs a; if (!fill(c, a)) return -1;
     if (a.n_particles < 2 || c->work == nullptr || c->work_doubles < work_doubles(a.B, a.n_particles)) return -2;
     if (a.status == nullptr || a.X == nullptr || a.q == nullptr || a.idx == nullptr) return -4;
+#if HB_DEVICE_BUILD
+    if (c->variant != 0) {   // one warp per filter, particles on the lanes (est_lanes.cuh); bit-identical to PfStep
+      cudaError_t e = launch_pf_lanes<E>(a, (cudaStream_t)c->stream);
+      return e == cudaSuccess ? finish() : (int)e;
+    }
+#endif
     launch_1d<PfStep<E>>(a, a.B, (cudaStream_t)c->stream); return finish();
   }
 };

@@ -44,7 +44,10 @@ struct OcpEvalTail {
 #define HB_EVQ_PAIRRED 1
 #endif
 #ifndef HB_EVQ_MINB8
-#define HB_EVQ_MINB8 2
+#define HB_EVQ_MINB8 2   // 3 (168 registers, 450 bytes of spills) measured 9 % slower at config 5
+#endif
+#ifndef HB_EVQ_MINB4
+#define HB_EVQ_MINB4 3
 #endif
 
 template <class P>
@@ -112,96 +115,10 @@ struct EvalQuad {
   // state for the Radau-3 constants; the largest |1 / pivot| met is returned so that the caller can hand nodes with
   // a degenerate pivot (stiff dt*f_x) to the partially pivoted one-thread-per-node kernel.
   // On return row r holds, in columns >= NPIV, the solution of variable r.
-  // HB_EVQ_BLOCK2 = 1 (experiment, off by default): the pivots are taken two at a time (2 x 2 diagonal blocks, static order): half as many
-  // broadcast rounds - each round is one dependent chain "publish rows -> __syncwarp -> read rows -> reciprocal ->
-  // multipliers -> row update", which is what bounds this kernel at 12 warps per SM - for the same number of FMAs.
-#ifndef HB_EVQ_BLOCK2
-#define HB_EVQ_BLOCK2 0
-#endif
   template <int NCOLS, int NPIV>
   static __device__ __forceinline__ double gauss_jordan(double (&R)[RPL][NCOLS], int q, double* pb) {
     constexpr int PS = (NCOLS + 1) & ~1;   // even stride: the pivot rows travel in 128-bit words
-    double maxinv = 0.0;                   // largest |1 / pivot| (|1 / det| of a block) met
-#if HB_EVQ_BLOCK2
-    static_assert(LPN >= 2, "block pivoting needs the two pivot rows on different lanes");
-    constexpr int NB2 = NPIV / 2;          // 2 x 2 blocks; an odd last pivot is handled by the scalar step below
-#pragma unroll
-    for (int bk = 0; bk < NB2; ++bk) {
-      const int c = 2 * bk;
-      const int po0 = c % LPN, plr0 = c / LPN, po1 = (c + 1) % LPN, plr1 = (c + 1) / LPN;
-      // both rows are published from column c (even) on, side by side in the two row buffers; the barrier after the
-      // reads frees them for the next round
-      double* prow = pb;
-      if (q == po0) {
-#pragma unroll
-        for (int j = c; j < NCOLS; j += 2)
-          *reinterpret_cast<double2*>(prow + j) = make_double2(R[plr0][j], (j + 1 < NCOLS) ? R[plr0][j + 1] : 0.0);
-      }
-      if (q == po1) {
-#pragma unroll
-        for (int j = c; j < NCOLS; j += 2)
-          *reinterpret_cast<double2*>(prow + PS + j) = make_double2(R[plr1][j], (j + 1 < NCOLS) ? R[plr1][j + 1] : 0.0);
-      }
-      __syncwarp();
-      double p0[PS], p1[PS];
-#pragma unroll
-      for (int j = c; j < NCOLS; j += 2) {
-        const double2 t0 = *reinterpret_cast<const double2*>(prow + j);
-        const double2 t1 = *reinterpret_cast<const double2*>(prow + PS + j);
-        p0[j] = t0.x; p0[j + 1] = t0.y; p1[j] = t1.x; p1[j + 1] = t1.y;
-      }
-      __syncwarp();
-      // inverse of the pivot block [a b; cc d] (rows c, c + 1; columns c, c + 1)
-      const double a = p0[c], b = p0[c + 1], cc = p1[c], d = p1[c + 1];
-      const double det = a * d - b * cc;
-      const double idet = rcp_nr(det);
-      maxinv = fmax(maxinv, fabs(idet) * fmax(fmax(fabs(a), fabs(d)), fmax(fabs(b), fabs(cc))));
-      const double i00 = d * idet, i01 = -b * idet, i10 = -cc * idet, i11 = a * idet;
-#pragma unroll
-      for (int lr = 0; lr < RPL; ++lr) {
-        const bool is0 = (lr == plr0) && (q == po0), is1 = (lr == plr1) && (q == po1);
-        // non-pivot row: multipliers (f0, f1) = (r[c], r[c+1]) inv, r -= f0 p0 + f1 p1
-        // pivot rows: replaced by inv [p0; p1] (normalised at once), written as the same update with suitable factors:
-        //   row c   <- i00 p0 + i01 p1 = r - ((1 - i00) p0 - i01 p1)          (r = p0)
-        //   row c+1 <- i10 p0 + i11 p1 = r - (-i10 p0 + (1 - i11) p1)         (r = p1)
-        const double r0 = R[lr][c], r1 = R[lr][c + 1];
-        double f0 = r0 * i00 + r1 * i10, f1 = r0 * i01 + r1 * i11;
-        f0 = is0 ? 1.0 - i00 : (is1 ? -i10 : f0);
-        f1 = is0 ? -i01 : (is1 ? 1.0 - i11 : f1);
-#pragma unroll
-        for (int j = c + 2; j < NCOLS; ++j) R[lr][j] -= f0 * p0[j] + f1 * p1[j];
-      }
-    }
-    if constexpr (NPIV % 2 == 1) {         // odd last pivot: one scalar step, its row normalised on the spot
-      constexpr int c = NPIV - 1;
-      const int po = c % LPN, plr = c / LPN;
-      double* prow = pb;
-      constexpr int j0 = c & ~1;
-      if (q == po) {
-#pragma unroll
-        for (int j = j0; j < NCOLS; j += 2)
-          *reinterpret_cast<double2*>(prow + j) = make_double2(R[plr][j], (j + 1 < NCOLS) ? R[plr][j + 1] : 0.0);
-      }
-      __syncwarp();
-      double pr[PS];
-#pragma unroll
-      for (int j = j0; j < NCOLS; j += 2) {
-        const double2 t2 = *reinterpret_cast<const double2*>(prow + j);
-        pr[j] = t2.x; pr[j + 1] = t2.y;
-      }
-      const double inv = rcp_nr(pr[c]);
-      maxinv = fmax(maxinv, fabs(inv));
-#pragma unroll
-      for (int lr = 0; lr < RPL; ++lr) {
-        const bool is_piv = (lr == plr) && (q == po);
-        const double f = is_piv ? 1.0 - inv : R[lr][c] * inv;   // pivot row: r - (1 - inv) r = inv r
-#pragma unroll
-        for (int j = c + 1; j < NCOLS; ++j) R[lr][j] -= f * pr[j];
-      }
-    }
-    __syncwarp();
-    return maxinv;
-#else
+    double maxinv = 0.0;                   // largest |1 / pivot| met
     double ipiv[RPL];
 #pragma unroll
     for (int lr = 0; lr < RPL; ++lr) ipiv[lr] = 1.0;
@@ -240,7 +157,6 @@ struct EvalQuad {
     }
     __syncwarp();
     return maxinv;
-#endif
   }
 
   static __device__ void run(const OcpArgs& a) {
@@ -713,7 +629,7 @@ struct EvalQuad {
 };
 
 template <class P>
-__global__ void __launch_bounds__(128, EvalQuad<P>::LPN == 4 ? 3 : HB_EVQ_MINB8) eval_quad_kernel(OcpArgs a) { EvalQuad<P>::run(a); }
+__global__ void __launch_bounds__(128, EvalQuad<P>::LPN == 4 ? HB_EVQ_MINB4 : HB_EVQ_MINB8) eval_quad_kernel(OcpArgs a) { EvalQuad<P>::run(a); }
 
 template <class P>
 inline cudaError_t launch_eval_quad(const OcpArgs& a, cudaStream_t s) {

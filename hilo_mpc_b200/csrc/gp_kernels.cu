@@ -254,8 +254,10 @@ __global__ void predict_reduce_kernel(int n, int M, const double* __restrict__ K
 //      never stored.
 // 8 warps (one CTA per SM: the Ks tile of n = 512 takes 135 KB), warp w owns the 8 x 16 part (rows 8 (w >> 1), columns
 // 16 (w & 1)) of the 32 x 32 output tile = 2 independent DMMA accumulators; n a multiple of 32 (else the unfused path).
-constexpr int QT = 32, FK = 16, FT = 256;
-constexpr int KS_LD = QT + 1;   // odd leading dimension: conflict-free B-operand loads (rows k..k+3, 8 columns)
+constexpr int QT = 32, FK = 16, FT = 256, TMR = 64;   // queries per CTA, k-step, threads, rows of L^-1 per outer step
+// leading dimensions = 4 (mod 16) doubles: the 16 lanes of a half-warp read fragment element (k = lane & 3, row or
+// column = lane >> 2) at k * LD + (lane >> 2), i.e. 4 k + (lane >> 2) (mod 16) - sixteen different 8-byte banks
+constexpr int KS_LD = QT + 4, ALD = FK + 4;
 
 __device__ __forceinline__ void cp_async16_gp(void* dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
@@ -267,10 +269,9 @@ __global__ void __launch_bounds__(FT) gp_predict_fused_kernel(int kind, int n, i
                                                               const double* __restrict__ Linv, const double* __restrict__ alpha,
                                                               double* __restrict__ mean, double* __restrict__ var) {
   extern __shared__ __align__(16) double sm[];
-  constexpr int ALD = FK + 2;                        // A-tile row stride: 16-byte aligned chunks
   double* Ks = sm;                                   // [n][KS_LD]
-  double* As = Ks + (size_t)n * KS_LD;               // [2][32][ALD]
-  double* colsum = As + 2 * 32 * ALD;                // [QT] sum of squares, [QT] mean
+  double* As = Ks + (size_t)n * KS_LD;               // [2][TMR][ALD]
+  double* colsum = As + 2 * TMR * ALD;               // [QT] sum of squares, [QT] mean
   double* musum = colsum + QT;
   const int q0 = blockIdx.x * QT, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid < QT) { colsum[tid] = 0.0; musum[tid] = 0.0; }
@@ -303,40 +304,51 @@ __global__ void __launch_bounds__(FT) gp_predict_fused_kernel(int kind, int n, i
   }
   __syncthreads();
   if (var != nullptr) {
-    const int wm = (warp >> 1) * 8, wn = (warp & 1) * 16;
-    auto load_stage = [&](int buf, int tm, int k0) {   // 32 rows x 16 doubles = 256 chunks of 16 bytes, one per thread
-      const int r = tid >> 3, cc = (tid & 7) * 2;
-      cp_async16_gp(As + (size_t)buf * 32 * ALD + r * ALD + cc, Linv + (size_t)(tm + r) * n + k0 + cc);
+    // warp tile: 16 rows of L^-1 (two fragments) x 16 queries (two fragments): 4 shared-memory loads per 4 DMMA
+    const int wm = (warp >> 1) * 16, wn = (warp & 1) * 16;
+    auto load_stage = [&](int buf, int tm, int k0) {   // TMR rows x 16 doubles = 512 chunks of 16 bytes, two per thread
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = tid + h * FT, r = c >> 3, cc = (c & 7) * 2;
+        cp_async16_gp(As + (size_t)buf * TMR * ALD + r * ALD + cc, Linv + (size_t)(tm + r) * n + k0 + cc);
+      }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
     double csq[2][2] = {{0.0, 0.0}, {0.0, 0.0}};   // partial sums of squares of this thread's columns (ni, e)
-    for (int tm = 0; tm < n; tm += 32) {
-      double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-      const int nk = (tm + 32) / FK;      // k-steps up to the diagonal block
+    for (int tm = 0; tm < n; tm += TMR) {
+      double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+      const int nk = (tm + TMR) / FK;      // k-steps up to the diagonal block
       load_stage(0, tm, 0);
       for (int ks = 0; ks < nk; ++ks) {
         if (ks + 1 < nk) load_stage((ks + 1) & 1, tm, (ks + 1) * FK);
         else asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 1;" ::: "memory");
         __syncthreads();
-        const double* A0 = As + (size_t)(ks & 1) * 32 * ALD;
+        const double* A0 = As + (size_t)(ks & 1) * TMR * ALD;
         const int k0 = ks * FK;
+        // L^-1 is lower triangular: k-steps right of the warp's last row hold zeros only
+        if (k0 < tm + wm + 16)
 #pragma unroll
         for (int kk = 0; kk < FK; kk += 4) {
-          const double a = A0[(wm + (lane >> 2)) * ALD + kk + (lane & 3)];
+          double av[2], bv[2];
 #pragma unroll
-          for (int ni = 0; ni < 2; ++ni) {
-            const double b = Ks[(size_t)(k0 + kk + (lane & 3)) * KS_LD + wn + ni * 8 + (lane >> 2)];
-            dmma(acc[ni][0], acc[ni][1], a, b);
-          }
+          for (int mi = 0; mi < 2; ++mi) av[mi] = A0[(wm + mi * 8 + (lane >> 2)) * ALD + kk + (lane & 3)];
+#pragma unroll
+          for (int ni = 0; ni < 2; ++ni) bv[ni] = Ks[(size_t)(k0 + kk + (lane & 3)) * KS_LD + wn + ni * 8 + (lane >> 2)];
+#pragma unroll
+          for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 2; ++ni) dmma(acc[mi][ni][0], acc[mi][ni][1], av[mi], bv[ni]);
         }
         __syncthreads();
       }
 #pragma unroll
-      for (int ni = 0; ni < 2; ++ni) {
-        csq[ni][0] += acc[ni][0] * acc[ni][0];
-        csq[ni][1] += acc[ni][1] * acc[ni][1];
-      }
+      for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 2; ++ni) {
+          csq[ni][0] += acc[mi][ni][0] * acc[mi][ni][0];
+          csq[ni][1] += acc[mi][ni][1] * acc[mi][ni][1];
+        }
     }
     // column c = wn + ni * 8 + 2 * (lane & 3) + e is shared by the 8 lanes with equal (lane & 3): reduce over lane >> 2
 #pragma unroll
@@ -454,8 +466,8 @@ int hb_gp_predict_kernel(int kind, int n, int d, int M, const double* X, const d
   if (n <= 0 || d <= 0 || M <= 0 || !X || !Xq || !length_scales || !alpha || !mean || !work) return -1;
   if (var != nullptr && Linv == nullptr) return -1;
   cudaStream_t s = (cudaStream_t)stream;
-  {  // fused path: no K* / V in HBM (n a multiple of 32, d <= 16, the tile fits shared memory)
-    const size_t smem = ((size_t)n * KS_LD + 2 * 32 * (FK + 2) + 2 * QT) * sizeof(double);
+  {  // fused path: no K* / V in HBM (n a multiple of 64, d <= 16, the tile fits shared memory)
+    const size_t smem = ((size_t)n * KS_LD + 2 * TMR * ALD + 2 * QT) * sizeof(double);
     static bool fused_off = getenv("HB_GP_UNFUSED") != nullptr;
     if (!fused_off && var == nullptr && d <= 16) {
       gp_mean_only_kernel<<<(M + 127) / 128, 128, 0, s>>>(kind, n, d, M, X, Xq, length_scales, signal_variance, prior_mean,
@@ -463,7 +475,7 @@ int hb_gp_predict_kernel(int kind, int n, int d, int M, const double* X, const d
       cudaError_t e = cudaGetLastError();
       return e == cudaSuccess ? 0 : (int)e;
     }
-    if (!fused_off && n % 32 == 0 && d <= 16 && smem <= 200 * 1024) {
+    if (!fused_off && n % TMR == 0 && d <= 16 && smem <= 200 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(gp_predict_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
       gp_predict_fused_kernel<<<(M + QT - 1) / QT, FT, smem, s>>>(kind, n, d, M, X, Xq, length_scales, signal_variance,

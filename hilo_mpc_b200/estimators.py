@@ -347,6 +347,7 @@ class ParticleFilter(_Estimator):
         self.last_roughening_noise = None
         self._sample_size = 15  # pf.py:79
         self._pdf = lhsnorm      # pf.py:80: initial sample, process noise and roughening all draw from it
+        self.kernel_variant = 1  # 1: one warp per filter, particles on the lanes (csrc/est_lanes.cuh), 0: one thread per filter
         self._X = None
         self.last_indices = None
         self.last_weights = None
@@ -451,7 +452,7 @@ class ParticleFilter(_Estimator):
         eng.call('pf', B, self._model.dt_value, self._x, P=self._P, X=self._X, y=yt, u=ut, p=pt,
                  Q=eng.tensor(self._Q), R=eng.tensor(self._R), y_pred=ypred, w=eng.tensor(w), v=eng.tensor(v),
                  unif=eng.tensor(uniforms), q=q, idx=idx, work=work, status=status, substeps=self._substeps,
-                 n_particles=ns, t0=self._t)
+                 n_particles=ns, t0=self._t, variant=self.kernel_variant)
         self.last_indices, self.last_weights = idx, q
         if self._roughening:
             self._roughen(torch, roughening_noise)

@@ -151,7 +151,7 @@ def robot_nn_nmpc(N: int = 30, dt: float = 1., integration_method: str = 'colloc
     nmpc = NMPC(model)
     nmpc.horizon = N
     theta = nmpc.create_path_variable(name='theta', u_pf_lb=.1, u_pf_ub=1., u_pf_ref=.5, u_pf_weight=10.,
-                                      theta_guess=0., theta_lb=0., theta_ub=100.)
+                                      theta_guess=0., theta_lb=0.)   # theta_ub = inf: the reference's default
     nmpc.quad_stage_cost.add_states(names=['px', 'py'], weights=[1., 1.],
                                     ref=np.array([30. - 14. * sx.cos(theta), 30. - 16. * sx.sin(theta)], dtype=object),
                                     path_following=True)

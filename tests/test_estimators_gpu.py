@@ -109,6 +109,38 @@ def test_particle_filter_indices_bit_exact(cuda_device):
         np.testing.assert_allclose(x[b].cpu().numpy(), xm, rtol=1e-12)
 
 
+def test_particle_filter_warp_kernel_is_bit_identical_to_thread_per_filter(cuda_device):
+    """One warp per filter with the particles on its lanes (est_lanes.cuh::PfLanes) keeps every running sum of the
+    reference in particle order, so weights, indices, particles and moments equal the one-thread-per-filter kernel bit
+    for bit - also with a particle count that is not a multiple of 32 and on a model with several states."""
+    import torch
+    from hilo_mpc_b200 import PF
+    from hilo_mpc_b200.library import cstr_model
+    rng = np.random.default_rng(11)
+    for model, ns, B in ((scalar_model(), 200, 300), (cstr_model(dt=0.005), 48, 130)):
+        nx, nu = model.n_x, model.n_u
+        x0 = np.array([9.]) if nx == 1 else np.array([2.14, 1.09, 114.2, 112.9])
+        Xp = x0 + (1. if nx == 1 else .05) * rng.standard_normal((B, ns, nx))
+        w = rng.normal(0., .1, size=(B, ns, nx))
+        v = rng.normal(0., .1, size=(B, ns, model.n_y))
+        un = rng.random((B, ns))
+        outs = []
+        for variant in (0, 1):
+            pf = PF(model)
+            pf.setup(n_samples=ns)
+            pf.Q, pf.R = (10., 1.) if nx == 1 else (np.eye(nx) * 1e-2, np.eye(model.n_y))
+            pf.kernel_variant = variant
+            pf.set_initial_guess(np.tile(x0, (B, 1)))
+            pf.set_particles(Xp)
+            y = np.full((B, 1), 3.2) if nx == 1 else np.tile([1.09, 114.2], (B, 1))
+            kw = {} if nu == 0 else dict(u=np.tile([14.19, -1113.5], (B, 1)))
+            x, P = pf.estimate(y=y, w=w, v=v, uniforms=un, **kw)
+            torch.cuda.synchronize()
+            outs.append([t.cpu().numpy().copy() for t in (x, P, pf.last_weights, pf.last_indices, pf.particles)])
+        for a_, b_ in zip(*outs):
+            np.testing.assert_array_equal(a_, b_)
+
+
 def test_pf_resample_entry_matches_numpy_choice(cuda_device):
     """hb_pf_resample vs np.random.choice on the legacy global RNG (pf.py:406), including a large ragged case."""
     import ctypes as C

@@ -84,8 +84,11 @@ def main():
     un = torch.tensor(rng.random((B, n_s)), device=dev)
     yp = torch.tensor(np.full((B, 1), 3.2), device=dev)
     ms = run(lambda: pf.estimate(y=yp, w=w, v=v, uniforms=un))
+    pf.kernel_variant = 0
+    ms_thread = run(lambda: pf.estimate(y=yp, w=w, v=v, uniforms=un))
+    pf.kernel_variant = 1
     byts = B * n_s * 8 * (1 + 1 + 1 + 1 + 1 + 1)   # particles in/out, w, v, uniforms, weights (+ int64 indices)
-    out['pf'] = {'ms_per_step': ms, 'particles': n_s, 'filter_steps_per_s': B / ms * 1e3,
+    out['pf'] = {'ms_per_step': ms, 'ms_per_step_one_thread_per_filter': ms_thread, 'particles': n_s, 'filter_steps_per_s': B / ms * 1e3,
                  'particle_propagations_per_s': B * n_s / ms * 1e3, 'algorithmic_bytes': byts + B * n_s * 8,
                  'gb_per_s': (byts + B * n_s * 8) / ms * 1e-6, 'model': 'scalar benchmark model of tests/test_KFs.py:548-566'}
     print(json.dumps(out))
