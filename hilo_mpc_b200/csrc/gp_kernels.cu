@@ -254,7 +254,7 @@ __global__ void predict_reduce_kernel(int n, int M, const double* __restrict__ K
 //      never stored.
 // 8 warps (one CTA per SM: the Ks tile of n = 512 takes 135 KB), warp w owns the 8 x 16 part (rows 8 (w >> 1), columns
 // 16 (w & 1)) of the 32 x 32 output tile = 2 independent DMMA accumulators; n a multiple of 32 (else the unfused path).
-constexpr int QT = 32, FK = 16, FT = 256, TMR = 64;   // queries per CTA, k-step, threads, rows of L^-1 per outer step
+constexpr int QT = 32, FK = 16, FT = 256, TMR = 64, NSTAGE = 4;   // queries per CTA, k-step, threads, rows of L^-1 per row block, tiles of the cp.async ring
 // leading dimensions = 4 (mod 16) doubles: the 16 lanes of a half-warp read fragment element (k = lane & 3, row or
 // column = lane >> 2) at k * LD + (lane >> 2), i.e. 4 k + (lane >> 2) (mod 16) - sixteen different 8-byte banks
 constexpr int KS_LD = QT + 4, ALD = FK + 4;
@@ -270,8 +270,8 @@ __global__ void __launch_bounds__(FT) gp_predict_fused_kernel(int kind, int n, i
                                                               double* __restrict__ mean, double* __restrict__ var) {
   extern __shared__ __align__(16) double sm[];
   double* Ks = sm;                                   // [n][KS_LD]
-  double* As = Ks + (size_t)n * KS_LD;               // [2][TMR][ALD]
-  double* colsum = As + 2 * TMR * ALD;               // [QT] sum of squares, [QT] mean
+  double* As = Ks + (size_t)n * KS_LD;               // [NSTAGE][TMR][ALD]
+  double* colsum = As + NSTAGE * TMR * ALD;          // [QT] sum of squares, [QT] mean
   double* musum = colsum + QT;
   const int q0 = blockIdx.x * QT, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid < QT) { colsum[tid] = 0.0; musum[tid] = 0.0; }
@@ -279,15 +279,19 @@ __global__ void __launch_bounds__(FT) gp_predict_fused_kernel(int kind, int n, i
   // ---- 1. cross covariance tile + mean: thread (q = tid % 32, rows tid / 32, +8, ...)
   {
     const int q = tid & 31, gq = q0 + q;
-    double xq[16];
+    double xq[16], il[16];   // reciprocal length scales once per thread: an fp64 division per (training point, feature) was
+                             // half of this kernel's time
 #pragma unroll
-    for (int k = 0; k < 16; ++k) xq[k] = (k < d && gq < M) ? Xq[(size_t)k * M + gq] / ls[k] : 0.0;
+    for (int k = 0; k < 16; ++k) {
+      il[k] = (k < d) ? 1.0 / ls[k] : 0.0;
+      xq[k] = (k < d && gq < M) ? Xq[(size_t)k * M + gq] * il[k] : 0.0;
+    }
     double mu = 0.0;
     for (int i = tid >> 5; i < n; i += FT / 32) {
       double d2 = 0.0;
 #pragma unroll
       for (int k = 0; k < 16; ++k)
-        if (k < d) { const double r = X[(size_t)k * n + i] / ls[k] - xq[k]; d2 += r * r; }
+        if (k < d) { const double r = __ldg(X + (size_t)k * n + i) * il[k] - xq[k]; d2 += r * r; }
       double v;
       if (kind == 0) v = sf2 * exp(-0.5 * d2);
       else {
@@ -312,35 +316,49 @@ __global__ void __launch_bounds__(FT) gp_predict_fused_kernel(int kind, int n, i
         const int c = tid + h * FT, r = c >> 3, cc = (c & 7) * 2;
         cp_async16_gp(As + (size_t)buf * TMR * ALD + r * ALD + cc, Linv + (size_t)(tm + r) * n + k0 + cc);
       }
-      asm volatile("cp.async.commit_group;" ::: "memory");
     };
+    // ONE pipeline over all (row block tm, k-step ks) pairs of the lower triangle, NSTAGE - 1 tiles in flight: the CTA
+    // is alone on its SM (the K* tile takes the shared memory), so only depth hides the L2 latency of the L^-1 tiles,
+    // and a pipeline that drained at every row block would pay that latency n / TMR times
     double csq[2][2] = {{0.0, 0.0}, {0.0, 0.0}};   // partial sums of squares of this thread's columns (ni, e)
+    double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+    int ltm = 0, lks = 0, lstep = 0;                // load cursor: row block, k-step, tile number
+    auto issue_next = [&]() {
+      if (ltm < n) {
+        load_stage(lstep % NSTAGE, ltm, lks * FK);
+        ++lstep;
+        if (++lks == (ltm + TMR) / FK) { lks = 0; ltm += TMR; }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");   // (possibly empty) group: the count stays uniform
+    };
+    int step = 0;
     for (int tm = 0; tm < n; tm += TMR) {
-      double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
       const int nk = (tm + TMR) / FK;      // k-steps up to the diagonal block
-      load_stage(0, tm, 0);
-      for (int ks = 0; ks < nk; ++ks) {
-        if (ks + 1 < nk) load_stage((ks + 1) & 1, tm, (ks + 1) * FK);
-        else asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
-        __syncthreads();
-        const double* A0 = As + (size_t)(ks & 1) * TMR * ALD;
+      for (int ks = 0; ks < nk; ++ks, ++step) {
+        if (step == 0) {
+#pragma unroll
+          for (int st = 0; st < NSTAGE - 1; ++st) issue_next();
+        }
+        asm volatile("cp.async.wait_group %0;" ::"n"(NSTAGE - 2) : "memory");
+        __syncthreads();       // tile `step` has landed for everybody; everybody is done with tile step - 1
+        issue_next();          // ... whose buffer takes tile step + NSTAGE - 1
+        const double* A0 = As + (size_t)(step % NSTAGE) * TMR * ALD;
         const int k0 = ks * FK;
         // L^-1 is lower triangular: k-steps right of the warp's last row hold zeros only
-        if (k0 < tm + wm + 16)
+        if (k0 < tm + wm + 16) {
 #pragma unroll
-        for (int kk = 0; kk < FK; kk += 4) {
-          double av[2], bv[2];
+          for (int kk = 0; kk < FK; kk += 4) {
+            double av[2], bv[2];
 #pragma unroll
-          for (int mi = 0; mi < 2; ++mi) av[mi] = A0[(wm + mi * 8 + (lane >> 2)) * ALD + kk + (lane & 3)];
+            for (int mi = 0; mi < 2; ++mi) av[mi] = A0[(wm + mi * 8 + (lane >> 2)) * ALD + kk + (lane & 3)];
 #pragma unroll
-          for (int ni = 0; ni < 2; ++ni) bv[ni] = Ks[(size_t)(k0 + kk + (lane & 3)) * KS_LD + wn + ni * 8 + (lane >> 2)];
+            for (int ni = 0; ni < 2; ++ni) bv[ni] = Ks[(size_t)(k0 + kk + (lane & 3)) * KS_LD + wn + ni * 8 + (lane >> 2)];
 #pragma unroll
-          for (int mi = 0; mi < 2; ++mi)
+            for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-            for (int ni = 0; ni < 2; ++ni) dmma(acc[mi][ni][0], acc[mi][ni][1], av[mi], bv[ni]);
+              for (int ni = 0; ni < 2; ++ni) dmma(acc[mi][ni][0], acc[mi][ni][1], av[mi], bv[ni]);
+          }
         }
-        __syncthreads();
       }
 #pragma unroll
       for (int mi = 0; mi < 2; ++mi)
@@ -348,8 +366,10 @@ __global__ void __launch_bounds__(FT) gp_predict_fused_kernel(int kind, int n, i
         for (int ni = 0; ni < 2; ++ni) {
           csq[ni][0] += acc[mi][ni][0] * acc[mi][ni][0];
           csq[ni][1] += acc[mi][ni][1] * acc[mi][ni][1];
+          acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0;
         }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     // column c = wn + ni * 8 + 2 * (lane & 3) + e is shared by the 8 lanes with equal (lane & 3): reduce over lane >> 2
 #pragma unroll
     for (int ni = 0; ni < 2; ++ni)
@@ -467,7 +487,7 @@ int hb_gp_predict_kernel(int kind, int n, int d, int M, const double* X, const d
   if (var != nullptr && Linv == nullptr) return -1;
   cudaStream_t s = (cudaStream_t)stream;
   {  // fused path: no K* / V in HBM (n a multiple of 64, d <= 16, the tile fits shared memory)
-    const size_t smem = ((size_t)n * KS_LD + 2 * TMR * ALD + 2 * QT) * sizeof(double);
+    const size_t smem = ((size_t)n * KS_LD + NSTAGE * TMR * ALD + 2 * QT) * sizeof(double);
     static bool fused_off = getenv("HB_GP_UNFUSED") != nullptr;
     if (!fused_off && var == nullptr && d <= 16) {
       gp_mean_only_kernel<<<(M + 127) / 128, 128, 0, s>>>(kind, n, d, M, X, Xq, length_scales, signal_variance, prior_mean,
@@ -475,7 +495,7 @@ int hb_gp_predict_kernel(int kind, int n, int d, int M, const double* X, const d
       cudaError_t e = cudaGetLastError();
       return e == cudaSuccess ? 0 : (int)e;
     }
-    if (!fused_off && n % TMR == 0 && d <= 16 && smem <= 200 * 1024) {
+    if (!fused_off && n % TMR == 0 && d <= 16 && smem <= 220 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(gp_predict_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
       gp_predict_fused_kernel<<<(M + QT - 1) / QT, FT, smem, s>>>(kind, n, d, M, X, Xq, length_scales, signal_variance,
