@@ -306,23 +306,43 @@ def _cpu_warm(config):
     return 0
 
 
+CPU_SAMPLE_DEADLINE_S = {2: 150., 3: 150., 4: 150., 5: 300.}   # wall-clock bound of one CPU sample (cold solves included)
+
+
 def cpu_sample(config, n_instances, steps, n_procs, rank=0):
     """Times the oracle on the first ``n_instances`` instances of the workload for ``steps`` warm closed-loop steps each
-    (after an untimed cold first solve) with ``n_procs`` worker processes.  Returns (units_per_s, seconds of the timed
-    solves on the slowest worker, converged fraction, wall seconds incl. the cold solves)."""
+    (after an untimed cold first solve) with ``n_procs`` worker processes, one library thread each.  Workers that have
+    not finished at the sample's deadline are dropped (the arm must end within minutes whatever the host): the rate is
+    (mean rate of the finished workers) x ``n_procs``.  Returns (units_per_s, seconds of the timed solves on the slowest
+    finished worker, converged fraction, wall seconds incl. the cold solves)."""
+    from threadpoolctl import threadpool_limits
     idx = np.arange(n_instances)
-    _cpu_nlp(config)   # in the parent: forked workers inherit the problem (config 3 fits its GP on the device here)
-    t_wall = time.perf_counter()
-    if n_procs <= 1:
-        done, ok, el = _cpu_closed_loop((config, idx, steps, rank))
-    else:
+    with threadpool_limits(limits=1):   # also in the parent: no library thread pool may exist when the workers are forked
+        _cpu_nlp(config)   # in the parent: forked workers inherit the problem (config 3 fits its GP on the device here)
+        t_wall = time.perf_counter()
+        if n_procs <= 1:
+            done, ok, el = _cpu_closed_loop((config, idx, steps, rank))
+            return done / el, el, ok / max(done, 1), time.perf_counter() - t_wall
         import multiprocessing as mp
         chunks = [c for c in np.array_split(idx, n_procs) if len(c)]
-        with mp.get_context('fork').Pool(len(chunks)) as pool:
-            res = pool.map(_cpu_closed_loop, [(config, c, steps, rank) for c in chunks])
-        done, ok = sum(r[0] for r in res), sum(r[1] for r in res)
-        el = max(r[2] for r in res)
-    return done / el, el, ok / max(done, 1), time.perf_counter() - t_wall
+        res = []
+        pool = mp.get_context('fork').Pool(len(chunks))
+        try:
+            it = pool.imap_unordered(_cpu_closed_loop, [(config, c, steps, rank) for c in chunks])
+            deadline = t_wall + CPU_SAMPLE_DEADLINE_S[config]
+            for _ in chunks:
+                try:
+                    res.append(it.next(timeout=max(1., deadline - time.perf_counter())))
+                except mp.TimeoutError:
+                    break
+        finally:
+            pool.terminate()
+            pool.join()
+    if not res:
+        raise RuntimeError(f'no CPU worker finished within {CPU_SAMPLE_DEADLINE_S[config]:.0f} s')
+    done, ok = sum(r[0] for r in res), sum(r[1] for r in res)
+    rate = len(chunks) * float(np.mean([r[0] / r[2] for r in res]))
+    return rate, max(r[2] for r in res), ok / max(done, 1), time.perf_counter() - t_wall
 
 
 def run_reference(args):
@@ -334,16 +354,16 @@ def run_reference(args):
     # config 3 needs the GP fitted on a device (hb_gp_fit); the CPU arm then differs from config 2 only by the GP terms
     per_worker_steps = {2: 4, 3: 3, 4: 4, 5: 2}[args.config]
     n_inst = cores
-    times, done_total = [], 0
+    times, rates = [], []
     t_budget = time.perf_counter()
     for k in range(max(1, args.steps // 10)):
         v, el, okf, wall = cpu_sample(args.config, n_inst, per_worker_steps, cores)
-        times.append(el)
-        done_total += n_inst * per_worker_steps
+        times.append(n_inst * per_worker_steps / v)   # seconds one sample takes at the measured rate
+        rates.append(v)
         if time.perf_counter() - t_budget > 30.:   # bounded sample: the whole arm stays within a few minutes
             break
     total = float(np.sum(times))
-    value = done_total / total
+    value = float(np.mean(rates))
     line = {
         'metric': w['metric'], 'value': value, 'unit': w['unit'], 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': 1e3 * total / max(1, len(times)), 'higher_is_better': True,
