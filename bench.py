@@ -342,6 +342,7 @@ def cpu_sample(config, n_instances, steps, n_procs, rank=0):
         raise RuntimeError(f'no CPU worker finished within {CPU_SAMPLE_DEADLINE_S[config]:.0f} s')
     done, ok = sum(r[0] for r in res), sum(r[1] for r in res)
     rate = len(chunks) * float(np.mean([r[0] / r[2] for r in res]))
+    cpu_sample.last_finished = (len(res), len(chunks))
     return rate, max(r[2] for r in res), ok / max(done, 1), time.perf_counter() - t_wall
 
 
@@ -364,6 +365,7 @@ def run_reference(args):
             break
     total = float(np.sum(times))
     value = float(np.mean(rates))
+    fin = getattr(cpu_sample, 'last_finished', (cores, cores))
     line = {
         'metric': w['metric'], 'value': value, 'unit': w['unit'], 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': 1e3 * total / max(1, len(times)), 'higher_is_better': True,
@@ -375,7 +377,7 @@ def run_reference(args):
                            'which the GPU arm also keeps out of its timed region), one instance per worker process'},
         'cpu_baseline': {'value': value, 'unit': w['unit'], 'cores': cores, 'kind': 'port',
                          'sample': f'{n_inst} instances x {per_worker_steps} closed-loop steps x {len(times)} repeats, '
-                                   f'{cores} processes; NumPy/SciPy restatement of the reference\'s flat NLP + IPOPT '
+                                   f'{cores} processes ({fin[0]} of {fin[1]} finished within the sample deadline); NumPy/SciPy restatement of the reference\'s flat NLP + IPOPT '
                                    f'algorithm (the reference itself is not installable here: no CasADi)'},
         'e2e': {'value': value, 'unit': w['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
