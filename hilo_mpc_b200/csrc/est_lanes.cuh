@@ -174,6 +174,10 @@ struct PfLanes {
       Ys[k] = Y;
     }
     __syncwarp();
+    if (!a.do_update) {                          // prediction pass only (see PfStep)
+      if (lane == 0) a.status[b] = 0;
+      return;
+    }
     // ---- 2. weights: q / sum(q), cdf = cumsum(q) / cdf[-1]  (the two running sums in particle order)
     double qsum = 0.0;
     if (lane == 0)

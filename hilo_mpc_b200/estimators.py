@@ -340,8 +340,8 @@ class ParticleFilter(_Estimator):
     def __init__(self, model, id=None, name=None, plot_backend=None, variant=None, roughening=False,
                  prior_editing=False, K=.2):
         super().__init__(model, id=id, name=name, plot_backend=plot_backend)
-        if prior_editing:
-            raise NotImplementedError("Prior editing is not supported by the B200 engine yet")
+        self._prior_editing = bool(prior_editing)
+        self.last_prior_editing_rounds = 0
         self._roughening = bool(roughening)
         self._roughening_tuning_param = float(K)   # pf.py:72-76
         self.last_roughening_noise = None
@@ -420,6 +420,33 @@ class ParticleFilter(_Estimator):
         self._x.copy_(mean)
         self._P.copy_(Xc.transpose(1, 2) @ Xc / (ns - 1))              # np.cov: unbiased
 
+    def _edit_prior(self, torch, B, ns, nx, yt, work, common, max_rounds: int = 1000):
+        """Prior editing (pf.py:378-398): particles whose predicted noisy measurement is more than six standard
+        deviations away from the measurement are jittered before the propagation - range of the particle set x K x
+        n_r^(-1/n_x), drawn from the filter's density in the reference's order - and the prediction pass (kernel call with
+        ``do_update=0``: nothing but the predicted measurements is produced) is repeated until none is left.  The check
+        runs on the device; only the count per filter and the jittered particles cross the bus."""
+        eng = self._engine
+        sig6 = 6. * float(np.sqrt(np.asarray(self._R, dtype=float).reshape(-1)[0]))
+        unif0 = torch.zeros(B, ns, dtype=torch.float64, device=eng.device)
+        Ys = work[B * ns * nx + B * ns:B * ns * nx + 2 * B * ns].view(B, ns)   # csrc/est_module.cuh: Xs | cdf | Ys
+        self.last_prior_editing_rounds = 0
+        for _ in range(max_rounds):
+            eng.call('pf', B, self._model.dt_value, self._x, X=self._X, unif=unif0, do_update=False, **common)
+            need = (yt[:, :1] - Ys).abs() > sig6
+            n_r = need.sum(dim=1).cpu().numpy()
+            if not n_r.any():
+                return
+            self.last_prior_editing_rounds += 1
+            Xh = self._X.cpu().numpy()
+            mask = need.cpu().numpy()
+            for b in np.nonzero(n_r)[0]:
+                spread = Xh[b].max(axis=0) - Xh[b].min(axis=0)
+                cov = self._roughening_tuning_param * np.diag(spread) * float(n_r[b]) ** (-1. / nx)
+                Xh[b, mask[b]] += self._draw(np.zeros(nx), cov, int(n_r[b]))
+            self._X = eng.tensor(Xh)
+        raise RuntimeError("Prior editing did not terminate: the measurement is out of reach of the particle set")
+
     def estimate(self, y=None, u=None, p=None, w=None, v=None, uniforms=None, roughening_noise=None, **kwargs):
         """One filter step. The random draws follow the reference (legacy NumPy global RNG, pf.py:363-365, 406, 413) unless
         ``w`` (process noise ``(B, n_s, n_x)``), ``v`` (measurement noise), ``uniforms`` and (with roughening)
@@ -441,18 +468,21 @@ class ParticleFilter(_Estimator):
             w = np.stack([self._draw(np.zeros(nx), self._Q, ns) for _ in range(B)])   # pf.py:363
         if v is None:
             v = np.stack([(np.sqrt(self._R) @ np.random.randn(ny, ns)).T for _ in range(B)])  # pf.py:365
-        if uniforms is None:
-            uniforms = np.stack([np.random.random_sample(ns) for _ in range(B)])  # what np.random.choice draws
         yt, ut, pt = self._inputs(y, u, p, B)
         q = torch.zeros(B, ns, dtype=torch.float64, device=eng.device)
         idx = torch.zeros(B, ns, dtype=torch.int64, device=eng.device)
         ypred = torch.zeros(B, ny, dtype=torch.float64, device=eng.device)
         status = torch.zeros(B, dtype=torch.int32, device=eng.device)
         work = torch.empty(eng.work_doubles(B, ns), dtype=torch.float64, device=eng.device)
-        eng.call('pf', B, self._model.dt_value, self._x, P=self._P, X=self._X, y=yt, u=ut, p=pt,
-                 Q=eng.tensor(self._Q), R=eng.tensor(self._R), y_pred=ypred, w=eng.tensor(w), v=eng.tensor(v),
-                 unif=eng.tensor(uniforms), q=q, idx=idx, work=work, status=status, substeps=self._substeps,
-                 n_particles=ns, t0=self._t, variant=self.kernel_variant)
+        wt, vt = eng.tensor(w), eng.tensor(v)
+        common = dict(P=self._P, y=yt, u=ut, p=pt, Q=eng.tensor(self._Q), R=eng.tensor(self._R), y_pred=ypred, w=wt, v=vt,
+                      q=q, idx=idx, work=work, status=status, substeps=self._substeps, n_particles=ns, t0=self._t,
+                      variant=self.kernel_variant)
+        if self._prior_editing:
+            self._edit_prior(torch, B, ns, nx, yt, work, common)
+        if uniforms is None:   # drawn after the prior editing, like the reference (pf.py:406)
+            uniforms = np.stack([np.random.random_sample(ns) for _ in range(B)])  # what np.random.choice draws
+        eng.call('pf', B, self._model.dt_value, self._x, X=self._X, unif=eng.tensor(uniforms), **common)
         self.last_indices, self.last_weights = idx, q
         if self._roughening:
             self._roughen(torch, roughening_noise)

@@ -196,6 +196,7 @@ typedef struct hb_est_call {
   int* status;               /* out [B]: 0 ok, -1 numerical failure                                               */
   void* stream;
   int variant;               /* UKF: 1 (default of the Python shell) one lane per sigma point, reductions by warp shuffles;
+                                PF: 1 one warp per filter, particles on the lanes (bit-identical results);
                                 0 one thread per filter                                                           */
 } hb_est_call;
 

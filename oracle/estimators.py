@@ -134,6 +134,30 @@ def pf_step(f, h, X, y, u, p, w, v, R, uniforms, dt=1., discrete=True, substeps=
     return Xr.sum(axis=1) / ns, np.cov(Xr), Xr, q, idx
 
 
+def pf_prior_editing(f, h, X, y, u, p, w, v, R, K, pdf, dt=1., discrete=True, substeps=10, max_rounds=1000):
+    """pf.py:378-398, restated: particles whose predicted noisy measurement lies more than six standard deviations from
+    ``y`` are jittered BEFORE the propagation (range of all particles x K x n_r^(-1/n), density ``pdf(mu, cov, n) ->
+    (n, n_x)``) and the prediction is repeated until none is left.  ``X``: n x ns.  Returns the edited particle set."""
+    X = np.array(X, dtype=float)
+    n = X.shape[0]
+    sigma = np.sqrt(R)
+
+    def predicted(Xc):
+        Xp = np.stack([f(Xc[:, k], u, p) if discrete else rk4(f, Xc[:, k], u, p, dt, substeps) for k in range(Xc.shape[1])],
+                      axis=1)
+        return np.stack([np.atleast_1d(h(Xp[:, k], u, p)) for k in range(Xc.shape[1])], axis=1) + v
+
+    for _ in range(max_rounds):
+        need = (np.abs(np.atleast_1d(y)[:, None] - predicted(X)) > 6 * sigma)[0]
+        n_r = int(need.sum())
+        if n_r == 0:
+            return X
+        rng_x = X.max(axis=1) - X.min(axis=1)
+        dx = pdf(np.zeros(n), K * np.diag(rng_x) * n_r ** (-1. / n), n_r)
+        X[:, np.where(need)[0]] += np.asarray(dx).T
+    raise RuntimeError("prior editing did not terminate")
+
+
 def lhsnorm(mu, sigma, n, rng=np.random):
     """pf.py:425-447, restated: Latin-hypercube normal sample, ``(n, n_mu)``; ``rng`` = the legacy global RNG module."""
     from scipy.stats import norm

@@ -241,6 +241,38 @@ def test_particle_filter_roughening_matches_oracle(cuda_device):
     np.testing.assert_allclose(np.asarray(pf1.solution['x'])[:, -1], xm1, rtol=1e-11)
 
 
+def test_particle_filter_prior_editing_matches_oracle(cuda_device):
+    """pf.py:378-398: particles whose predicted measurement is more than 6 sigma off are jittered before the propagation
+    until none is left.  Legacy global RNG seeded: the engine must draw in the reference's order (process noise,
+    measurement noise, editing jitter round by round, resampling uniforms) and equal the oracle's restatement."""
+    from hilo_mpc_b200 import PF
+    from oracle import estimators as est
+    f, hfun = (lambda x_, u, p: x_ / 2 + 25 * x_ / (1 + x_ ** 2)), (lambda x_, u, p: x_ ** 2 / 20)
+    ns, R, K = 40, .04, .5
+    rng = np.random.default_rng(5)
+    X0 = rng.normal(9., 2.5, size=(ns, 1))
+    y = np.array([3.6])
+    for variant in (1, 0):
+        pf = PF(scalar_model(), prior_editing=True, K=K)
+        pf.kernel_variant = variant
+        pf.setup(n_samples=ns)
+        pf.Q, pf.R = 1., R
+        pf.set_initial_guess(np.array([9.]))
+        pf.set_particles(X0.T)
+        np.random.seed(123)
+        pf.estimate(y=y)
+        assert pf.last_prior_editing_rounds >= 1          # the case does exercise the loop
+        np.random.seed(123)
+        w1 = est.lhsnorm(np.zeros(1), np.array([[1.]]), ns)
+        v1 = (np.sqrt(np.array([[R]])) @ np.random.randn(1, ns)).T
+        Xe = est.pf_prior_editing(f, hfun, X0.T, y, None, None, w1.T, v1.T, np.array([[R]]), K, est.lhsnorm)
+        u1 = np.random.random_sample(ns)
+        xm, Pm, Xr, q1, i1 = est.pf_step(f, hfun, Xe, y, None, None, w1.T, v1.T, np.array([[R]]), u1)
+        np.testing.assert_array_equal(pf.last_indices[0].cpu().numpy(), i1)
+        np.testing.assert_allclose(pf.particles[0].cpu().numpy(), Xr.T, rtol=1e-11)
+        np.testing.assert_allclose(np.asarray(pf.solution['x'])[:, -1], xm, rtol=1e-11)
+
+
 def test_ukf_bioreactor_sigma_point_golden(cuda_device):
     """tests/test_KFs.py:716-756 through the reference's positional predict / update pass-throughs (kf.py:309-325)."""
     from hilo_mpc_b200 import UKF
