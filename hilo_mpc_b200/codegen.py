@@ -122,9 +122,21 @@ class OcpGenerator:
             Hf = sx.hessian(sx.dot(lamf, s.ode), np.concatenate([s.x, s.u]))
         else:
             Hf = np.full((s.nx + s.nu, s.nx + s.nu), sx.Expr.const(0.), dtype=object)
-        L.append(_indent(sx.Function('f_hess', ins + [('lamf', lamf)],
-                                     [('hxx', Hf[:s.nx, :s.nx]), ('hux', Hf[s.nx:, :s.nx]), ('huu', Hf[s.nx:, s.nx:])])
-                         .c_source(QUAL, scalar_inputs=scal)))
+        f_hess = sx.Function('f_hess', ins + [('lamf', lamf)],
+                             [('hxx', Hf[:s.nx, :s.nx]), ('hux', Hf[s.nx:, :s.nx]), ('huu', Hf[s.nx:, s.nx:])])
+        L.append(_indent(f_hess.c_source(QUAL, scalar_inputs=scal)))
+        # Call nodes (GP mean, MLP layer) are loops over a table; Jacobian and Hessian of a collocation point are evaluated
+        # at the same point one after the other, so the Jacobian pass evaluates the loop once at order 2 and leaves its
+        # outputs in a per-thread cache the Hessian pass reads (csrc/eval_quad.cuh, OcpEval): one walk instead of two
+        cache = dict(mode='store', slots={}, size=0)
+        if ex and s.method == 'collocation' and sx.gp_tables_used(list(s.ode)):
+            src_jac = sx.Function('f_jac', ins, [('f', s.ode), ('fx', fx), ('fu', fu)]).c_source(
+                QUAL, scalar_inputs=scal, name='f_jac_c', call_cache=cache)
+            if cache['size'] > 0:
+                L.append(_indent(src_jac))
+                L.append(_indent(f_hess.c_source(QUAL, scalar_inputs=scal, name='f_hess_c',
+                                                 call_cache=dict(mode='load', slots=cache['slots'], size=cache['size']))))
+        L.append(f"  static constexpr int NCALLCACHE = {cache['size']};")
         # ---- Lagrange term
         lx, lu, lxx, lux, luu = cost_derivatives(s.lag, s.lag_ls, s.lag_rest, s.x, s.u, exact=ex)
         L.append(_indent(sx.Function('lag_raw', ins, [('l', [s.lag])]).c_source(QUAL, scalar_inputs=scal)))

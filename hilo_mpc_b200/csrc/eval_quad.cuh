@@ -229,6 +229,9 @@ struct EvalQuad {
       phi += bs.value(mu);
     }
     // ---------------------------------------------------------------- 1b. derivatives at the collocation points
+    // outputs of the model's call nodes (GP / MLP loops) at this lane's point: filled by the Jacobian pass, read by the
+    // Hessian pass further down (thread-local memory; one walk over the table instead of two)
+    double cc[P::NCALLCACHE > 0 ? P::NCALLCACHE : 1];
     if (q < D) {
       double cb = 0.0, ctau = 0.0;
 #pragma unroll
@@ -236,7 +239,8 @@ struct EvalQuad {
         if (q == i) { cb = P::CB(i + 1); ctau = P::CTAU(i); }
       const double ti = t + dt * ctau;
       double* F = S + oF + q * FSZ;
-      P::f_jac(Xq, u, sp, ti, dt, F, F + NX, F + NX + NX * NX);
+      if constexpr (P::NCALLCACHE > 0) P::f_jac_c(Xq, u, sp, ti, dt, F, F + NX, F + NX + NX * NX, cc);
+      else P::f_jac(Xq, u, sp, ti, dt, F, F + NX, F + NX + NX * NX);
       double* L = S + oL + q * LSZ;
       double l = 0.0, lx[NX], lu[NU], lxx[NX * NX], lux[NU * NX], luu[NU * NU];
       if (with_lag && !P::OBJ_DISCRETE) {
@@ -366,7 +370,8 @@ struct EvalQuad {
         double nu[NX], hxx[NX * NX], hux[NU * NX], huu[NU * NU];
 #pragma unroll
         for (int rr = 0; rr < NX; ++rr) nu[rr] = dt * S[oNU + q * NX + rr];
-        P::f_hess(Xq, u, sp, t + dt * ctau, dt, nu, hxx, hux, huu);
+        if constexpr (P::NCALLCACHE > 0) P::f_hess_c(Xq, u, sp, t + dt * ctau, dt, nu, hxx, hux, huu, cc);
+        else P::f_hess(Xq, u, sp, t + dt * ctau, dt, nu, hxx, hux, huu);
         double* L = S + oL + q * LSZ;
 #pragma unroll
         for (int j = 0; j < NX * NX; ++j) L[1 + NX + NU + j] += hxx[j];

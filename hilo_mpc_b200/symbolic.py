@@ -773,8 +773,24 @@ def _c_const(v: float) -> str:
     return r
 
 
-def _emit(outputs: List[Expr], inputs: Dict[int, str], lang: str, tmp: str = 't') -> Tuple[List[str], List[str]]:
-    """Straight-line code for ``outputs``; returns (statements, output operand strings)."""
+def _cache_copy(var: str, off: int, nout: int, load: bool) -> str:
+    """C statement that moves the outputs of one call group from / to the call cache ``cc`` (a rolled loop: the cache is
+    meant to live in thread-local memory, not in registers, between the two functions)."""
+    loop = f'for (int e_ = 0; e_ < {nout}; ++e_)'
+    if load:
+        return f'double {var}[{nout}]; {loop} {var}[e_] = cc[{off} + e_];'
+    return f'{loop} cc[{off} + e_] = {var}[e_];'
+
+
+def _emit(outputs: List[Expr], inputs: Dict[int, str], lang: str, tmp: str = 't',
+          call_cache: Optional[dict] = None) -> Tuple[List[str], List[str]]:
+    """Straight-line code for ``outputs``; returns (statements, output operand strings).
+
+    ``call_cache`` (C only) shares the results of call nodes (GP / MLP loops) between two generated functions that are
+    evaluated at the same point one after the other - Jacobian first, Lagrangian Hessian later: with ``mode='store'``
+    every call group is evaluated at derivative order 2 whatever this function needs and its outputs are copied to the
+    array ``cc`` (slots recorded in ``call_cache['slots']``, total in ``call_cache['size']``); with ``mode='load'`` groups
+    found in the slots read ``cc`` instead of walking the table again."""
     order = topo_sort(outputs)
     uses: Dict[int, int] = {}
     for node in order:
@@ -809,9 +825,18 @@ def _emit(outputs: List[Expr], inputs: Dict[int, str], lang: str, tmp: str = 't'
                 nz, nh, no = t['nz'], t['nh'], t['no']
                 var = f'{tmp}mlp{len(gp_groups)}'
                 if lang == 'c':
+                    if call_cache is not None and call_cache['mode'] == 'store':
+                        order = 2
                     nout = no + (no * nz if order >= 1 else 0) + (no * nz * (nz + 1) // 2 if order >= 2 else 0)
-                    lines.append(f'double {var}[{nout}]; {{ const double {var}z[{nz}] = {{{", ".join(a)}}}; '
-                                 f'hb::mlp1_eval<{nz}, {nh}, {no}, {order}, {t["act"]}>(hb_mlp_tab_{mid}, {var}z, {var}); }}')
+                    if call_cache is not None and call_cache['mode'] == 'load' and key in call_cache['slots']:
+                        lines.append(_cache_copy(var, *call_cache['slots'][key], load=True))
+                    else:
+                        lines.append(f'double {var}[{nout}]; {{ const double {var}z[{nz}] = {{{", ".join(a)}}}; '
+                                     f'hb::mlp1_eval<{nz}, {nh}, {no}, {order}, {t["act"]}>(hb_mlp_tab_{mid}, {var}z, {var}); }}')
+                        if call_cache is not None and call_cache['mode'] == 'store':
+                            call_cache['slots'][key] = (call_cache['size'], nout)
+                            lines.append(_cache_copy(var, call_cache['size'], nout, load=False))
+                            call_cache['size'] += nout
                 else:
                     lines.append(f'{var} = _mlp_numpy({mid!r}, {order}, {", ".join(a)})')
                 gp_groups[key] = var
@@ -830,10 +855,19 @@ def _emit(outputs: List[Expr], inputs: Dict[int, str], lang: str, tmp: str = 't'
                 dd = GP_TABLES[gid]['d']
                 var = f'{tmp}gp{len(gp_groups)}'
                 if lang == 'c':
+                    if call_cache is not None and call_cache['mode'] == 'store':
+                        order = 2
                     nout = 1 + (dd if order >= 1 else 0) + (dd * (dd + 1) // 2 if order >= 2 else 0)
-                    lines.append(f'double {var}[{nout}]; {{ const double {var}x[{dd}] = {{{", ".join(a)}}}; '
-                                 f'hb::gp_se_eval<{dd}, {order}>(hb_gp_tab_{gid}, {GP_TABLES[gid]["n"]}, hb_gp_ils_{gid}, '
-                                 f'{var}x, {var}); }}')
+                    if call_cache is not None and call_cache['mode'] == 'load' and key in call_cache['slots']:
+                        lines.append(_cache_copy(var, *call_cache['slots'][key], load=True))
+                    else:
+                        lines.append(f'double {var}[{nout}]; {{ const double {var}x[{dd}] = {{{", ".join(a)}}}; '
+                                     f'hb::gp_se_eval<{dd}, {order}>(hb_gp_tab_{gid}, {GP_TABLES[gid]["n"]}, hb_gp_ils_{gid}, '
+                                     f'{var}x, {var}); }}')
+                        if call_cache is not None and call_cache['mode'] == 'store':
+                            call_cache['slots'][key] = (call_cache['size'], nout)
+                            lines.append(_cache_copy(var, call_cache['size'], nout, load=False))
+                            call_cache['size'] += nout
                 else:
                     lines.append(f'{var} = _gp_numpy({gid!r}, {order}, {", ".join(a)})')
                 gp_groups[key] = var
@@ -934,9 +968,10 @@ class Function:
 
     # -- CUDA / C emission
     def c_source(self, qualifiers: str = '__host__ __device__ __forceinline__', real: str = 'double',
-                 scalar_inputs: Sequence[str] = (), name: Optional[str] = None) -> str:
+                 scalar_inputs: Sequence[str] = (), name: Optional[str] = None, call_cache: Optional[dict] = None) -> str:
         """Emit ``void name(const real* in0, ..., real* out0, ...)``; 2-D outputs are stored row-major. Inputs listed
-        in ``scalar_inputs`` (length-1 vectors) are passed by value."""
+        in ``scalar_inputs`` (length-1 vectors) are passed by value.  With ``call_cache`` (see ``_emit``) the function
+        gets a last argument ``cc``: the call cache it fills (``mode='store'``) or reads (``mode='load'``)."""
         in_map: Dict[int, str] = {}
         sig = []
         for iname, vec in zip(self.in_names, self.inputs):
@@ -950,8 +985,10 @@ class Function:
                     in_map[s.id] = f'{iname}[{k}]'
                 sig.append(f'const {real}* __restrict__ {iname}')
         flat = [o for vec in self.outputs for o in vec]
-        lines, outs = _emit(flat, in_map, 'c')
+        lines, outs = _emit(flat, in_map, 'c', call_cache=call_cache)
         sig += [f'{real}* __restrict__ {n}' for n in self.out_names]
+        if call_cache is not None:
+            sig.append(f'{real}* __restrict__ cc' if call_cache['mode'] == 'store' else f'const {real}* __restrict__ cc')
         src = [f"{qualifiers} void {name or self.name}({', '.join(sig)})", '{']
         src += ['    ' + ln for ln in lines]
         pos = 0

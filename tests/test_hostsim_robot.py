@@ -1,5 +1,6 @@
 """Config 5 ingredients on the CPU: MLP graph (a9) inside the model + path-following augmentation (mpc.py:1173-1204)."""
 import numpy as np
+import pytest
 
 from hilo_mpc_b200.codegen import OcpGenerator
 from hilo_mpc_b200.examples import bicycle_ann, robot_initial_states, robot_nn_nmpc
@@ -24,13 +25,18 @@ def test_mlp_graph_matches_numeric_forward_pass_and_true_dynamics():
     assert np.corrcoef(net.predict(Z).ravel(), true.ravel())[0, 1] > .98
 
 
-def test_path_following_nn_nmpc_host_kernels_match_oracle():
+@pytest.mark.parametrize('hidden', [8, 16])
+def test_path_following_nn_nmpc_host_kernels_match_oracle(hidden):
+    # hidden = 8: the network is unrolled into the expression graph; hidden = 16: it enters as call nodes, and the
+    # generated Jacobian / Hessian functions share one walk over the weight table through the call cache
     N = 5
-    nmpc = robot_nn_nmpc(N=N, setup=False, hidden=8)
+    nmpc = robot_nn_nmpc(N=N, setup=False, hidden=hidden)
     nmpc._build_module = False
     nmpc.setup()
     spec = nmpc.spec
     assert spec.nx == 5 and spec.nu == 3  # theta and u_theta were appended
+    src = OcpGenerator(spec).source()
+    assert ('f_jac_c' in src and 'f_hess_c' in src and 'NCALLCACHE = 84' in src) == (hidden == 16)
     host = HostOcp(OcpGenerator(spec).build(hostsim=True))
     B = 2
     x0 = np.column_stack([robot_initial_states(B), np.zeros(B)])
