@@ -180,3 +180,53 @@ def test_mlp_call_node_equals_the_unrolled_graph_and_its_generated_c_code(tmp_pa
     np.testing.assert_allclose(o_y, np.asarray(ref[0]).reshape(-1), rtol=1e-12)
     np.testing.assert_allclose(o_J.reshape(no, nz), ref[1], rtol=1e-11, atol=1e-12)
     np.testing.assert_allclose(o_H.reshape(nz, nz), ref[2], rtol=1e-10, atol=1e-11)
+
+
+def test_call_cache_shares_one_table_walk_between_jacobian_and_hessian_functions(tmp_path):
+    """``c_source(call_cache=...)``: the Jacobian function evaluates the call groups at order 2 and stores their outputs,
+    the Hessian function reads them instead of calling again; both must equal the plain functions (GP and MLP nodes)."""
+    import ctypes as C
+    import os
+    import subprocess
+    from hilo_mpc_b200.ann import ANN, Layer
+    rng = np.random.default_rng(4)
+    nz, nh, no = 3, 18, 2
+    net = ANN([f'z{i}' for i in range(nz)], [f'y{i}' for i in range(no)])
+    net.add_layers(Layer.dense(nh, 'tanh'))
+    net.setup()
+    net.set_weights([rng.normal(size=(nh, nz)), rng.normal(size=(no, nh))], [rng.normal(size=nh), rng.normal(size=no)])
+    gid = sx.register_gp_table(rng.normal(size=(40, 2)), rng.normal(size=40), np.array([.7, 1.3]))
+    x, lam = sx.sym('x', nz), sx.sym('l', no + 1)
+    y = list(net.predict(sx.as_vector([x[0], sx.sin(x[1]), x[2] * x[0]]))) + [sx.gp_mean_node(gid, [x[1], x[2]]) * x[0]]
+    y = np.array(y, dtype=object)
+    jac = sx.Function('jac', [('x', x)], [('y', y), ('J', sx.jacobian(y, x))])
+    hes = sx.Function('hes', [('x', x), ('l', lam)], [('H', sx.hessian(sx.dot(lam, y), x))])
+    cache = dict(mode='store', slots={}, size=0)
+    src_jc = jac.c_source(qualifiers='', name='jac_c', call_cache=cache)
+    assert cache['size'] == (no + no * nz + no * nz * (nz + 1) // 2) + (1 + 2 + 3) and len(cache['slots']) == 2
+    src_hc = hes.c_source(qualifiers='', name='hes_c', call_cache=dict(mode='load', slots=cache['slots'], size=cache['size']))
+    assert 'mlp1_eval' not in src_hc and 'gp_se_eval' not in src_hc      # nothing is walked a second time
+    ids = sx.gp_tables_used(np.concatenate([o for o in jac.outputs] + [o for o in hes.outputs]))
+    csrc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'hilo_mpc_b200', 'csrc')
+    src = '\n'.join(['#define HB_HOSTSIM', '#include "ocp_kernels.cuh"', sx.gp_tables_c_source(ids), 'extern "C" {',
+                     jac.c_source(qualifiers=''), hes.c_source(qualifiers=''), src_jc, src_hc, '}'])
+    cu = tmp_path / 'cache_fun.cpp'
+    cu.write_text(src)
+    so = tmp_path / 'cache_fun.so'
+    subprocess.run(['g++', '-O1', '-std=c++17', '-shared', '-fPIC', '-DHB_HOSTSIM', '-I', csrc, str(cu), '-o', str(so)],
+                   check=True)
+    lib = C.CDLL(str(so))
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    xv, lv = rng.normal(size=nz), rng.normal(size=no + 1)
+    ny = no + 1
+    y0, J0, H0 = np.zeros(ny), np.zeros(ny * nz), np.zeros(nz * nz)
+    y1, J1, H1, cc = np.zeros(ny), np.zeros(ny * nz), np.zeros(nz * nz), np.zeros(cache['size'])
+    lib.jac(dp(xv), dp(y0), dp(J0))
+    lib.hes(dp(xv), dp(lv), dp(H0))
+    lib.jac_c(dp(xv), dp(y1), dp(J1), dp(cc))
+    lib.hes_c(dp(xv), dp(lv), dp(H1), dp(cc))
+    np.testing.assert_allclose(y1, y0, rtol=1e-14)
+    np.testing.assert_allclose(J1, J0, rtol=1e-13, atol=1e-14)
+    np.testing.assert_allclose(H1, H0, rtol=1e-13, atol=1e-14)
+    ref = hes(xv, lv)
+    np.testing.assert_allclose(H1.reshape(nz, nz), np.asarray(ref), rtol=1e-10, atol=1e-11)
