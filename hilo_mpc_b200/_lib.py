@@ -85,7 +85,7 @@ def load() -> C.CDLL:
     return lib
 
 
-ABI_VERSION = 7   # HB_ABI_VERSION of include/hilo_b200.h this binding was written against
+ABI_VERSION = 8   # HB_ABI_VERSION of include/hilo_b200.h this binding was written against
 
 
 def _register_optional(lib: C.CDLL) -> None:
@@ -103,6 +103,8 @@ def _register_optional(lib: C.CDLL) -> None:
         'hb_gp_predict': (pred, i),
         'hb_gp_fit_kernel': ([i] + fit, i),
         'hb_gp_predict_kernel': ([i] + pred, i),
+        'hb_gp_lml_grad_work_doubles': ([i], sz),
+        'hb_gp_lml_grad': ([i, i, i, vp, vp, d, d, vp, vp, vp, vp, vp], i),
     }
     for name, (args, res) in sigs.items():
         fn = getattr(lib, name)

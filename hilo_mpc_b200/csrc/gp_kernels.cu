@@ -419,6 +419,75 @@ __global__ void __launch_bounds__(128) gp_mean_only_kernel(int kind, int n, int 
   mean[m] = prior + sf2 * mu;
 }
 
+// ------------------------------------------------------------------------------ gradient of the log marginal likelihood
+// dNLML/dtheta_j = 1/2 tr(W dK/dtheta_j) with W = K^-1 - alpha alpha^T (Rasmussen & Williams (5.9); gp.py:660-697 obtains
+// it by automatic differentiation of the CasADi graph).  Kinv comes from the own DMMA GEMM (L^-T L^-1); this kernel then
+// makes ONE pass over the (i, j) pairs, recomputes r_ij and the covariance factors on the fly (nothing of size d x n x n is
+// ever stored) and reduces  sum W,  sum W sf2 g(r),  sum W sf2 h(r) D2_k  (dK/dlog l_k = sf2 h(r) D2_k, D2_k = ((x_k -
+// x'_k) / l_k)^2;  SE: h = g;  exponential: h = g / r;  Matern 3/2: h = 3 e^-t;  5/2: h = 5/3 (1 + t) e^-t).
+// out = [1/2 sigma_n^2 tr W | 1/2 sum_k-terms (d) | 1/2 sum W K]  - derivatives with respect to the LOG parameters.
+__global__ void transpose_kernel(int n, const double* __restrict__ A, double* __restrict__ At) {
+  __shared__ double tile[32][33];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int i = by + r, j = bx + threadIdx.x;
+    tile[r][threadIdx.x] = (i < n && j < n) ? A[(size_t)i * n + j] : 0.0;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int i = bx + r, j = by + threadIdx.x;
+    if (i < n && j < n) At[(size_t)i * n + j] = tile[threadIdx.x][r];
+  }
+}
+
+__global__ void __launch_bounds__(256) gp_lml_grad_kernel(int kind, int n, int d, const double* __restrict__ X,
+                                                          const double* __restrict__ ls, double sf2, double noise,
+                                                          const double* __restrict__ Kinv,
+                                                          const double* __restrict__ alpha, double* __restrict__ out) {
+  const int i = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  double acc[18];   // [0] trace part, [1 .. d] length scales, [d + 1] signal variance
+#pragma unroll
+  for (int k = 0; k < 18; ++k) acc[k] = 0.0;
+  if (j < n) {
+    const double w = Kinv[(size_t)i * n + j] - alpha[i] * alpha[j];
+    double D2[16], r2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      D2[k] = 0.0;
+      if (k < d) { const double t = (X[(size_t)k * n + i] - X[(size_t)k * n + j]) / ls[k]; D2[k] = t * t; r2 += D2[k]; }
+    }
+    double g, h;
+    if (kind == 0) { g = exp(-0.5 * r2); h = g; }
+    else {
+      const double r = sqrt(r2);
+      if (kind == 1) { g = exp(-r); h = (r > 0.0) ? g / r : 0.0; }
+      else if (kind == 2) { const double t = 1.7320508075688772 * r, e = exp(-t); g = (1.0 + t) * e; h = 3.0 * e; }
+      else { const double t = 2.23606797749979 * r, e = exp(-t); g = (1.0 + t + t * t * (1.0 / 3.0)) * e; h = (5.0 / 3.0) * (1.0 + t) * e; }
+    }
+    if (i == j) acc[0] = 0.5 * noise * w;
+    const double wh = 0.5 * sf2 * w * h;
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+      if (k < d) acc[1 + k] = wh * D2[k];
+    acc[1 + d] = 0.5 * sf2 * w * g;
+  }
+  __shared__ double red[8][18];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int k = 0; k < d + 2; ++k) {
+    double v = acc[k];
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    if (lane == 0) red[warp][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < d + 2) {
+    double v = 0.0;
+    for (int wq = 0; wq < (int)(blockDim.x >> 5); ++wq) v += red[wq][threadIdx.x];
+    atomicAdd(out + threadIdx.x, v);
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -511,6 +580,31 @@ int hb_gp_predict_kernel(int kind, int n, int d, int M, const double* X, const d
   if (var != nullptr) dgemm_dmma(n, M, n, 1.0, Linv, n, Ks, M, 0, 0.0, V, M, 0, 1, s);
   predict_reduce_kernel<<<(M + 127) / 128, 128, 0, s>>>(n, M, Ks, var ? V : nullptr, alpha, prior_mean,
                                                         signal_variance, noise_variance, mean, var);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
+size_t hb_gp_lml_grad_work_doubles(int n) { return (size_t)2 * n * n; }
+
+int hb_gp_lml_grad(int kind, int n, int d, const double* X, const double* length_scales, double signal_variance,
+                   double noise_variance, const double* Linv, const double* alpha, double* work, double* grad,
+                   void* stream) {
+  if (kind < 0 || kind > 3 || n <= 0 || d <= 0 || d > 16) return -1;
+  if (!X || !length_scales || !Linv || !alpha || !work || !grad) return -1;
+  cudaStream_t s = (cudaStream_t)stream;
+  double* LinvT = work;                     // [n][n]
+  double* Kinv = work + (size_t)n * n;      // [n][n] = L^-T L^-1
+  {
+    dim3 grid((n + 31) / 32, (n + 31) / 32), block(32, 8);
+    transpose_kernel<<<grid, block, 0, s>>>(n, Linv, LinvT);
+  }
+  dgemm_dmma(n, n, n, 1.0, LinvT, n, Linv, n, 0, 0.0, Kinv, n, 0, 0, s);
+  cudaMemsetAsync(grad, 0, (size_t)(d + 2) * sizeof(double), s);
+  {
+    dim3 grid((n + 255) / 256, n);
+    gp_lml_grad_kernel<<<grid, 256, 0, s>>>(kind, n, d, X, length_scales, signal_variance, noise_variance, Kinv, alpha,
+                                            grad);
+  }
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
 }

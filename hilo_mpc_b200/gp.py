@@ -327,23 +327,22 @@ class GaussianProcess:
             return 1e300, np.zeros_like(theta)
         fit = self._fit
         X, Linv, alpha = fit['X'], fit['Linv'], fit['alpha']
-        W = Linv.T @ Linv - torch.outer(alpha, alpha)
-        ls = self.kernel.length_scale_vector(d)
-        D2 = ((X[:, :, None] - X[:, None, :]) / fit['ls'][:, None, None]) ** 2      # (d, n, n)
-        gk, hk = self.kernel.g_h(D2.sum(0), xp=torch)
-        WK = W * (self.kernel.signal_variance * gk)
-        WH = W * (self.kernel.signal_variance * hk)
+        n = X.shape[1]
+        lib = _lib.load()
+        work = torch.empty(lib.hb_gp_lml_grad_work_doubles(n), dtype=torch.float64, device=X.device)
+        gd = torch.empty(d + 2, dtype=torch.float64, device=X.device)
+        st = torch.cuda.current_stream(X.device)
+        _lib.check(lib.hb_gp_lml_grad(self.kernel.kind, n, d, X.data_ptr(), fit['ls'].data_ptr(),
+                                      float(self.kernel.signal_variance), float(self.noise_variance), Linv.data_ptr(),
+                                      alpha.data_ptr(), work.data_ptr(), gd.data_ptr(), st.cuda_stream), 'hb_gp_lml_grad')
+        gh = gd.cpu().numpy()                            # [noise | length scales (d) | signal variance], log parameters
         g = np.empty(full.size)
-        g[0] = .5 * self.noise_variance * float(torch.trace(W).item())
-        if nl == 1:
-            g[1] = .5 * float((WH * D2.sum(0)).sum().item())
-        else:
-            g[1:1 + nl] = .5 * (WH[None] * D2).sum(dim=(1, 2)).cpu().numpy()
-        g[1 + nl] = .5 * float(WK.sum().item())
+        g[0] = gh[0]
+        g[1:1 + nl] = gh[1:1 + d].sum() if nl == 1 else gh[1:1 + d]
+        g[1 + nl] = gh[1 + d]
         if nm:                                           # dNLML/dbeta_j = -Phi_j^T alpha
             Phi = torch.stack(self.mean.basis(X, xp=torch))
             g[2 + nl:] = -(Phi @ alpha).cpu().numpy()
-        del ls
         return -fit['lml'], g[free]
 
     def fit_model(self, fixed: Sequence[str] = (), maxiter: int = 500) -> None:

@@ -29,7 +29,7 @@ extern "C" {
 #endif
 
 /* ------------------------------------------------------------------------------------------------ library */
-#define HB_ABI_VERSION 7              /* bumps on every incompatible change of a struct or signature below */
+#define HB_ABI_VERSION 8              /* bumps on every incompatible change of a struct or signature below */
 int hb_version(void);                 /* HB_ABI_VERSION the library was built with; generated modules export the same
                                          number (hbm_abi_version) and hb_ocp_open / hb_est_open refuse a mismatch (-5) */
 const char* hb_last_error(void);      /* host string describing the last failure on this thread */
@@ -255,6 +255,14 @@ int hb_gp_fit_kernel(int kind, int n, int d, const double* X, const double* y, c
 int hb_gp_predict_kernel(int kind, int n, int d, int M, const double* X, const double* Xq, const double* length_scales,
                          double signal_variance, double noise_variance, double prior_mean, const double* Linv,
                          const double* alpha, double* mean, double* var, double* work, void* stream);
+/* Gradient of the NEGATIVE log marginal likelihood with respect to the log hyper-parameters, from the factorisation
+ * hb_gp_fit_kernel left behind: grad [d + 2] = [d/dlog sigma_n^2 | d/dlog l_1 .. l_d | d/dlog sigma_f^2]
+ * = 1/2 tr((K^-1 - alpha alpha^T) dK/dtheta_j).  Replaces the automatic differentiation of the likelihood graph inside
+ * GaussianProcess.fit_model (gp.py:660-697, inference.py:197-217).  work: hb_gp_lml_grad_work_doubles(n) doubles.   */
+size_t hb_gp_lml_grad_work_doubles(int n);
+int hb_gp_lml_grad(int kind, int n, int d, const double* X, const double* length_scales, double signal_variance,
+                   double noise_variance, const double* Linv, const double* alpha, double* work, double* grad,
+                   void* stream);
 
 #ifdef __cplusplus
 }

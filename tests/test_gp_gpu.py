@@ -244,3 +244,31 @@ def test_gp_mean_functions(cuda_device):
     gp2.fit_model()
     np.testing.assert_allclose([p.value for p in gp2.hyperparameters],
                                [.02183, 1.1918832, 1.4624534, .2201449, .4017997], rtol=1e-6)
+
+
+@pytest.mark.parametrize('kernel', ['squared_exponential', 'exponential', 'matern_32', 'matern_52'])
+def test_lml_gradient_kernel_matches_finite_differences(cuda_device, kernel):
+    """``hb_gp_lml_grad`` (own GEMM + one reduction pass over the pairs) against central differences of the negative log
+    marginal likelihood in the log hyper-parameters, ARD length scales, every stationary kernel family."""
+    from hilo_mpc_b200.gp import GP, Kernel
+    rng = np.random.default_rng(17)
+    n, d = 70, 3
+    X = rng.uniform(-1., 1., size=(d, n))
+    y = (np.sin(2. * X[0]) + X[1] * X[2] + .05 * rng.normal(size=n))[None, :]
+    gp = GP([f'f{k}' for k in range(d)], 'y', noise_variance=.04,
+            kernel=getattr(Kernel, kernel)(signal_variance=1.7, length_scales=[.6, 1.1, .9], ard=True))
+    gp.set_training_data(X, y)
+    gp.setup()
+    nl = d
+    base = np.concatenate([[np.log(gp.noise_variance)], np.log(gp.kernel.length_scales), [np.log(gp.kernel.signal_variance)]])
+    free = np.ones(base.size, dtype=bool)
+    f0, g = gp._nlml_and_grad(base.copy(), free, base)
+    assert np.isfinite(f0) and g.shape == (nl + 2,)
+    h = 1e-5
+    fd = np.empty_like(g)
+    for j in range(base.size):
+        tp, tm = base.copy(), base.copy()
+        tp[j] += h
+        tm[j] -= h
+        fd[j] = (gp._nlml_and_grad(tp, free, base)[0] - gp._nlml_and_grad(tm, free, base)[0]) / (2. * h)
+    np.testing.assert_allclose(g, fd, rtol=2e-6, atol=1e-7)
