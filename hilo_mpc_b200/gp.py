@@ -306,7 +306,7 @@ class GaussianProcess:
 
     def _nlml_and_grad(self, theta, free, base):
         """Negative LML and its gradient w.r.t. the free log-hyper-parameters: factorisation by ``hb_gp_fit`` (setup),
-        ``dNLML/dtheta_j = 1/2 tr((K^-1 - alpha alpha^T) dK/dtheta_j)`` as device matrix products."""
+        ``dNLML/dtheta_j = 1/2 tr((K^-1 - alpha alpha^T) dK/dtheta_j)`` by ``hb_gp_lml_grad`` (csrc/gp_kernels.cu)."""
         torch = _lib.require_cuda()
         full = base.copy()
         full[free] = theta
