@@ -53,4 +53,4 @@ class HostEst:
         rc = fn(C.byref(call))
         if rc != 0:
             raise RuntimeError(f'hbm_{which}_step returned {rc}')
-        return dict(x=x, P=P, X=X, y_pred=ypred, status=status, q=q, idx=idx)
+        return dict(x=x, P=P, X=X, y_pred=ypred, status=status, q=q, idx=idx, work=work)

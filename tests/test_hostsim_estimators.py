@@ -117,6 +117,46 @@ def test_pf_step_indices_bit_exact_and_moments():
         np.testing.assert_allclose(out['P'][b], np.atleast_2d(P), rtol=1e-10)
 
 
+def test_pf_prediction_only_pass_and_prior_editing_loop():
+    """``do_update = 0`` (the pass the prior-editing loop repeats, pf.py:378-398) leaves particles and estimate alone and
+    delivers the predicted noisy measurements; the editing loop driven with it equals the oracle's restatement."""
+    m = scalar_model()
+    h = HostEst(build_est_module(m, hostsim=True))
+    f, hfun = (lambda x, u, p: x / 2 + 25 * x / (1 + x ** 2)), (lambda x, u, p: x ** 2 / 20)
+    rng = np.random.default_rng(5)
+    ns, R, K = 40, .04, .5
+    X0 = rng.normal(9., 2.5, size=(1, ns, 1))
+    y = np.array([[3.6]])
+    w = rng.normal(0., 1., size=(1, ns, 1))
+    v = rng.normal(0., np.sqrt(R), size=(1, ns, 1))
+    x_in = np.full((1, 1), 9.)
+    out = h.call('pf', x_in, P=np.ones((1, 1, 1)), X=X0, y=y, Q=[[1.]], R=[[R]], w=w, v=v, unif=np.zeros((1, ns)),
+                 do_update=False)
+    np.testing.assert_array_equal(out['X'], X0)                    # particles untouched
+    np.testing.assert_array_equal(out['x'], x_in)                  # estimate untouched
+    Ys = out['work'][ns + ns:ns + 2 * ns]                          # Xs | cdf | Ys  (csrc/est_module.cuh)
+    Yo = np.array([hfun(f(X0[0, k, 0], None, None), None, None) for k in range(ns)]) + v[0, :, 0]
+    np.testing.assert_allclose(Ys, Yo, rtol=1e-13)
+    # the loop of ParticleFilter._edit_prior on the host kernels, jitter drawn like the oracle draws it
+    draws = np.random.RandomState(3)
+    pdf = lambda mu, cov, n: draws.multivariate_normal(mu, cov, size=n)
+    X = X0.copy()
+    rounds = 0
+    while True:
+        o = h.call('pf', x_in, P=np.ones((1, 1, 1)), X=X, y=y, Q=[[1.]], R=[[R]], w=w, v=v, unif=np.zeros((1, ns)),
+                   do_update=False)
+        need = np.abs(y[0, 0] - o['work'][2 * ns:3 * ns]) > 6. * np.sqrt(R)
+        if not need.any():
+            break
+        rounds += 1
+        spread = X[0].max(axis=0) - X[0].min(axis=0)
+        X[0, need] += pdf(np.zeros(1), K * np.diag(spread) * float(need.sum()) ** -1., int(need.sum()))
+    draws = np.random.RandomState(3)
+    Xe = est.pf_prior_editing(f, hfun, X0[0].T, y[0], None, None, w[0].T, v[0].T, np.array([[R]]), K, pdf)
+    assert rounds >= 1
+    np.testing.assert_allclose(X[0].T, Xe, rtol=1e-13)
+
+
 def bioreactor_model():
     """tests/test_KFs.py:695-712 (equation-string front end; parameters in order of appearance)."""
     m = Model()
