@@ -301,11 +301,6 @@ def _cpu_closed_loop_body(arg):
     return done, ok, secs
 
 
-def _cpu_warm(config):
-    nlp, ctl = _cpu_nlp(config)
-    return 0
-
-
 CPU_SAMPLE_DEADLINE_S = {2: 150., 3: 150., 4: 150., 5: 300.}   # wall-clock bound of one CPU sample (cold solves included)
 
 
