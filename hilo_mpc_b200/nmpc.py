@@ -472,12 +472,29 @@ class NMPC(DynamicOptimization):
         if n_tvp:
             block = np.zeros((N, n_tvp))
             for j, name in enumerate(self._tvp_names):
-                vals = tvp[name] if (tvp is not None and name in tvp) else self._tvp_values.get(name)
+                passed = tvp is not None and name in tvp
+                vals = tvp[name] if passed else self._tvp_values.get(name)
                 if vals is None:
                     raise ValueError(f"No values for the time-varying parameter {name} were supplied")
                 vals = np.asarray(vals, dtype=float).reshape(-1)
-                idx = (self._n_iterations + np.arange(N)) % len(vals)  # shifted horizon with wrap (mpc.py:293-333)
-                block[:, j] = vals[idx]
+                if len(vals) < N:
+                    raise TypeError(f"When passing time-varying parameters, you need to pass a number of values at "
+                                    f"least as long as the prediction horizon. The parameter {name} has {len(vals)} "
+                                    f"values but the MPC has a prediction horizon length of {N}.")
+                if passed:   # values handed to optimize() ARE the horizon of this step (mpc.py:342-355)
+                    block[:, j] = vals[:N]
+                    continue
+                # Stored values (mpc.py:293-333, optimizer.py:1106-1143): the horizon moves on by one value per
+                # iteration.  Past the end of the data the reference "loops back" with the index ci - N floor(ci / N) of
+                # the iteration ci that appends the value - i.e. position (ci + j + 1) mod N of the data, not a wrap
+                # modulo its length; reproduced as it is (tests/golden/reference_numeric.json, 'tvp_horizon').
+                pos = self._n_iterations + np.arange(N)
+                beyond = pos >= len(vals)
+                if beyond.any() and self._n_iterations > 0:
+                    warnings.warn("The prediction horizon is predicting outside the values of the time varying "
+                                  "parameters. I am now taking looping back the values and start from there. "
+                                  "See documentation for info.")
+                block[:, j] = vals[np.where(beyond, (pos + 1) % N, np.minimum(pos, len(vals) - 1))]
             cols.append(torch.tensor(block, dtype=torch.float64, device=device).unsqueeze(0))
         if n_cp:
             if cp is None:

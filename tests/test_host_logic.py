@@ -110,7 +110,7 @@ def test_control_loop_hands_only_constant_parameters_to_the_controller():
     nmpc = NMPC(plant)
     nmpc.horizon = 4
     nmpc.quad_stage_cost.add_states(names=['a'], weights=[1.], ref=[0.])
-    nmpc.set_time_varying_parameters(['w'], values={'w': [1., 2., 3.]})
+    nmpc.set_time_varying_parameters(['w'], values={'w': [1., 2., 3., 4., 5.]})
     nmpc._build_module = False
     nmpc.setup()
     assert list(nmpc._time_varying_parameters) == ['w'] == list(nmpc._tvp_names)
@@ -118,4 +118,4 @@ def test_control_loop_hands_only_constant_parameters_to_the_controller():
         nmpc._stage_parameters([1., 2., 3.], None, None, torch, torch.device('cpu'), 2)
     sp = nmpc._stage_parameters([7.], None, None, torch, torch.device('cpu'), 2)
     assert sp.shape[-1] == 2 and sp.shape[-2] == 4                    # per stage: [w_k, k]
-    assert np.allclose(sp.reshape(-1, 4, 2)[0].numpy(), [[1., 7.], [2., 7.], [3., 7.], [1., 7.]])
+    assert np.allclose(sp.reshape(-1, 4, 2)[0].numpy(), [[1., 7.], [2., 7.], [3., 7.], [4., 7.]])

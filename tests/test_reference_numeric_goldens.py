@@ -53,3 +53,40 @@ def test_pf_resampling_roughening_moments_equal_the_reference(case):
     np.testing.assert_allclose(Xr, c['X_out'], rtol=0, atol=1e-12)
     np.testing.assert_allclose(Xr.sum(axis=1) / ns, c['x_mean'], rtol=0, atol=1e-12)
     np.testing.assert_allclose(np.cov(Xr), c['P'], rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize('case', range(len(GOLD['tvp_horizon']['cases'])))
+def test_time_varying_parameter_horizon_equals_the_reference(case):
+    """``NMPC._get_tvp_parameters_values`` (mpc.py:293-333) executed iteration by iteration: inside the data the horizon
+    is ``values[ci : ci + N]``; past its end the reference appends ``values[ci mod N]`` - reproduced as it is - and values
+    shorter than the horizon are a TypeError.  ``optimize(tvp=...)`` takes the first N values as they are (mpc.py:342-355)."""
+    import warnings
+    import torch
+    from hilo_mpc_b200 import Model, NMPC
+    c = GOLD['tvp_horizon']['cases'][case]
+    N, values = c['N'], c['values']
+    m = Model(name=f'tvp_case{case}')
+    x = m.set_dynamical_states(['a'])
+    u = m.set_inputs(['u'])
+    p = m.set_parameters(list(values))
+    m.set_dynamical_equations([-x[0] + u[0] + sum(p[k] for k in range(len(values)))])
+    m.setup(dt=.1)
+    nmpc = NMPC(m)
+    nmpc.horizon = N
+    nmpc.quad_stage_cost.add_states(names=['a'], weights=[1.], ref=[0.])
+    nmpc.set_time_varying_parameters(list(values), values=values)
+    nmpc._build_module = False
+    nmpc.setup()
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        for ci, hor in enumerate(c['horizons']):
+            nmpc._n_iterations = ci
+            sp = nmpc._stage_parameters(None, None, None, torch, torch.device('cpu'), 1)
+            got = sp.reshape(N, -1).numpy()[:, :len(values)].T
+            np.testing.assert_array_equal(got, np.asarray(hor))
+    nmpc._n_iterations = 3
+    fresh = {k: [float(100 + i) for i in range(N + 2)] for k in values}
+    sp = nmpc._stage_parameters(None, fresh, None, torch, torch.device('cpu'), 1)
+    np.testing.assert_array_equal(sp.reshape(N, -1).numpy()[:, 0], np.asarray(fresh[list(values)[0]][:N]))
+    with pytest.raises(TypeError):
+        nmpc._stage_parameters(None, {k: [1.] * (N - 1) for k in values}, None, torch, torch.device('cpu'), 1)

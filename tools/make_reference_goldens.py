@@ -10,6 +10,8 @@ the reference tree, executes it unmodified in a namespace with a *stub* ``ca`` (
   every collocation transcription is built from (NMPC, MHE).
 * ``lhsnorm`` (hilo_mpc/modules/estimator/pf.py:425-447): Latin-hypercube normal sampling of the particle filter.
 * the resampling / roughening / moment block of ``ParticleFilter.estimate`` (pf.py:405-421), with the legacy global RNG.
+* ``NMPC._get_tvp_parameters_values`` (mpc.py:293-333): the horizon of stored time-varying parameter values iteration by
+  iteration, including what it does once the horizon runs past the end of the data.
 
 Run:  python tools/make_reference_goldens.py   (needs /root/reference; the tests only read the committed JSON).
 """
@@ -133,6 +135,41 @@ def main():
                          'q': q.tolist(), 'ind': np.asarray(env['ind']).tolist(), 'X_out': np.asarray(env['X']).tolist(),
                          'x_mean': np.asarray(env['x']).tolist(), 'P': np.asarray(env['P']).tolist()})
     out['pf_resample_block'] = {'source': f'hilo_mpc/modules/estimator/pf.py:{start + 1}-{end + 1}', 'cases': pf_cases}
+
+    # ---- horizon of the time-varying parameters, iteration by iteration (NMPC._get_tvp_parameters_values)
+    path = os.path.join(REF, 'hilo_mpc', 'modules', 'controller', 'mpc.py')
+    src, span = _function_source(path, '_get_tvp_parameters_values', cls='NMPC')
+
+    class _DM:
+        @staticmethod
+        def zeros(n, m):
+            return np.zeros((n, m))
+    ca.DM = _DM
+    import warnings
+    ns = {'np': np, 'ca': ca, 'warnings': warnings}
+    exec(src, ns)
+    tvp_cases = []
+    for N, lengths, iters in ((4, (4, 7), 12), (5, (5,), 11), (3, (10, 3), 9), (6, (8,), 20)):
+        values = {f'p{k}': [float(10 * (k + 1) + i) for i in range(L)] for k, L in enumerate(lengths)}
+
+        class _Self:
+            _n_iterations = 0
+            _time_varying_parameters = list(values)
+            _time_varying_parameters_values = values
+            _time_varying_parameters_horizon = None
+            prediction_horizon = N
+            _prediction_horizon = N
+            _n_tvp = len(values)
+        obj = _Self()
+        horizons = []
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            for ci in range(iters):
+                obj._n_iterations = ci
+                ns['_get_tvp_parameters_values'](obj, values)
+                horizons.append(np.asarray(obj._time_varying_parameters_horizon).tolist())
+        tvp_cases.append({'N': N, 'values': values, 'horizons': horizons})
+    out['tvp_horizon'] = {'source': f'hilo_mpc/modules/controller/mpc.py:{span[0]}-{span[1]}', 'cases': tvp_cases}
 
     with open(OUT, 'w') as f:
         json.dump(out, f)
