@@ -17,10 +17,14 @@ import numpy as np
 
 from . import symbolic as sx
 
-FUNCTIONS = {
-    'sin': sx.sin, 'cos': sx.cos, 'tan': sx.tan, 'exp': sx.exp, 'log': sx.log, 'sqrt': sx.sqrt, 'tanh': sx.tanh,
-    'atan': sx.atan, 'arctan': sx.atan, 'asin': sx.asin, 'acos': sx.acos, 'sinh': sx.sinh, 'cosh': sx.cosh,
-    'abs': sx.fabs, 'fabs': sx.fabs, 'sign': sx.sign, 'atan2': sx.atan2, 'arctan2': sx.atan2,
+FUNCTIONS = {   # the reference's table (parsing.py:36-58) plus a few aliases
+    'sqrt': sx.sqrt, 'exp': sx.exp, 'log': sx.log, 'log10': lambda a: sx.log(a) / math.log(10.), 'sign': sx.sign,
+    'abs': sx.fabs, 'min': sx.fmin, 'max': sx.fmax, 'sin': sx.sin, 'cos': sx.cos, 'tan': sx.tan,
+    'arcsin': sx.asin, 'arccos': sx.acos, 'arctan': sx.atan, 'arctan2': sx.atan2,
+    'sinh': sx.sinh, 'cosh': sx.cosh, 'tanh': sx.tanh,
+    'arsinh': lambda a: sx.log(a + sx.sqrt(a * a + 1.)), 'arcosh': lambda a: sx.log(a + sx.sqrt(a * a - 1.)),
+    'artanh': lambda a: .5 * sx.log((1. + a) / (1. - a)),
+    'atan': sx.atan, 'asin': sx.asin, 'acos': sx.acos, 'fabs': sx.fabs, 'atan2': sx.atan2,
 }
 CONSTANTS = {'pi': math.pi, 'e': math.e, 'inf': math.inf}
 
@@ -110,10 +114,16 @@ def parse_dynamic_equations(equations, discrete: bool = False, **kwargs) -> dict
         if s is not None:
             known[key] = s
     odes, meas, aux = [], [], {}
+    derivative_of = {}   # 'dv(t)/dt' / 'd/dt(v(t))' / 'v(k+1)' -> its right-hand side, for nested use (parsing.py:374, :420)
+    pending = '...'
     for raw in equations:
         if '|' in raw:
             continue
-        eq = raw.replace(' ', '').replace('\t', '')
+        # a line ending in '...' is continued on the next one (parsing.py:344-347)
+        pending = pending.replace('...', raw.replace(' ', '').replace('\t', ''))
+        if pending.endswith('...'):
+            continue
+        eq, pending = pending, '...'
         if not eq or eq.startswith('#') or '=' not in eq:
             continue
         eq = eq.replace('^', '**')
@@ -137,6 +147,7 @@ def parse_dynamic_equations(equations, discrete: bool = False, **kwargs) -> dict
                 known[state] = s
                 model['x'].append(s)
             odes.append(rhs)
+            derivative_of[lhs] = f'({rhs})'
             continue
         if lhs == '0':
             raise NotImplementedError("Algebraic equations (DAE models) are not supported by the B200 engine yet")
@@ -159,10 +170,22 @@ def parse_dynamic_equations(equations, discrete: bool = False, **kwargs) -> dict
             raise NotImplementedError("Explicit algebraic variables z(t) = ... are not supported by the B200 engine")
         aux[lhs] = ast.parse(rhs, mode='eval')
     ev = _Evaluator(known, model['p'], model['u'], discrete, aux)
+    # A left-hand side such as dv(t)/dt may be used inside other equations: the reference substitutes its right-hand
+    # side textually, longest keys first, where the match is followed by an operator, ')' or the end (parsing.py:446-467)
+    keys = sorted(derivative_of, reverse=True)
+    pattern = re.compile('|'.join(re.escape(k) for k in keys)) if keys else None
+
+    def nested(m):
+        end = m.end()
+        nxt = '+' if end == len(m.string) else m.string[end]
+        return pattern.sub(nested, derivative_of[m.group(0)]) if nxt in '+-*/)' else m.group(0)
+
+    def expand(rhs):
+        return pattern.sub(nested, rhs) if pattern is not None else rhs
     for rhs in odes:
-        model['ode'].append(ev.eval(ast.parse(rhs, mode='eval')))
+        model['ode'].append(ev.eval(ast.parse(expand(rhs), mode='eval')))
     for rhs in meas:
-        model['meas'].append(ev.eval(ast.parse(rhs, mode='eval')))
+        model['meas'].append(ev.eval(ast.parse(expand(rhs), mode='eval')))
     return model
 
 

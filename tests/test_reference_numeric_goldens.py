@@ -1,7 +1,8 @@
 """Oracle and host logic against golden vectors produced by EXECUTING the reference's own source
 (tools/make_reference_goldens.py; fixtures in tests/golden/reference_numeric.json): collocation constants
-(modeling.py:1092-1127), Latin-hypercube normal sampling (pf.py:425-447) and the resampling / roughening / moment block of
-ParticleFilter.estimate (pf.py:405-421)."""
+(modeling.py:1092-1127), Latin-hypercube normal sampling (pf.py:425-447), the resampling / roughening / moment block of
+ParticleFilter.estimate (pf.py:405-421), the horizon of time-varying parameter values (mpc.py:293-333) and the
+equation-string parser (util/parsing.py)."""
 import json
 import os
 
@@ -90,3 +91,24 @@ def test_time_varying_parameter_horizon_equals_the_reference(case):
     np.testing.assert_array_equal(sp.reshape(N, -1).numpy()[:, 0], np.asarray(fresh[list(values)[0]][:N]))
     with pytest.raises(TypeError):
         nmpc._stage_parameters(None, {k: [1.] * (N - 1) for k in values}, None, torch, torch.device('cpu'), 1)
+
+
+@pytest.mark.parametrize('case', range(len(GOLD['parser']['cases'])))
+def test_equation_string_parser_equals_the_reference(case):
+    """The reference's parser module (hilo_mpc/util/parsing.py) executed unmodified with a stub ``casadi``: which names
+    become states / measurements / inputs / parameters and in which order, the constants, and the values of every
+    right-hand side at random points must be what ``hilo_mpc_b200.parsing`` produces for the same strings."""
+    from hilo_mpc_b200 import symbolic as sx
+    from hilo_mpc_b200.parsing import parse_dynamic_equations
+    c = GOLD['parser']['cases'][case]
+    t, dt = sx.sym('t'), sx.sym('dt')
+    model = parse_dynamic_equations(c['equations'].split('\n'), discrete=c['discrete'], t=t, dt=dt)
+    for k in ('x', 'y', 'u', 'p'):
+        assert [s.name for s in model[k]] == c['names'][k], k
+    assert {k: float(v) for k, v in model['const'].items()} == c['const']
+    syms = model['x'] + model['y'] + model['u'] + model['p'] + [t, dt]
+    for kind in ('ode', 'meas'):
+        F = sx.Function(kind, [('v', np.array(syms, dtype=object))], [('out', np.array(model[kind], dtype=object))])
+        for pt in c['points']:
+            vals = np.array([pt['env'][s.name] for s in syms])
+            np.testing.assert_allclose(np.asarray(F(vals)).reshape(-1), pt['values'][kind], rtol=1e-13, atol=1e-14)

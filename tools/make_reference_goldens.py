@@ -70,6 +70,175 @@ def _function_source(path, name, cls=None):
     return textwrap.dedent('\n'.join(lines)), (fn.lineno, fn.end_lineno)
 
 
+class _SX:
+    """Stub of ``casadi.SX`` for the parser: a named symbol or a closure over an environment ``{name: value}``."""
+
+    def __init__(self, fn, name=None):
+        self.fn, self._name = fn, name
+
+    @staticmethod
+    def sym(name):
+        return _SX(lambda env, n=name: env[n], name)
+
+    def name(self):
+        return self._name
+
+    def elements(self):
+        return [self]
+
+    @staticmethod
+    def _f(v):
+        return v.fn if isinstance(v, _SX) else (lambda env, c=float(v): c)
+
+    @staticmethod
+    def _bin(a, b, op):
+        fa, fb = _SX._f(a), _SX._f(b)
+        return _SX(lambda env: op(fa(env), fb(env)))
+
+    def __add__(self, o): return _SX._bin(self, o, lambda a, b: a + b)
+    def __radd__(self, o): return _SX._bin(o, self, lambda a, b: a + b)
+    def __sub__(self, o): return _SX._bin(self, o, lambda a, b: a - b)
+    def __rsub__(self, o): return _SX._bin(o, self, lambda a, b: a - b)
+    def __mul__(self, o): return _SX._bin(self, o, lambda a, b: a * b)
+    def __rmul__(self, o): return _SX._bin(o, self, lambda a, b: a * b)
+    def __truediv__(self, o): return _SX._bin(self, o, lambda a, b: a / b)
+    def __rtruediv__(self, o): return _SX._bin(o, self, lambda a, b: a / b)
+    def __pow__(self, o): return _SX._bin(self, o, lambda a, b: a ** b)
+    def __rpow__(self, o): return _SX._bin(o, self, lambda a, b: a ** b)
+
+    def __neg__(self):
+        f = self.fn
+        return _SX(lambda env: -f(env))
+
+
+def _stub_casadi_module():
+    import math
+    import types
+    m = types.ModuleType('casadi')
+    m.SX = _SX
+    m.MX = _SX
+
+    def lift1(fun):
+        def wrapped(a):
+            if isinstance(a, _SX):
+                f = a.fn
+                return _SX(lambda env: fun(f(env)))
+            return fun(a)
+        return wrapped
+
+    def lift2(fun):
+        return lambda a, b: _SX._bin(a, b, fun) if isinstance(a, _SX) or isinstance(b, _SX) else fun(a, b)
+    for name, fun in (('sqrt', math.sqrt), ('exp', math.exp), ('log', math.log), ('log10', math.log10),
+                      ('sign', lambda v: float((v > 0) - (v < 0))), ('fabs', abs), ('sin', math.sin), ('cos', math.cos),
+                      ('tan', math.tan), ('asin', math.asin), ('acos', math.acos), ('atan', math.atan),
+                      ('sinh', math.sinh), ('cosh', math.cosh), ('tanh', math.tanh), ('asinh', math.asinh),
+                      ('acosh', math.acosh), ('atanh', math.atanh)):
+        setattr(m, name, lift1(fun))
+    for name, fun in (('fmin', min), ('fmax', max), ('atan2', math.atan2), ('plus', lambda a, b: a + b),
+                      ('minus', lambda a, b: a - b), ('times', lambda a, b: a * b), ('rdivide', lambda a, b: a / b),
+                      ('power', lambda a, b: a ** b)):
+        setattr(m, name, lift2(fun))
+    return m
+
+
+PARSER_CASES = [
+    # (name, discrete, equations) - strings of the reference's tests (tests/test_parsing.py, test_KFs.py, test_MHE.py,
+    # test_NMPC.py) restricted to ODE models, plus the features the front end has to get right: constants, auxiliary
+    # expressions that are inlined, inputs v(k), parameters in order of appearance, '^', line continuation '...'
+    ('double_replace', False, """
+        dx/dt = u(k)
+        dy/dt = ar + ar
+
+        ar = sin(2*x(t))
+        """),
+    ('hill_oscillator', False, """
+        # ODE's
+        d/dt(x_1(t)) = x_2(t)
+        d/dt(x_2(t)) = -p*x_1(t)
+
+        # Algebraic equations
+        p = r - 2*q*cos(omega*t)
+
+        # Measurement equations
+        y(k) = x_1(t) + x_2(t)*sin(omega*t)
+        """),
+    ('hill_oscillator_discrete', True, """
+        # ODE's
+        x_1(k + 1) = x_1(k) + x_2(k)*dt
+        x_2(k + 1) = x_2(k) - p*x_1(k)*dt
+
+        # Algebraic equations
+        p = r - 2*q*cos(omega*t(k))
+
+        # Measurement equations
+        y(k) = x_1(k) + x_2(k)*sin(omega*t(k))
+        """),
+    ('cart_pole_nested_derivative', False, """
+        # DAE's
+        dx(t)/dt = v(t)
+        dv(t)/dt = (3/4*m*g*sin(theta(t))*cos(theta(t)) - 1/2*m*l*sin(theta(t))*omega(t)^2 + F(k))/...
+        (M + m - 3/4*m*cos(theta(t))^2)
+        d/dt(theta(t)) = omega(t)
+        d/dt(omega(t)) = 3/(2*l)*(dv(t)/dt*cos(theta(t)) + g*sin(theta(t)))
+        y(k) = h + l*cos(theta(t))
+
+        # Constants
+        g = 9.81
+        """),
+    ('bioreactor', False, """
+        dT/dt = alpha*(T_amb - T(t))
+        dcB/dt = r - D(k)*cB(t)
+        dcS/dt = -r/Y - D(k)*cS(t)
+
+        y_0(k) = T(t)
+        y_1(k) = cB(t)
+
+        r = (mu_0 + mu_1*T(t))*cS(t)*cB(t)/(K + cS(t))
+        """),
+    ('kf_two_tank', False, """
+        dx_1/dt = -k_1*x_1(t) + u(k)
+        dx_2/dt = k_1*x_1(t) - k_2*x_2(t)
+        y(k) = x_2(t)
+        """),
+    ('functions', False, """
+        da/dt = -sqrt(abs(a(t))) + exp(-b(t)^2)*u_1(k) + log(1 + c^2) + tanh(a(t))*arctan(b(t))
+        db/dt = min(a(t), b(t)) - max(u_2(k), 0.5) + arctan2(a(t), 1 + b(t)^2) + sign(u_1(k))*log10(10 + a(t)^2)
+        z_out(k) = sinh(a(t)/10) + cosh(b(t)/10) + arsinh(a(t)) - cos(c)*tan(b(t)/4)
+        c = 0.75
+        """),
+]
+
+
+def _parser_goldens():
+    import importlib.util
+    import warnings
+    path = os.path.join(REF, 'hilo_mpc', 'util', 'parsing.py')
+    sys.modules['casadi'] = _stub_casadi_module()
+    try:
+        spec = importlib.util.spec_from_file_location('_ref_parsing', path)
+        mod = importlib.util.module_from_spec(spec)
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            spec.loader.exec_module(mod)      # the reference file itself, unmodified
+            cases = []
+            for name, discrete, text in PARSER_CASES:
+                t, dt = _SX.sym('t'), _SX.sym('dt')
+                model = mod.parse_dynamic_equations(text.split('\n'), discrete=discrete, t=[t], dt=[dt])
+                names = {k: [v.name() for v in model[k]] for k in ('x', 'y', 'z', 'u', 'p')}
+                rng = np.random.RandomState(abs(hash(name)) % 1000 if False else len(name))
+                allnames = sorted(set(sum(names.values(), [])) | {'t', 'dt'})
+                points = []
+                for _ in range(3):
+                    env = {n: float(rng.uniform(.2, 1.5)) for n in allnames}
+                    vals = {k: [float(_SX._f(e)(env)) for e in model[k]] for k in ('ode', 'alg', 'meas', 'quad')}
+                    points.append({'env': env, 'values': vals})
+                cases.append({'name': name, 'discrete': discrete, 'equations': text, 'names': names,
+                              'const': {k: float(v) for k, v in model['const'].items()}, 'points': points})
+    finally:
+        del sys.modules['casadi']
+    return {'source': 'hilo_mpc/util/parsing.py (whole module, executed with a stub casadi)', 'cases': cases}
+
+
 def main():
     out = {'reference': 'hilo-mpc/hilo-mpc @ /root/reference', 'generator': 'tools/make_reference_goldens.py'}
     ca = _CaStub()
@@ -170,6 +339,9 @@ def main():
                 horizons.append(np.asarray(obj._time_varying_parameters_horizon).tolist())
         tvp_cases.append({'N': N, 'values': values, 'horizons': horizons})
     out['tvp_horizon'] = {'source': f'hilo_mpc/modules/controller/mpc.py:{span[0]}-{span[1]}', 'cases': tvp_cases}
+
+    # ---- equation-string parser (hilo_mpc/util/parsing.py), executed as a module with a stub `casadi`
+    out['parser'] = _parser_goldens()
 
     with open(OUT, 'w') as f:
         json.dump(out, f)
