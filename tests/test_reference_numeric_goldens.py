@@ -1,8 +1,8 @@
 """Oracle and host logic against golden vectors produced by EXECUTING the reference's own source
 (tools/make_reference_goldens.py; fixtures in tests/golden/reference_numeric.json): collocation constants
 (modeling.py:1092-1127), Latin-hypercube normal sampling (pf.py:425-447), the resampling / roughening / moment block of
-ParticleFilter.estimate (pf.py:405-421), the horizon of time-varying parameter values (mpc.py:293-333) and the
-equation-string parser (util/parsing.py)."""
+ParticleFilter.estimate (pf.py:405-421), the horizon of time-varying parameter values (mpc.py:293-333), the
+equation-string parser (util/parsing.py) and the export of trained networks (util/machine_learning.py:521-578)."""
 import json
 import os
 
@@ -112,3 +112,30 @@ def test_equation_string_parser_equals_the_reference(case):
         for pt in c['points']:
             vals = np.array([pt['env'][s.name] for s in syms])
             np.testing.assert_allclose(np.asarray(F(vals)).reshape(-1), pt['values'][kind], rtol=1e-13, atol=1e-14)
+
+
+@pytest.mark.parametrize('case', range(len(GOLD['net_to_graph']['cases'])))
+def test_network_export_equals_the_reference(case):
+    """``Activation`` + ``net_to_casadi_graph`` (util/machine_learning.py:44-118, :521-578) executed from source with a
+    stub ``ca``: the labels of trained weights - one or two hidden layers, tanh / sigmoid / softplus / linear, with and
+    without z-score scaling - must be what ``ANN.predict`` gives numerically and through its expression graph (call
+    nodes and unrolled)."""
+    from hilo_mpc_b200 import symbolic as sx
+    from hilo_mpc_b200.ann import ANN, Layer
+    c = GOLD['net_to_graph']['cases'][case]
+    net = ANN([f'x{k}' for k in range(c['n_in'])], [f'y{k}' for k in range(c['n_out'])])
+    net.add_layers(*[Layer.dense(h, a) for a, h in c['hidden']])
+    net.setup()
+    net.set_weights([np.array(w) for w in c['weights']], [np.array(b) for b in c['bias']],
+                    input_scaling=c['input_scaling'], output_scaling=c['output_scaling'])
+    net.call_node_min_hidden = 1
+    z = sx.sym('z', c['n_in'])
+    funs = []
+    for mode in ('call', 'unroll'):
+        net.symbolic_mode = mode
+        funs.append(sx.Function('net', [('z', z)], [('y', net.predict(z))]))
+    for pt in c['points']:
+        x = np.array(pt['x'])
+        np.testing.assert_allclose(net.predict(x[:, None])[:, 0], pt['out']['labels'], rtol=1e-12, atol=1e-13)
+        for F in funs:
+            np.testing.assert_allclose(np.asarray(F(x)).reshape(-1), pt['out']['labels'], rtol=1e-12, atol=1e-13)

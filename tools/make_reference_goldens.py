@@ -10,6 +10,8 @@ the reference tree, executes it unmodified in a namespace with a *stub* ``ca`` (
   every collocation transcription is built from (NMPC, MHE).
 * ``lhsnorm`` (hilo_mpc/modules/estimator/pf.py:425-447): Latin-hypercube normal sampling of the particle filter.
 * the resampling / roughening / moment block of ``ParticleFilter.estimate`` (pf.py:405-421), with the legacy global RNG.
+* the equation-string parser (hilo_mpc/util/parsing.py, the whole module) and ``Activation`` / ``net_to_casadi_graph``
+  (hilo_mpc/util/machine_learning.py) on symbols that are closures over a name -> value environment.
 * ``NMPC._get_tvp_parameters_values`` (mpc.py:293-333): the horizon of stored time-varying parameter values iteration by
   iteration, including what it does once the horizon runs past the end of the data.
 
@@ -120,6 +122,8 @@ def _stub_casadi_module():
 
     def lift1(fun):
         def wrapped(a):
+            if isinstance(a, np.ndarray):      # vectors are object arrays of scalar symbols
+                return np.array([wrapped(v) for v in a.flat], dtype=object).reshape(a.shape)
             if isinstance(a, _SX):
                 f = a.fn
                 return _SX(lambda env: fun(f(env)))
@@ -127,7 +131,13 @@ def _stub_casadi_module():
         return wrapped
 
     def lift2(fun):
-        return lambda a, b: _SX._bin(a, b, fun) if isinstance(a, _SX) or isinstance(b, _SX) else fun(a, b)
+        def wrapped(a, b):
+            if isinstance(a, np.ndarray) or isinstance(b, np.ndarray):
+                a2, b2 = np.broadcast_arrays(np.asarray(a, dtype=object), np.asarray(b, dtype=object))
+                return np.array([wrapped(u, v) for u, v in zip(a2.flat, b2.flat)], dtype=object).reshape(a2.shape)
+            return _SX._bin(a, b, fun) if isinstance(a, _SX) or isinstance(b, _SX) else fun(a, b)
+        return wrapped
+    m.sum1 = lambda a: np.sum(a, axis=0)
     for name, fun in (('sqrt', math.sqrt), ('exp', math.exp), ('log', math.log), ('log10', math.log10),
                       ('sign', lambda v: float((v > 0) - (v < 0))), ('fabs', abs), ('sin', math.sin), ('cos', math.cos),
                       ('tan', math.tan), ('asin', math.asin), ('acos', math.acos), ('atan', math.atan),
@@ -239,6 +249,68 @@ def _parser_goldens():
     return {'source': 'hilo_mpc/util/parsing.py (whole module, executed with a stub casadi)', 'cases': cases}
 
 
+def _class_source(path, name):
+    src = open(path).read()
+    tree = ast.parse(src)
+    node = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == name)
+    return '\n'.join(src.split('\n')[node.lineno - 1:node.end_lineno]), (node.lineno, node.end_lineno)
+
+
+def _network_goldens():
+    """``Activation`` and ``net_to_casadi_graph`` (hilo_mpc/util/machine_learning.py:44-118, :521-578) executed from their
+    source text with the stub ``ca``: forward pass of trained weights incl. z-score scaling of inputs and outputs."""
+    path = os.path.join(REF, 'hilo_mpc', 'util', 'machine_learning.py')
+    ca = _stub_casadi_module()
+
+    class _Function:
+        def __init__(self, name, ins, outs, in_names, out_names):
+            self.ins, self.outs, self.out_names = ins, outs, out_names
+
+        def __call__(self, xv):
+            env = {s.name(): float(v) for s, v in zip(self.ins[0], xv)}
+            return {n: [float(_SX._f(e)(env)) for e in np.asarray(o, dtype=object).reshape(-1)]
+                    for n, o in zip(self.out_names, self.outs)}
+    ca.Function = _Function
+    src_a, span_a = _class_source(path, 'Activation')
+    src_f, span_f = _function_source(path, 'net_to_casadi_graph')
+    ns = {'ca': ca, 'np': np}
+    exec(src_a, ns)
+    exec(src_f, ns)
+
+    class _Layer:
+        def __init__(self, nodes, activation):
+            self.type, self.nodes, self.activation = 'dense', nodes, activation
+
+    class _Scaler:
+        def __init__(self, mean, scale):
+            self.mean_, self.scale_ = np.asarray(mean, dtype=float), np.asarray(scale, dtype=float)
+    cases = []
+    for seed, n_in, hidden, n_out, scaled in ((1, 3, [('tanh', 7)], 2, False), (2, 5, [('sigmoid', 6)], 4, True),
+                                              (3, 2, [('tanh', 5), ('softplus', 4)], 1, True),
+                                              (4, 4, [('linear', 3), ('tanh', 8)], 2, False)):
+        rng = np.random.RandomState(seed)
+        sizes = [n_in] + [h for _, h in hidden] + [n_out]
+        weights = [rng.normal(size=(sizes[k + 1], sizes[k])) for k in range(len(sizes) - 1)]
+        bias = [rng.normal(size=sizes[k + 1]) for k in range(len(sizes) - 1)]
+        kw = {}
+        if scaled:
+            kw = dict(input_scaling=_Scaler(rng.normal(size=n_in), rng.uniform(.5, 2., n_in)),
+                      output_scaling=_Scaler(rng.normal(size=n_out), rng.uniform(.5, 2., n_out)))
+        x = np.array([_SX.sym(f'x{k}') for k in range(n_in)], dtype=object)
+        fun = ns['net_to_casadi_graph']({'weights': weights, 'bias': bias}, x.copy(), [_Layer(h, a) for a, h in hidden], **kw)
+        fun.ins = [list(x)]      # the routine scales `h` in place; the inputs of the function are the plain symbols
+        pts = []
+        for _ in range(3):
+            xv = rng.normal(size=n_in)
+            pts.append({'x': xv.tolist(), 'out': fun(xv)})
+        cases.append({'n_in': n_in, 'hidden': [[a, h] for a, h in hidden], 'n_out': n_out,
+                      'weights': [w.tolist() for w in weights], 'bias': [b.tolist() for b in bias],
+                      'input_scaling': None if not scaled else [kw['input_scaling'].mean_.tolist(), kw['input_scaling'].scale_.tolist()],
+                      'output_scaling': None if not scaled else [kw['output_scaling'].mean_.tolist(), kw['output_scaling'].scale_.tolist()],
+                      'points': pts})
+    return {'source': f'hilo_mpc/util/machine_learning.py:{span_a[0]}-{span_a[1]}, {span_f[0]}-{span_f[1]}', 'cases': cases}
+
+
 def main():
     out = {'reference': 'hilo-mpc/hilo-mpc @ /root/reference', 'generator': 'tools/make_reference_goldens.py'}
     ca = _CaStub()
@@ -342,6 +414,9 @@ def main():
 
     # ---- equation-string parser (hilo_mpc/util/parsing.py), executed as a module with a stub `casadi`
     out['parser'] = _parser_goldens()
+
+    # ---- export of a trained feed-forward network to an expression graph (util/machine_learning.py)
+    out['net_to_graph'] = _network_goldens()
 
     with open(OUT, 'w') as f:
         json.dump(out, f)
