@@ -2,7 +2,8 @@
 (tools/make_reference_goldens.py; fixtures in tests/golden/reference_numeric.json): collocation constants
 (modeling.py:1092-1127), Latin-hypercube normal sampling (pf.py:425-447), the resampling / roughening / moment block of
 ParticleFilter.estimate (pf.py:405-421), the horizon of time-varying parameter values (mpc.py:293-333), the
-equation-string parser (util/parsing.py) and the export of trained networks (util/machine_learning.py:521-578)."""
+equation-string parser (util/parsing.py), the export of trained networks (util/machine_learning.py:521-578) and one
+interval of the collocation / explicit Runge-Kutta transcription (modeling.py:1129-1281)."""
 import json
 import os
 
@@ -139,3 +140,61 @@ def test_network_export_equals_the_reference(case):
         np.testing.assert_allclose(net.predict(x[:, None])[:, 0], pt['out']['labels'], rtol=1e-12, atol=1e-13)
         for F in funs:
             np.testing.assert_allclose(np.asarray(F(x)).reshape(-1), pt['out']['labels'], rtol=1e-12, atol=1e-13)
+
+
+def _toy_discretisation_problem(method, **opts):
+    """The toy problem of ``tools/make_reference_goldens.py::_discretisation_goldens`` through the public API."""
+    from hilo_mpc_b200 import Model, NMPC
+    from hilo_mpc_b200 import symbolic as sx
+    from oracle.nmpc import FlatNlp
+    m = Model(name='toy_disc')
+    x = m.set_dynamical_states(['x0', 'x1'])
+    u = m.set_inputs(['u0'])
+    p = m.set_parameters(['p0'])
+    t = m.time
+    m.set_dynamical_equations([x[1] + p[0] * sx.sin(t) * u[0], -x[0] * x[0] * x[1] + sx.cos(x[0]) * u[0] - .3 * t])
+    m.setup(dt=.1)
+    nmpc = NMPC(m)
+    nmpc.horizon = 2
+    nmpc.stage_cost.cost = x[0] * x[0] + .1 * u[0] * u[0] + x[1] * sx.sin(t)
+    nmpc.set_nlp_options(integration_method=method, **opts)
+    nmpc._build_module = False
+    nmpc.setup()
+    nlp = FlatNlp(nmpc.spec)
+    e = nlp._stage_exprs(True, False, False)
+    args = np.concatenate([e['w'], [e['t'], e['dt']], e['sp']])
+    F = sx.Function('stage', [('v', args)], [('g', np.asarray(e['g'], dtype=object)), ('J', np.array([e['J']], dtype=object))])
+    return F, nmpc.spec
+
+
+@pytest.mark.parametrize('case', range(len(GOLD['discretisation']['collocation'])))
+def test_collocation_interval_equals_the_reference(case):
+    """``RungeKutta._collocation`` (modeling.py:1129-1210) executed from source on a toy problem with explicit time
+    dependence and a Lagrange term: collocation equations ``dt f_i - sum_j C_ji X_j``, end state ``sum_i D_i X_i`` and
+    quadrature ``sum_i B_i l_i dt`` - including the time ``t + T[i - 1]`` at which the reference evaluates point i
+     - must be what the oracle's stage functions (and with them the NLP the engine is compared with)
+    contain."""
+    c = GOLD['discretisation']['collocation'][case]
+    deg = c['degree']
+    F, spec = _toy_discretisation_problem('collocation', degree=deg, collocation_points=c['points'])
+    assert spec.nsp == 1
+    for pt in c['evals']:
+        env = pt['env']
+        w = [env['x_0'], env['x_1'], env['u_0']] + [env[f'x_{k}_{i}'] for k in range(deg) for i in range(2)] + [0., 0.]
+        g, J = F(np.array(w + [env['t_0'], env['dt_0'], env['p_0']]))
+        g = np.asarray(g).reshape(-1)
+        np.testing.assert_allclose(g[:2 * deg], pt['ce'], rtol=1e-12, atol=1e-13)
+        np.testing.assert_allclose(-g[2 * deg:], pt['xf'], rtol=1e-12, atol=1e-13)      # g_N = x_next - x_f at x_next = 0
+        np.testing.assert_allclose(np.asarray(J).reshape(-1), pt['J'], rtol=1e-12, atol=1e-13)
+
+
+@pytest.mark.parametrize('case', range(len(GOLD['discretisation']['explicit'])))
+def test_explicit_runge_kutta_step_equals_the_reference(case):
+    """``RungeKutta._explicit`` (modeling.py:1213-1281) with the reference's Butcher tableaus for order 1-4."""
+    c = GOLD['discretisation']['explicit'][case]
+    F, spec = _toy_discretisation_problem('erk', order=c['order'])
+    for pt in c['evals']:
+        env = pt['env']
+        g, J = F(np.array([env['x_0'], env['x_1'], env['u_0'], 0., 0., env['t_0'], env['dt_0'], env['p_0']]))
+        np.testing.assert_allclose(-np.asarray(g).reshape(-1), pt['xf'], rtol=1e-12, atol=1e-13)
+        np.testing.assert_allclose(np.asarray(J).reshape(-1), pt['J'], rtol=1e-12, atol=1e-13)

@@ -12,6 +12,8 @@ the reference tree, executes it unmodified in a namespace with a *stub* ``ca`` (
 * the resampling / roughening / moment block of ``ParticleFilter.estimate`` (pf.py:405-421), with the legacy global RNG.
 * the equation-string parser (hilo_mpc/util/parsing.py, the whole module) and ``Activation`` / ``net_to_casadi_graph``
   (hilo_mpc/util/machine_learning.py) on symbols that are closures over a name -> value environment.
+* ``RungeKutta._collocation`` / ``RungeKutta._explicit`` (hilo_mpc/util/modeling.py:1129-1281): one interval of the
+  transcription on a toy problem, ``ca.Function`` calls with symbolic arguments emulated by re-binding names.
 * ``NMPC._get_tvp_parameters_values`` (mpc.py:293-333): the horizon of stored time-varying parameter values iteration by
   iteration, including what it does once the horizon runs past the end of the data.
 
@@ -94,8 +96,13 @@ class _SX:
 
     @staticmethod
     def _bin(a, b, op):
+        if isinstance(a, np.ndarray) or isinstance(b, np.ndarray):
+            return NotImplemented          # let numpy broadcast over vectors of symbols
         fa, fb = _SX._f(a), _SX._f(b)
         return _SX(lambda env: op(fa(env), fb(env)))
+
+    def zeros(self, n):                    # h.zeros(n) in RungeKutta._construct_polynomial_basis
+        return np.zeros(n, dtype=object)
 
     def __add__(self, o): return _SX._bin(self, o, lambda a, b: a + b)
     def __radd__(self, o): return _SX._bin(o, self, lambda a, b: a + b)
@@ -247,6 +254,118 @@ def _parser_goldens():
     finally:
         del sys.modules['casadi']
     return {'source': 'hilo_mpc/util/parsing.py (whole module, executed with a stub casadi)', 'cases': cases}
+
+
+class _Vec(np.ndarray):
+    """Vector / matrix of ``_SX`` scalars with the few ``casadi.SX`` methods the discretisation routines call."""
+
+    def __new__(cls, items=(), shape=None):
+        a = np.empty(len(items), dtype=object)
+        for k, v in enumerate(items):
+            a[k] = v
+        if shape is not None:
+            a = a.reshape(shape)
+        return a.view(cls)
+
+    def size1(self):
+        return self.shape[0] if self.ndim else 1
+
+    def is_empty(self):
+        return self.size == 0
+
+    @staticmethod
+    def sym(name, n=1):
+        if isinstance(n, tuple):
+            return _Vec([_SX.sym(f'{name}_{i}_{j}') for i in range(n[0]) for j in range(n[1])], shape=n)
+        return _Vec([_SX.sym(f'{name}_{i}') for i in range(n)])
+
+
+class _SymFunction:
+    """``ca.Function(name, ins, outs)`` on closures: a call with new (symbolic or numeric) arguments rebinds the names of
+    the input symbols in the environment the output closures are evaluated in."""
+
+    def __init__(self, name, ins, outs, *opts):
+        self.names = [[s.name() for s in np.asarray(v, dtype=object).reshape(-1)] for v in ins]
+        self.outs = [np.asarray(o, dtype=object).reshape(-1) for o in outs]
+
+    def __call__(self, *args):
+        binds = []
+        for names, a in zip(self.names, args):
+            vals = list(np.asarray(a, dtype=object).reshape(-1)) if not isinstance(a, _SX) else [a]
+            assert len(vals) == len(names), (names, vals)
+            binds += [(n, _SX._f(v)) for n, v in zip(names, vals)]
+
+        def rebound(e):
+            f = _SX._f(e)
+            return _SX(lambda env: f({**env, **{n: b(env) for n, b in binds}}))
+        res = [_Vec([rebound(e) for e in o]) for o in self.outs]
+        return res[0] if len(res) == 1 else res
+
+
+def _discretisation_goldens():
+    """``RungeKutta._collocation`` and ``RungeKutta._explicit`` (hilo_mpc/util/modeling.py:1128-1281) executed from source
+    on a toy problem with explicit time dependence and a Lagrange term: collocation equations, end state, quadrature /
+    one explicit Runge-Kutta step, evaluated at random points."""
+    path = os.path.join(REF, 'hilo_mpc', 'util', 'modeling.py')
+    ca = _stub_casadi_module()
+    ca.SX = _Vec
+    ca.MX = _Vec
+    ca.Function = _SymFunction
+    ca.vertcat = lambda *a: _Vec([e for v in a for e in np.asarray(v, dtype=object).reshape(-1)])
+    ca.collocation_points = _CaStub.collocation_points
+    src = open(path).read()
+    tree = ast.parse(src)
+    lines = src.split('\n')
+    node = next(n for n in tree.body if isinstance(n, ast.Assign) and getattr(n.targets[0], 'id', '') == 'EXPLICIT_METHODS')
+    ns = {'np': np, 'ca': ca, 'Symbolic': object}
+    exec('\n'.join(lines[node.lineno - 1:node.end_lineno]), ns)
+    spans = {}
+    body = []
+    for name, deco in (('_construct_polynomial_basis', '@staticmethod'), ('_collocation', '@classmethod'),
+                       ('_explicit', '@classmethod')):   # the decorators the methods carry in the reference
+        fsrc, spans[name] = _function_source(path, name, cls='RungeKutta')
+        body.append(textwrap.indent(deco + '\n' + fsrc.replace(deco + '\n', ''), '    '))
+    exec('class RungeKutta:\n' + '\n'.join(body), ns)
+    RK = ns['RungeKutta']
+
+    def problem():
+        t, dt = _Vec.sym('t'), _SX.sym('dt_0')
+        x, u, p = _Vec.sym('x', 2), _Vec.sym('u', 1), _Vec.sym('p', 1)
+        z = _Vec.sym('z', 0)
+        sin, cos = ca.sin, ca.cos
+        ode = _Vec([x[1] + p[0] * sin(t[0]) * u[0], -x[0] * x[0] * x[1] + cos(x[0]) * u[0] - .3 * t[0]])
+        quad = _Vec([x[0] * x[0] + .1 * u[0] * u[0] + x[1] * sin(t[0])])
+        return dict(ode=ode, alg=_Vec([]), quad=quad, meas=None, t=t, x=x, z=z, u=u, p=p, dt=dt)
+    out = {'source': f"hilo_mpc/util/modeling.py:{spans['_collocation'][0]}-{spans['_explicit'][1]}",
+           'toy': 'x0\' = x1 + p sin(t) u,  x1\' = -x0^2 x1 + cos(x0) u - 0.3 t,  l = x0^2 + 0.1 u^2 + x1 sin(t)',
+           'collocation': [], 'explicit': []}
+    rng = np.random.RandomState(12)
+
+    def ev(e, env):
+        return [float(_SX._f(v)(env)) for v in np.asarray(e, dtype=object).reshape(-1)]
+    for points in ('radau', 'legendre'):
+        for degree in (2, 3, 4):
+            pr = problem()
+            RK._collocation(pr, degree=degree, collocation_points=points)
+            pts = []
+            for _ in range(2):
+                env = {'t_0': rng.uniform(0., 2.), 'dt_0': rng.uniform(.05, .5), 'x_0': rng.normal(), 'x_1': rng.normal(),
+                       'u_0': rng.normal(), 'p_0': rng.normal()}
+                for k in range(degree):
+                    env[f'x_{k}_0'], env[f'x_{k}_1'] = rng.normal(), rng.normal()
+                pts.append({'env': env, 'ce': ev(pr['collocation_equations'], env), 'xf': ev(pr['ode'], env),
+                            'J': ev(pr['quad'], env)})
+            out['collocation'].append({'points': points, 'degree': degree, 'evals': pts})
+    for order in (1, 2, 3, 4):
+        pr = problem()
+        RK._explicit(pr, order=order)
+        pts = []
+        for _ in range(2):
+            env = {'t_0': rng.uniform(0., 2.), 'dt_0': rng.uniform(.05, .5), 'x_0': rng.normal(), 'x_1': rng.normal(),
+                   'u_0': rng.normal(), 'p_0': rng.normal()}
+            pts.append({'env': env, 'xf': ev(pr['ode'], env), 'J': ev(pr['quad'], env)})
+        out['explicit'].append({'order': order, 'evals': pts})
+    return out
 
 
 def _class_source(path, name):
@@ -417,6 +536,9 @@ def main():
 
     # ---- export of a trained feed-forward network to an expression graph (util/machine_learning.py)
     out['net_to_graph'] = _network_goldens()
+
+    # ---- one interval of the collocation / explicit Runge-Kutta transcription (util/modeling.py)
+    out['discretisation'] = _discretisation_goldens()
 
     with open(OUT, 'w') as f:
         json.dump(out, f)
