@@ -12,8 +12,15 @@ Parity status:
   Gram matrices / GP-LML / fitted GP hyper-parameters (gpml values, with and without a trainable mean): pinned by the
   golden numbers in the reference's own tests (``tests/test_KFs.py``, ``tests/test_LQR.py``, ``tests/test_kernels.py``,
   ``tests/test_GPs.py``) — reproduced in ``tests/test_oracle_golden.py``.
-* NMPC / LMPC / MHE / PF-estimate: the reference's tests hold NO numeric assertion for these and the reference
-  cannot be executed here (``casadi`` is not installed) -> "parity unpinned" at the IPOPT/qpOASES boundary.  The
+* Pinned by EXECUTING reference source under a stub ``casadi`` (``tools/make_reference_goldens.py`` ->
+  ``tests/golden/reference_numeric.json``, ``tests/test_reference_numeric_goldens.py``): the collocation constants
+  (``modeling.py:1092-1127``), one interval of the collocation and of the explicit Runge-Kutta transcription
+  (``RungeKutta._collocation`` / ``_explicit``, ``modeling.py:1129-1281``) against the stage functions of ``FlatNlp``,
+  ``lhsnorm`` and the PF resampling / roughening / moment block (``pf.py:405-447``), the horizon of time-varying parameter
+  values (``mpc.py:293-333``), the equation-string parser (``util/parsing.py``), the export of trained networks
+  (``util/machine_learning.py:521-578``).
+* NMPC / LMPC / MHE solves: the reference's tests hold NO numeric assertion for these and IPOPT / qpOASES cannot be run
+  here (``casadi`` is not installed) -> "parity unpinned" at the IPOPT/qpOASES boundary only.  The
   oracle restates the transcription exactly and is validated by its own KKT residual, by SciPy's independent
   solvers (SLSQP on the flat NMPC and MHE problems, trust-constr on the condensed LMPC QP:
   ``tests/test_oracle_crosscheck.py``, ``tests/test_hostsim_lmpc_mhe.py``) and by the LQR golden in the linear-quadratic
