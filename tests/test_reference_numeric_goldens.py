@@ -198,3 +198,44 @@ def test_explicit_runge_kutta_step_equals_the_reference(case):
         g, J = F(np.array([env['x_0'], env['x_1'], env['u_0'], 0., 0., env['t_0'], env['dt_0'], env['p_0']]))
         np.testing.assert_allclose(-np.asarray(g).reshape(-1), pt['xf'], rtol=1e-12, atol=1e-13)
         np.testing.assert_allclose(np.asarray(J).reshape(-1), pt['J'], rtol=1e-12, atol=1e-13)
+
+
+@pytest.mark.parametrize('case', range(len(GOLD['quadratic_cost']['cases'])))
+def test_quadratic_stage_cost_equals_the_reference(case):
+    """``QuadraticCost`` (modeling.py:89-531) executed from its class source the way ``NMPC._define_cost_terms`` drives it
+    (mpc.py:207-242): scaled references (``ref / scale[ind]``), stabilisation terms, a full weight matrix and the
+    input-change term with its ``u_old`` placeholder.  The Lagrange term the product hands to the kernels must be the same
+    function of the scaled variables."""
+    from hilo_mpc_b200 import Model, NMPC
+    from hilo_mpc_b200 import symbolic as sx
+    c = GOLD['quadratic_cost']['cases'][case]
+    m = Model(name=f'cost_case{case}')
+    x = m.set_dynamical_states(['c_A', 'c_B', 'T'])
+    u = m.set_inputs(['F', 'Q'])
+    m.set_dynamical_equations([-x[0] + u[0], x[0] - x[1], -x[2] + u[1]])
+    m.setup(dt=.1)
+    nmpc = NMPC(m)
+    nmpc.horizon = 3
+    q = nmpc.quad_stage_cost
+    if c['label'] == 'reference_tracking_scaled':
+        q.add_states(names=['c_A', 'T'], weights=[1., 10.], ref=[2.1, 110.])
+        q.add_inputs(names=['F', 'Q'], weights=[.1, .2], ref=[14., -1100.])
+    elif c['label'] == 'stabilisation_and_matrix_weight':
+        q.add_states(names=['c_B'], weights=3.)
+        q.add_inputs(names=['Q', 'F'], weights=np.array([[2., .5], [.5, 1.]]))
+    else:
+        q.add_states(names=['c_A', 'c_B', 'T'], weights=[1., 2., 3.], ref=[1., 1., 100.])
+        q.add_inputs_change(names=['F'], weights=[5.])
+        q.add_inputs_change(names=['Q'], weights=[7.])
+    nmpc.set_scaling(x_scaling=c['x_scale'], u_scaling=c['u_scale'])
+    nmpc._build_module = False
+    nmpc.setup()
+    s = nmpc.spec
+    assert list(nmpc._du_ind) == c['ind_input_changes']
+    lag = s.lag if s.lag_du is None else s.lag + s.lag_du
+    args = np.concatenate([s.x, s.u, s.uold])
+    F = sx.Function('lag', [('v', args)], [('l', np.array([lag], dtype=object))])
+    for pt in c['points']:
+        env = pt['env']
+        vals = [env[n] for n in ('c_A', 'c_B', 'T', 'F', 'Q')] + [env[n] for n in c['u_old_names']]
+        np.testing.assert_allclose(float(np.asarray(F(np.array(vals))).reshape(-1)[0]), pt['cost'], rtol=1e-12)

@@ -368,6 +368,87 @@ def _discretisation_goldens():
     return out
 
 
+def _quadratic_cost_goldens():
+    """``GenericCost`` + ``QuadraticCost`` (hilo_mpc/util/modeling.py:38-531) executed from their class sources (helpers
+    from hilo_mpc/util/util.py likewise) on a stub model: reference tracking of states and inputs with scaling, a
+    stabilisation term, a full weight matrix and the input-change term, exactly as ``NMPC._define_cost_terms`` sets them
+    up (mpc.py:207-242).  Stored: the cost as a function of the (scaled) model variables and the ``u_old`` placeholder."""
+    import collections
+    path = os.path.join(REF, 'hilo_mpc', 'util', 'modeling.py')
+    upath = os.path.join(REF, 'hilo_mpc', 'util', 'util.py')
+    ca = _stub_casadi_module()
+
+    class _DM(np.ndarray):
+        def __new__(cls, a=()):
+            return np.asarray(a, dtype=float).view(cls)
+    ca.DM = _DM
+    ca.SX = _Vec
+    ca.MX = type('_MX', (), {})          # nothing is an MX here
+    ca.vertcat = lambda *a: _Vec([e for v in a for e in np.asarray(v, dtype=object).reshape(-1)])
+    ca.mtimes = lambda a, b: np.dot(a, b)
+
+    def substitute(expr, old, new):
+        names = [sym.name() for sym in np.asarray(old, dtype=object).reshape(-1)]
+        vals = [_SX._f(v) for v in np.asarray(new, dtype=object).reshape(-1)]
+        assert len(names) == len(vals)
+
+        def rebound(e):
+            f = _SX._f(e)
+            return _SX(lambda env: f({**env, **{n: v(env) for n, v in zip(names, vals)}}))
+        if isinstance(expr, np.ndarray):
+            return _Vec([rebound(e) for e in expr.reshape(-1)])
+        return rebound(expr)
+    ca.substitute = substitute
+    ns = {'np': np, 'ca': ca, 'sys': sys, 'warnings': __import__('warnings')}
+    for name in ('check_and_wrap_to_list', 'check_if_has_duplicates', 'check_if_list_of_type', 'check_if_list_of_none',
+                 'check_if_square', 'who_am_i'):
+        exec(_function_source(upath, name)[0], ns)
+    spans = {}
+    for name in ('GenericCost', 'QuadraticCost'):
+        src, spans[name] = _class_source(path, name)
+        exec(src, ns)
+
+    class _Names(_Vec):
+        pass
+
+    def named(names):
+        v = _Vec([_SX.sym(n) for n in names]).view(_Names)
+        v._names = list(names)
+        return v
+
+    class _Model:
+        def __init__(self):
+            self._x, self._u, self._y = named(['c_A', 'c_B', 'T']), named(['F', 'Q']), named([])
+            self.dynamical_state_names, self.input_names, self.measurement_names = self._x._names, self._u._names, []
+            self.n_y, self.meas = 0, _Vec([])
+    cases = []
+    rng = np.random.RandomState(21)
+    x_scale, u_scale = [1., 2., 100.], [10., 1000.]
+    setups = collections.OrderedDict([
+        ('reference_tracking_scaled', lambda q: (q.add_states(names=['c_A', 'T'], weights=[1., 10.], ref=[2.1, 110.]),
+                                                 q.add_inputs(names=['F', 'Q'], weights=[.1, .2], ref=[14., -1100.]))),
+        ('stabilisation_and_matrix_weight', lambda q: (q.add_states(names=['c_B'], weights=3.),
+                                                       q.add_inputs(names=['Q', 'F'], weights=np.array([[2., .5], [.5, 1.]])))),
+        ('input_change', lambda q: (q.add_states(names=['c_A', 'c_B', 'T'], weights=[1., 2., 3.], ref=[1., 1., 100.]),
+                                    q.add_inputs_change(names=['F'], weights=[5.]),
+                                    q.add_inputs_change(names=['Q'], weights=[7.]))),
+    ])
+    for label, build in setups.items():
+        model = _Model()
+        q = ns['QuadraticCost'](model)
+        build(q)
+        q._setup(x_scale=x_scale, u_scale=u_scale, y_scale=[], path_variables=[], time_variable=None)
+        old_names = [sym.name() for sym in np.asarray(q.input_change_placeholder, dtype=object).reshape(-1)] \
+            if len(q.input_change_placeholder) else []
+        pts = []
+        for _ in range(3):
+            env = {n: float(rng.normal()) for n in model._x._names + model._u._names + old_names}
+            pts.append({'env': env, 'cost': float(_SX._f(q.cost)(env))})
+        cases.append({'label': label, 'x_scale': x_scale, 'u_scale': u_scale, 'u_old_names': old_names,
+                      'ind_input_changes': [int(i) for i in q._ind_input_changes], 'points': pts})
+    return {'source': f"hilo_mpc/util/modeling.py:{spans['GenericCost'][0]}-{spans['QuadraticCost'][1]}", 'cases': cases}
+
+
 def _class_source(path, name):
     src = open(path).read()
     tree = ast.parse(src)
@@ -539,6 +620,9 @@ def main():
 
     # ---- one interval of the collocation / explicit Runge-Kutta transcription (util/modeling.py)
     out['discretisation'] = _discretisation_goldens()
+
+    # ---- quadratic stage cost incl. scaled references and the input-change term (util/modeling.py)
+    out['quadratic_cost'] = _quadratic_cost_goldens()
 
     with open(OUT, 'w') as f:
         json.dump(out, f)
