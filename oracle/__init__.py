@@ -16,7 +16,8 @@ Parity status:
   ``tests/golden/reference_numeric.json``, ``tests/test_reference_numeric_goldens.py``): the collocation constants
   (``modeling.py:1092-1127``), one interval of the collocation and of the explicit Runge-Kutta transcription
   (``RungeKutta._collocation`` / ``_explicit``, ``modeling.py:1129-1281``) against the stage functions of ``FlatNlp``,
-  the quadratic stage cost incl. scaled references and the input-change term (``QuadraticCost``, ``modeling.py:38-531``),
+  the quadratic costs incl. scaled references, the input-change term and the MHE flavour on physical quantities
+  (``QuadraticCost`` / ``MHEQuadraticCost``, ``modeling.py:38-818``),
   ``lhsnorm`` and the PF resampling / roughening / moment block (``pf.py:405-447``), the horizon of time-varying parameter
   values (``mpc.py:293-333``), the equation-string parser (``util/parsing.py``), the export of trained networks
   (``util/machine_learning.py:521-578``).

@@ -239,3 +239,42 @@ def test_quadratic_stage_cost_equals_the_reference(case):
         env = pt['env']
         vals = [env[n] for n in ('c_A', 'c_B', 'T', 'F', 'Q')] + [env[n] for n in c['u_old_names']]
         np.testing.assert_allclose(float(np.asarray(F(np.array(vals))).reshape(-1)[0]), pt['cost'], rtol=1e-12)
+
+
+def test_mhe_quadratic_costs_equal_the_reference():
+    """``MHEQuadraticCost`` (modeling.py:533-818) executed from its class source: arrival cost on states and parameters
+    with guesses as placeholders, stage cost on measurements and state noise, all on PHYSICAL quantities (``_setup``
+    substitutes ``x -> x * scale``, modeling.py:668-684).  ``MHE.setup`` must hand the same functions of the scaled
+    variables to the kernels."""
+    from hilo_mpc_b200 import MHE, Model
+    from hilo_mpc_b200 import symbolic as sx
+    g = GOLD['quadratic_cost']['mhe']
+    m = Model(name='mhe_cost_case')
+    x = m.set_dynamical_states(['a', 'b'])
+    u = m.set_inputs(['f'])
+    p = m.set_parameters(['k'])
+    m.set_measurements(['y1', 'y2'])
+    m.set_measurement_equations([x[0] * x[1] + p[0], x[1] * u[0]])
+    m.set_dynamical_equations([-p[0] * x[0] + u[0], x[0] - x[1]])
+    m.setup(dt=.1)
+    mhe = MHE(m)
+    mhe.horizon = 3
+    mhe.quad_arrival_cost.add_states(weights=[10., 5.], guess=[.5, .2])
+    mhe.quad_arrival_cost.add_parameters(weights=[2.], guess=[1.])
+    mhe.quad_stage_cost.add_measurements(weights=[100., 10.])
+    mhe.quad_stage_cost.add_state_noise(weights=[20., 30.])
+    mhe.set_scaling(x_scaling=g['x_scale'], p_scaling=g['p_scale'], w_scaling=g['w_scale'])
+    mhe._build_module = False
+    mhe.setup()
+    s = mhe.spec
+    Fa = sx.Function('arr', [('v', np.concatenate([s.x, s.ap]))], [('c', np.array([s.arr], dtype=object))])
+    Fs = sx.Function('lag', [('v', np.concatenate([s.x, s.u, s.sp]))], [('c', np.array([s.lag], dtype=object))])
+    for pt in g['points']:
+        e = pt['env']
+        xa = [e['a'], e['b'], e['k']]                              # scaled states, then the scaled parameter
+        arr = Fa(np.array(xa + [e[n] for n in g['arrival_placeholders']]))
+        np.testing.assert_allclose(float(np.asarray(arr).reshape(-1)[0]), pt['arrival'], rtol=1e-12)
+        w = [e[n] for n in g['w_names']]
+        sp = [e['f']] + [e[n] for n in g['stage_placeholders']]    # [u_meas | y_meas]
+        lag = Fs(np.array(xa + w + sp))
+        np.testing.assert_allclose(float(np.asarray(lag).reshape(-1)[0]), pt['stage'], rtol=1e-12)

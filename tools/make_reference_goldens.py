@@ -446,7 +446,43 @@ def _quadratic_cost_goldens():
             pts.append({'env': env, 'cost': float(_SX._f(q.cost)(env))})
         cases.append({'label': label, 'x_scale': x_scale, 'u_scale': u_scale, 'u_old_names': old_names,
                       'ind_input_changes': [int(i) for i in q._ind_input_changes], 'points': pts})
-    return {'source': f"hilo_mpc/util/modeling.py:{spans['GenericCost'][0]}-{spans['QuadraticCost'][1]}", 'cases': cases}
+    # ---- the MHE flavour: costs on PHYSICAL quantities (x -> x * scale is substituted in _setup), guesses and
+    # measurements as placeholders
+    src, spans['MHEQuadraticCost'] = _class_source(path, 'MHEQuadraticCost')
+    exec(src, ns)
+
+    class _MheModel:
+        def __init__(self):
+            self.x, self.p, self.u, self.y = named(['a', 'b']), named(['k']), named(['f']), named(['y1', 'y2'])
+            self._x, self._p, self._u, self._y = self.x, self.p, self.u, self.y
+            self.dynamical_state_names, self.parameter_names = self.x._names, self.p._names
+            self.input_names, self.measurement_names = self.u._names, self.y._names
+            self.n_x, self.n_p, self.n_u, self.n_y = 2, 1, 1, 2
+            self.meas = _Vec([self.x[0] * self.x[1] + self.p[0], self.x[1] * self.u[0]])
+    xs, ps, ws = [2., 5.], [3.], [.5, .25]
+    mm = _MheModel()
+    arr = ns['MHEQuadraticCost'](mm)
+    arr.add_states(weights=[10., 5.], guess=[.5, .2])
+    arr.add_parameters(weights=[2.], guess=[1.])
+    arr._setup(x_scale=xs, w_scale=ws, p_scale=ps, u_scale=[1.])
+    stg = ns['MHEQuadraticCost'](mm)
+    stg.add_measurements(weights=[100., 10.])
+    stg.add_state_noise(weights=[20., 30.])
+    stg._setup(x_scale=xs, w_scale=ws, p_scale=ps, u_scale=[1.])
+
+    def placeholders(q):
+        return [sym.name() for lst in (q._iter_ref_list, q._tv_ref_list) for r in lst
+                for sym in np.asarray(r['placeholder'], dtype=object).reshape(-1)]
+    mhe_pts = []
+    w_names = [sym.name() for sym in np.asarray(stg._w, dtype=object).reshape(-1)]
+    for _ in range(3):
+        env = {n: float(rng.normal()) for n in ['a', 'b', 'k', 'f'] + w_names + placeholders(arr) + placeholders(stg)}
+        mhe_pts.append({'env': env, 'arrival': float(_SX._f(arr.cost)(env)), 'stage': float(_SX._f(stg.cost)(env))})
+    mhe = {'x_scale': xs, 'p_scale': ps, 'w_scale': ws, 'w_names': w_names, 'arrival_placeholders': placeholders(arr),
+           'stage_placeholders': placeholders(stg), 'points': mhe_pts,
+           'model': "x = [a, b], p = [k], u = [f], y1 = a b + k, y2 = b f"}
+    return {'source': f"hilo_mpc/util/modeling.py:{spans['GenericCost'][0]}-{spans['MHEQuadraticCost'][1]}", 'cases': cases,
+            'mhe': mhe}
 
 
 def _class_source(path, name):
