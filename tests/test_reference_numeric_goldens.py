@@ -278,3 +278,46 @@ def test_mhe_quadratic_costs_equal_the_reference():
         sp = [e['f']] + [e[n] for n in g['stage_placeholders']]    # [u_meas | y_meas]
         lag = Fs(np.array(xa + w + sp))
         np.testing.assert_allclose(float(np.asarray(lag).reshape(-1)[0]), pt['stage'], rtol=1e-12)
+
+
+@pytest.mark.parametrize('case', range(len(GOLD['lmpc_matrices']['cases'])))
+def test_lmpc_qp_matrices_equal_the_reference(case):
+    """The matrix construction of ``LMPC.setup`` (mpc.py:2179-2266) executed from its source lines: ``H``, the equality
+    block ``Aeq`` - whose input block really is ``kron(B, I_N)`` -, tiled bounds and index lists.  The
+    oracle's flat QP must be these matrices entry by entry, and the product's condensed form (``bug_compat=True``) must
+    be their elimination: ``Aeq [x_0; Phi x_0 + Gam u; u] = 0`` and the same objective."""
+    from oracle.lmpc import lmpc_flat_qp
+    c = GOLD['lmpc_matrices']['cases'][case]
+    A, B, Q, R, P = (np.array(c[k]) for k in ('A', 'B', 'Q', 'R', 'P'))
+    nx, nu, N = c['nx'], c['nu'], c['N']
+    H, Aeq = lmpc_flat_qp(A, B, Q, R, P, N, bug_compat=True)
+    np.testing.assert_array_equal(H, np.array(c['H']))
+    np.testing.assert_array_equal(Aeq, np.array(c['Aeq']))
+    assert not np.any(np.array(c['beq']))
+    intended = lmpc_flat_qp(A, B, Q, R, P, N, bug_compat=False)[1]
+    assert np.array_equal(intended, Aeq) == (nx == 1 and nu == 1)            # the two only coincide for scalars
+    assert c['x_ind'] == [list(range(k * nx, (k + 1) * nx)) for k in range(N + 1)]
+    assert c['u_ind'] == [list(range((N + 1) * nx + k * nu, (N + 1) * nx + (k + 1) * nu)) for k in range(N)]
+    # product: condensed matrices of the same QP
+    from hilo_mpc_b200 import LMPC, Model
+    m = Model(discrete=True, name=f'lmpc_case{case}')
+    m.A, m.B = A, B
+    m.setup(dt=1.)
+    mpc = LMPC(m, bug_compat=True)
+    mpc.Q, mpc.R, mpc.P, mpc.horizon = Q, R, P, N
+    mpc.set_box_constraints(x_lb=list(-np.arange(1, nx + 1.)), x_ub=list(2 * np.arange(1, nx + 1.)), u_lb=[-1.] * nu,
+                            u_ub=[3.] * nu)
+    mpc._build_module = False
+    mpc.setup(solver='condensed')
+    cd = mpc._condensed
+    np.testing.assert_array_equal(np.concatenate([np.tile(mpc.spec.x_lb, N + 1), cd['ulb']]), np.array(c['v_lb']))
+    np.testing.assert_array_equal(np.concatenate([np.tile(mpc.spec.x_ub, N + 1), cd['uub']]), np.array(c['v_ub']))
+    rng = np.random.default_rng(case)
+    for _ in range(3):
+        x0, u = rng.normal(size=nx), rng.normal(size=N * nu)
+        v = np.concatenate([x0, cd['Phi'] @ x0 + cd['Gam'] @ u, u])
+        np.testing.assert_allclose(np.array(c['Aeq']) @ v, 0., atol=1e-11)
+        full = .5 * v @ np.array(c['H']) @ v
+        cond = .5 * u @ cd['H'] @ u + (cd['F'] @ x0) @ u
+        v0 = np.concatenate([x0, cd['Phi'] @ x0, np.zeros(N * nu)])
+        np.testing.assert_allclose(full - .5 * v0 @ np.array(c['H']) @ v0, cond, rtol=1e-10, atol=1e-11)

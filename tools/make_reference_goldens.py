@@ -14,6 +14,8 @@ the reference tree, executes it unmodified in a namespace with a *stub* ``ca`` (
   (hilo_mpc/util/machine_learning.py) on symbols that are closures over a name -> value environment.
 * ``RungeKutta._collocation`` / ``RungeKutta._explicit`` (hilo_mpc/util/modeling.py:1129-1281): one interval of the
   transcription on a toy problem, ``ca.Function`` calls with symbolic arguments emulated by re-binding names.
+* ``GenericCost`` / ``QuadraticCost`` / ``MHEQuadraticCost`` (hilo_mpc/util/modeling.py:38-818) from their class sources on
+  stub models, and the matrix-construction lines of ``LMPC.setup`` (mpc.py:2179-2266) with a numeric stub.
 * ``NMPC._get_tvp_parameters_values`` (mpc.py:293-333): the horizon of stored time-varying parameter values iteration by
   iteration, including what it does once the horizon runs past the end of the data.
 
@@ -485,6 +487,69 @@ def _quadratic_cost_goldens():
             'mhe': mhe}
 
 
+def _lmpc_goldens():
+    """The matrix construction of ``LMPC.setup`` (hilo_mpc/modules/controller/mpc.py, from ``n_x = self._n_x`` to
+    ``v_ub = ca.vertcat(...)``) executed from its source lines with a numeric stub ``ca`` (DM = NumPy arrays): the QP the
+    reference really hands to qpOASES - in particular the input block of the equality constraints."""
+    import scipy.linalg
+    path = os.path.join(REF, 'hilo_mpc', 'modules', 'controller', 'mpc.py')
+    lines = open(path).read().split('\n')
+    tree = ast.parse('\n'.join(lines))
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == 'LMPC')
+    fn = next(n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name == 'setup')
+    body = lines[fn.lineno - 1:fn.end_lineno]
+    start = next(i for i, ln in enumerate(body) if ln.strip() == 'n_x = self._n_x')
+    end = next(i for i, ln in enumerate(body) if ln.strip().startswith('v_ub = ca.vertcat('))
+    block = textwrap.dedent('\n'.join(body[start:end + 1]))
+
+    class _DMns:
+        @staticmethod
+        def zeros(*shape):
+            shape = shape[0] if len(shape) == 1 and isinstance(shape[0], tuple) else shape
+            return np.zeros(shape if len(shape) > 1 else (shape[0], 1))
+
+        @staticmethod
+        def ones(*shape):
+            shape = shape[0] if len(shape) == 1 and isinstance(shape[0], tuple) else shape
+            return np.ones(shape if len(shape) > 1 else (shape[0], 1))
+
+        @staticmethod
+        def eye(n):
+            return np.eye(n)
+    ca = type('ca', (), {})()
+    ca.DM = _DMns
+    ca.kron = lambda a, b: np.kron(np.atleast_2d(a), np.atleast_2d(b))
+    ca.horzcat = lambda *a: np.hstack([np.atleast_2d(v) for v in a])
+    ca.vertcat = lambda *a: np.vstack([np.atleast_2d(v) for v in a])
+    ca.diagcat = lambda *a: scipy.linalg.block_diag(*a)
+    cases = []
+    rng = np.random.RandomState(8)
+    for nx, nu, N in ((2, 1, 10), (2, 1, 3), (3, 2, 4), (1, 1, 5)):
+        if (nx, nu) == (2, 1):
+            A, B = np.array([[1., .5], [0., 1.]]), np.array([[.125], [.5]])      # double integrator, tests/test_LMPC.py:8-33
+        else:
+            A, B = rng.normal(size=(nx, nx)), rng.normal(size=(nx, nu))
+        Q, R, P = np.diag(rng.uniform(.5, 2., nx)), np.diag(rng.uniform(.5, 2., nu)), np.diag(rng.uniform(.5, 2., nx))
+
+        class _Mdl:
+            state_matrix, input_matrix, n_x = A, B, nx
+
+        class _Self:
+            _n_x, _n_u, _horizon, horizon, _n_tvp = nx, nu, N, N, 0
+            _model = _Mdl()
+            _x_lb, _x_ub = -np.arange(1, nx + 1.).reshape(-1, 1), np.arange(1, nx + 1.).reshape(-1, 1) * 2
+            _u_lb, _u_ub = -np.ones((nu, 1)), np.ones((nu, 1)) * 3
+        obj = _Self()
+        obj.Q, obj.R, obj.P = Q, R, P
+        env = {'np': np, 'ca': ca, 'self': obj}
+        exec(block, env)
+        cases.append({'nx': nx, 'nu': nu, 'N': N, 'A': A.tolist(), 'B': B.tolist(), 'Q': Q.tolist(), 'R': R.tolist(),
+                      'P': P.tolist(), 'Aeq': np.asarray(env['Aeq']).tolist(), 'beq': np.asarray(env['beq']).reshape(-1).tolist(),
+                      'H': np.asarray(env['H']).tolist(), 'v_lb': np.asarray(env['v_lb']).reshape(-1).tolist(),
+                      'v_ub': np.asarray(env['v_ub']).reshape(-1).tolist(), 'x_ind': env['x_ind'], 'u_ind': env['u_ind']})
+    return {'source': f'hilo_mpc/modules/controller/mpc.py:{fn.lineno + start}-{fn.lineno + end}', 'cases': cases}
+
+
 def _class_source(path, name):
     src = open(path).read()
     tree = ast.parse(src)
@@ -659,6 +724,9 @@ def main():
 
     # ---- quadratic stage cost incl. scaled references and the input-change term (util/modeling.py)
     out['quadratic_cost'] = _quadratic_cost_goldens()
+
+    # ---- the QP matrices LMPC.setup builds (mpc.py)
+    out['lmpc_matrices'] = _lmpc_goldens()
 
     with open(OUT, 'w') as f:
         json.dump(out, f)
