@@ -3,7 +3,8 @@
 (modeling.py:1092-1127), Latin-hypercube normal sampling (pf.py:425-447), the resampling / roughening / moment block of
 ParticleFilter.estimate (pf.py:405-421), the horizon of time-varying parameter values (mpc.py:293-333), the
 equation-string parser (util/parsing.py), the export of trained networks (util/machine_learning.py:521-578) and one
-interval of the collocation / explicit Runge-Kutta transcription (modeling.py:1129-1281)."""
+interval of the collocation / explicit Runge-Kutta transcription (modeling.py:1129-1281), the quadratic cost classes
+(modeling.py:38-818), the QP matrices of LMPC.setup (mpc.py:2179-2266) and the horizon loop of NMPC._setup."""
 import json
 import os
 
@@ -321,3 +322,48 @@ def test_lmpc_qp_matrices_equal_the_reference(case):
         cond = .5 * u @ cd['H'] @ u + (cd['F'] @ x0) @ u
         v0 = np.concatenate([x0, cd['Phi'] @ x0, np.zeros(N * nu)])
         np.testing.assert_allclose(full - .5 * v0 @ np.array(c['H']) @ v0, cond, rtol=1e-10, atol=1e-11)
+
+
+def test_nmpc_horizon_assembly_equals_the_reference():
+    """The horizon loop of ``NMPC._setup`` (mpc.py, ``for ii in range(self._prediction_horizon)`` ... ``time += dt_ii``)
+    executed from its source lines around the executed ``RungeKutta._collocation``: constraint vector (collocation and
+    continuity equations interval by interval), objective (sum of the quadratures + Mayer term at ``time + dt`` of the last
+    interval), running time with per-interval ``dt`` and the ``u_old`` rule (parameter in interval 0, the interval's own
+    input afterwards - the input-change cost vanishes there).  The oracle's NLP callback, built from the
+    product's ``OcpSpec`` of the same problem, must give the same ``f`` and ``g``."""
+    from hilo_mpc_b200 import Model, NMPC
+    from hilo_mpc_b200 import symbolic as sx
+    from oracle.nmpc import FlatNlp
+    G = GOLD['nmpc_assembly']
+    N, deg = G['N'], G['degree']
+    assert G['g_lb_ub_all_zero']
+    m = Model(name='toy_assembly')
+    x = m.set_dynamical_states(['x0', 'x1'])
+    u = m.set_inputs(['u0'])
+    p = m.set_parameters(['p0'])
+    t = m.time
+    m.set_dynamical_equations([x[1] + p[0] * sx.sin(t) * u[0], -x[0] * x[0] * x[1] + sx.cos(x[0]) * u[0] - .3 * t])
+    m.setup(dt=.1)
+    nmpc = NMPC(m)
+    nmpc.horizon = N
+    nmpc.stage_cost.cost = x[0] * x[0] + .1 * u[0] * u[0] + x[1] * sx.sin(t)
+    nmpc.quad_stage_cost.add_inputs_change(names=['u0'], weights=[5.])
+    nmpc.terminal_cost.cost = 2. * x[0] * x[0] + x[1] * x[1] + .1 * t * x[0]
+    nmpc.set_nlp_options(integration_method='collocation', degree=deg, collocation_points='radau')
+    nmpc._build_module = False
+    nmpc.setup()
+    nlp = FlatNlp(nmpc.spec)
+    assert nlp.n_g == N * (deg * 2 + 2)
+    for pt in G['points']:
+        e = pt['env']
+        v = np.zeros(nlp.n_v)
+        for k in range(N + 1):
+            v[nlp.x_ind[k]] = [e[f'X{k}_0'], e[f'X{k}_1']]
+        for k in range(N):
+            v[nlp.u_ind[k]] = [e[f'U{k}_0']]
+            v[nlp.c_ind[k]] = [e[f'C{k}_{i}'] for i in range(deg * 2)]
+        dts = np.array([e[f'PDT_{k}'] for k in range(N)])
+        cb = nlp.callback(e['PTIME_0'], dts, np.full((N, 1), e['CP_0']), np.zeros(0), np.array([e['UOLD_0']]))
+        f, _, g, _, _ = cb(v, None)
+        np.testing.assert_allclose(g, pt['g'], rtol=1e-12, atol=1e-13)
+        np.testing.assert_allclose(f, pt['J'], rtol=1e-12)

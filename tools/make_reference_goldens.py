@@ -16,6 +16,8 @@ the reference tree, executes it unmodified in a namespace with a *stub* ``ca`` (
   transcription on a toy problem, ``ca.Function`` calls with symbolic arguments emulated by re-binding names.
 * ``GenericCost`` / ``QuadraticCost`` / ``MHEQuadraticCost`` (hilo_mpc/util/modeling.py:38-818) from their class sources on
   stub models, and the matrix-construction lines of ``LMPC.setup`` (mpc.py:2179-2266) with a numeric stub.
+* the horizon loop of ``NMPC._setup`` (mpc.py: ``for ii in range(self._prediction_horizon)`` ... ``time += dt_ii``) around
+  the executed ``RungeKutta._collocation``: objective and constraint vector of the whole NLP.
 * ``NMPC._get_tvp_parameters_values`` (mpc.py:293-333): the horizon of stored time-varying parameter values iteration by
   iteration, including what it does once the horizon runs past the end of the data.
 
@@ -550,6 +552,112 @@ def _lmpc_goldens():
     return {'source': f'hilo_mpc/modules/controller/mpc.py:{fn.lineno + start}-{fn.lineno + end}', 'cases': cases}
 
 
+def _nmpc_assembly_goldens():
+    """The horizon loop of ``NMPC._setup`` (hilo_mpc/modules/controller/mpc.py, ``for ii in range(self._prediction_horizon)``
+    ... ``time += dt_ii``) executed from its source lines: how the per-interval pieces are assembled into the NLP - the
+    collocation and continuity constraints interval by interval, the sum of the quadratures, the Mayer term at
+    ``time + dt`` of the last interval, the running time, and ``u_old``: the parameter for the first interval, the
+    interval's OWN input afterwards.  The per-interval function is the executed
+    ``RungeKutta._collocation`` (above); the glue that hands it to the loop is this script's."""
+    mpath = os.path.join(REF, 'hilo_mpc', 'util', 'modeling.py')
+    cpath = os.path.join(REF, 'hilo_mpc', 'modules', 'controller', 'mpc.py')
+    opath = os.path.join(REF, 'hilo_mpc', 'modules', 'optimizer.py')
+    ca = _stub_casadi_module()
+    ca.SX = _Vec
+    ca.MX = _Vec
+    ca.Function = _SymFunction
+    ca.vertcat = lambda *a: _Vec([e for v in a for e in np.asarray(v, dtype=object).reshape(-1)])
+    ca.collocation_points = _CaStub.collocation_points
+    ns = {'np': np, 'ca': ca, 'Symbolic': object}
+    body = []
+    for name, deco in (('_construct_polynomial_basis', '@staticmethod'), ('_collocation', '@classmethod')):
+        fsrc, _ = _function_source(mpath, name, cls='RungeKutta')
+        body.append(textwrap.indent(deco + '\n' + fsrc.replace(deco + '\n', ''), '    '))
+    exec('class RungeKutta:\n' + '\n'.join(body), ns)
+    N, deg, nx = 3, 2, 2
+    t, dt = _Vec.sym('t'), _SX.sym('dt_0')
+    x, u, p = _Vec.sym('x', nx), _Vec.sym('u', 1), _Vec.sym('p', 2)        # p = [model parameter, u_old]
+    sin, cos = ca.sin, ca.cos
+    pr = dict(ode=_Vec([x[1] + p[0] * sin(t[0]) * u[0], -x[0] * x[0] * x[1] + cos(x[0]) * u[0] - .3 * t[0]]),
+              alg=_Vec([]), meas=None, t=t, x=x, z=_Vec.sym('z', 0), u=u, p=p, dt=dt,
+              quad=_Vec([x[0] * x[0] + .1 * u[0] * u[0] + x[1] * sin(t[0]) + 5. * (u[0] - p[1]) * (u[0] - p[1])]))
+    ns['RungeKutta']._collocation(pr, degree=deg, collocation_points='radau')
+    ipsyms = _Vec([e for v in pr['collocation_points_ode'] for e in v])
+    stage = _SymFunction('stage', [t, _Vec([dt]), ipsyms, x, u, _Vec([p[0]]), _Vec([p[1]])],
+                         [pr['collocation_equations'], pr['ode'], pr['quad']])
+
+    def int_dynamics_fun(time, dt_ii, ip_ii, x_ii, u_ii, zp_ii, p_ii, e_soft, tv_ref_ii, u_old0):
+        return stage(time, _Vec([dt_ii]), ip_ii, x_ii, u_ii, p_ii, u_old0)
+    tm, xm = _Vec.sym('tm'), _Vec.sym('xm', nx)
+    mayer = _SymFunction('may', [tm, xm], [_Vec([2. * xm[0] * xm[0] + xm[1] * xm[1] + .1 * tm[0] * xm[0]])])
+    # the loop, from the reference
+    lines = open(cpath).read().split('\n')
+    start = next(i for i, ln in enumerate(lines) if ln.strip() == 'for ii in range(self._prediction_horizon):'
+                 and 'x_ii = x[ii, 0]' in lines[i + 1])
+    end = next(i for i in range(start, len(lines)) if lines[i].strip() == 'time += dt_ii')
+    loop = textwrap.dedent('\n'.join(lines[start:end + 1]))
+    rsrc, _ = _function_source(opath, '_rearrange_parameters', cls='DynamicOptimization')
+    exec(rsrc, ns)
+
+    class _Flag:
+        is_set = False
+        is_soft = False
+
+    class _QS:
+        _ind_input_changes = [0]
+
+    class _Self:
+        _prediction_horizon = _control_horizon = N
+        quad_stage_cost = _QS()
+        _nlp_options = {'integration_method': 'collocation', 'objective_function': 'continuous', 'ipopt_debugger': False}
+        _lag_term_flag = _may_term_flag = True
+        _lag_term_fun = None
+        terminal_constraint = stage_constraint = _Flag()
+        _n_tvp = 0
+        _g_indices = {}
+
+        def _may_term_fun(self, tt, xx, tv):
+            return mayer(tt, xx)
+
+        def _rearrange_parameters(self, tvp, cp):
+            return ns['_rearrange_parameters'](self, tvp, cp)
+    xs = np.empty((N + 1, 1), dtype=object)
+    us = np.empty((N, 1), dtype=object)
+    ips = np.empty((N, 1), dtype=object)
+    zps = np.empty((N, 1), dtype=object)
+    for k in range(N + 1):
+        xs[k, 0] = _Vec.sym(f'X{k}', nx)
+    for k in range(N):
+        us[k, 0], ips[k, 0], zps[k, 0] = _Vec.sym(f'U{k}', 1), _Vec.sym(f'C{k}', deg * nx), _Vec([])
+
+    class _Mdl:
+        n_x = nx
+    env = {'np': np, 'ca': ca, 'self': _Self(), 'x': xs, 'u': us, 'ip': ips, 'zp': zps, 'model': _Mdl(),
+           'tv_p': np.empty((0, N), dtype=object), 'c_p': _Vec.sym('CP', 1), 'u_old': _Vec.sym('UOLD', 1),
+           'tv_ref_sc': np.empty((0, N), dtype=object), 'tv_ref_tc': _Vec([]), '_dt': _Vec.sym('PDT', N),
+           'time': _Vec.sym('PTIME'), 'g': [], 'g_lb': [], 'g_ub': [], 'J': 0, 'ind_g': 0,
+           'int_dynamics_fun': int_dynamics_fun, 'e_soft_stage': _Vec([]), 'e_soft_term': _Vec([]),
+           'gk_col_lb': [np.zeros(deg * nx)], 'gk_col_ub': [np.zeros(deg * nx)]}
+    exec(loop, env)
+    gvec = [e for blk in env['g'] for e in np.asarray(blk, dtype=object).reshape(-1)]
+    names = [f'X{k}_{i}' for k in range(N + 1) for i in range(nx)] + [f'U{k}_0' for k in range(N)] + \
+        [f'C{k}_{i}' for k in range(N) for i in range(deg * nx)] + ['CP_0', 'UOLD_0', 'PTIME_0'] + [f'PDT_{k}' for k in range(N)]
+    rng = np.random.RandomState(33)
+    pts = []
+    for _ in range(3):
+        ev = {n: float(rng.normal()) for n in names}
+        ev['PTIME_0'] = float(rng.uniform(0., 2.))
+        for k in range(N):
+            ev[f'PDT_{k}'] = float(rng.uniform(.05, .4))
+        ev0 = dict(ev)
+        pts.append({'env': ev0, 'g': [float(_SX._f(e)(dict(ev0))) for e in gvec],
+                    'J': float(_SX._f(np.asarray(env['J'], dtype=object).reshape(-1)[0])(dict(ev0)))})
+    return {'source': f'hilo_mpc/modules/controller/mpc.py:{start + 1}-{end + 1}', 'N': N, 'degree': deg, 'points': pts,
+            'g_lb_ub_all_zero': bool(all(not np.any(b) for b in env['g_lb']) and all(not np.any(b) for b in env['g_ub'])),
+            'toy': "x0' = x1 + p sin(t) u, x1' = -x0^2 x1 + cos(x0) u - 0.3 t; l = x0^2 + 0.1 u^2 + x1 sin(t) + 5 (u - u_old)^2; "
+                   "Mayer 2 x0^2 + x1^2 + 0.1 t x0"}
+
+
 def _class_source(path, name):
     src = open(path).read()
     tree = ast.parse(src)
@@ -727,6 +835,9 @@ def main():
 
     # ---- the QP matrices LMPC.setup builds (mpc.py)
     out['lmpc_matrices'] = _lmpc_goldens()
+
+    # ---- the horizon loop of NMPC._setup (mpc.py)
+    out['nmpc_assembly'] = _nmpc_assembly_goldens()
 
     with open(OUT, 'w') as f:
         json.dump(out, f)
