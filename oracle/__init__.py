@@ -21,8 +21,8 @@ Parity status:
   ``lhsnorm`` and the PF resampling / roughening / moment block (``pf.py:405-447``), the horizon of time-varying parameter
   values (``mpc.py:293-333``), the equation-string parser (``util/parsing.py``), the export of trained networks
   (``util/machine_learning.py:521-578``), the QP matrices of ``LMPC.setup`` (``mpc.py:2179-2266``) against
-  ``oracle/lmpc.py`` and the product's condensed form, and the horizon loop of ``NMPC._setup`` (objective and constraint
-  vector of the whole NLP) against ``FlatNlp``.
+  ``oracle/lmpc.py`` and the product's condensed form, the horizon loops of ``NMPC._setup`` and ``MHE.setup`` (objective and
+  constraint vector of the whole NLP) against ``FlatNlp`` / ``oracle/independent.py::ReactionMheNlp``.
 * NMPC / LMPC / MHE solves: the reference's tests hold NO numeric assertion for these and IPOPT / qpOASES cannot be run
   here (``casadi`` is not installed) -> "parity unpinned" at the IPOPT/qpOASES boundary only.  The
   oracle restates the transcription exactly and is validated by its own KKT residual, by SciPy's independent

@@ -4,7 +4,7 @@
 ParticleFilter.estimate (pf.py:405-421), the horizon of time-varying parameter values (mpc.py:293-333), the
 equation-string parser (util/parsing.py), the export of trained networks (util/machine_learning.py:521-578) and one
 interval of the collocation / explicit Runge-Kutta transcription (modeling.py:1129-1281), the quadratic cost classes
-(modeling.py:38-818), the QP matrices of LMPC.setup (mpc.py:2179-2266) and the horizon loop of NMPC._setup."""
+(modeling.py:38-818), the QP matrices of LMPC.setup (mpc.py:2179-2266) and the horizon loops of NMPC._setup and MHE.setup."""
 import json
 import os
 
@@ -367,3 +367,29 @@ def test_nmpc_horizon_assembly_equals_the_reference():
         f, _, g, _, _ = cb(v, None)
         np.testing.assert_allclose(g, pt['g'], rtol=1e-12, atol=1e-13)
         np.testing.assert_allclose(f, pt['J'], rtol=1e-12)
+
+
+def test_mhe_horizon_assembly_equals_the_reference():
+    """The horizon loop of ``MHE.setup`` (mhe.py, ``for ii in range(self._horizon)`` ... ``time += dt_ii``) executed from
+    its source lines on the reaction model of the MHE tests, around the executed ``RungeKutta._collocation`` and
+    ``MHEQuadraticCost``: continuity with the additive state noise, arrival cost in interval 0 only, measurement / noise
+    cost from interval 1 on, one parameter variable for the horizon.  ``oracle/independent.py::ReactionMheNlp`` - the
+    product-free restatement that ``tests/test_independent_nlp.py`` ties to the form the engine solves - must give the same
+    objective and constraints."""
+    from oracle.independent import ReactionMheNlp
+    G = GOLD['mhe_assembly']
+    N, deg = G['N'], G['degree']
+    for pt in G['points']:
+        e = pt['env']
+        nlp = ReactionMheNlp(N, G['dt'], [e[f'YM{k}'] for k in range(N)], [e[f'UM{k}'] for k in range(N)],
+                             [e['XA_0'], e['XA_1']], e['PA_0'], degree=deg)
+        v = np.zeros(nlp.n_v)
+        v[0] = e['P_0']
+        for k in range(N + 1):
+            v[nlp.ix(k)] = [e[f'X{k}_0'], e[f'X{k}_1']]
+        for k in range(N):
+            v[nlp.iw(k)] = [e[f'W{k}_0'], e[f'W{k}_1']]
+            for i in range(deg):
+                v[nlp.ic(k, i)] = [e[f'C{k}_{2 * i}'], e[f'C{k}_{2 * i + 1}']]
+        np.testing.assert_allclose(nlp.constraints(v), pt['g'], rtol=1e-12, atol=1e-13)
+        np.testing.assert_allclose(nlp.objective(v), pt['J'], rtol=1e-12)

@@ -17,7 +17,8 @@ the reference tree, executes it unmodified in a namespace with a *stub* ``ca`` (
 * ``GenericCost`` / ``QuadraticCost`` / ``MHEQuadraticCost`` (hilo_mpc/util/modeling.py:38-818) from their class sources on
   stub models, and the matrix-construction lines of ``LMPC.setup`` (mpc.py:2179-2266) with a numeric stub.
 * the horizon loop of ``NMPC._setup`` (mpc.py: ``for ii in range(self._prediction_horizon)`` ... ``time += dt_ii``) around
-  the executed ``RungeKutta._collocation``: objective and constraint vector of the whole NLP.
+  the executed ``RungeKutta._collocation``: objective and constraint vector of the whole NLP; the loop of ``MHE.setup``
+  (mhe.py) the same way on the reaction model of the MHE tests.
 * ``NMPC._get_tvp_parameters_values`` (mpc.py:293-333): the horizon of stored time-varying parameter values iteration by
   iteration, including what it does once the horizon runs past the end of the data.
 
@@ -260,6 +261,24 @@ def _parser_goldens():
     return {'source': 'hilo_mpc/util/parsing.py (whole module, executed with a stub casadi)', 'cases': cases}
 
 
+class _LazyEnv:
+    """Environment with re-bound names: a binding is evaluated (in the outer environment) only when it is looked up, so
+    a substitution of variables the expression does not depend on needs no value for them."""
+
+    def __init__(self, outer, binds):
+        self.outer, self.binds = outer, binds
+
+    def __getitem__(self, name):
+        b = self.binds.get(name)
+        return self.outer[name] if b is None else b(self.outer)
+
+
+def _rebind(e, names, vals):
+    f = _SX._f(e)
+    binds = dict(zip(names, vals))
+    return _SX(lambda env: f(_LazyEnv(env, binds)))
+
+
 class _Vec(np.ndarray):
     """Vector / matrix of ``_SX`` scalars with the few ``casadi.SX`` methods the discretisation routines call."""
 
@@ -300,8 +319,7 @@ class _SymFunction:
             binds += [(n, _SX._f(v)) for n, v in zip(names, vals)]
 
         def rebound(e):
-            f = _SX._f(e)
-            return _SX(lambda env: f({**env, **{n: b(env) for n, b in binds}}))
+            return _rebind(e, [n for n, _ in binds], [b for _, b in binds])
         res = [_Vec([rebound(e) for e in o]) for o in self.outs]
         return res[0] if len(res) == 1 else res
 
@@ -397,8 +415,7 @@ def _quadratic_cost_goldens():
         assert len(names) == len(vals)
 
         def rebound(e):
-            f = _SX._f(e)
-            return _SX(lambda env: f({**env, **{n: v(env) for n, v in zip(names, vals)}}))
+            return _rebind(e, names, vals)
         if isinstance(expr, np.ndarray):
             return _Vec([rebound(e) for e in expr.reshape(-1)])
         return rebound(expr)
@@ -658,6 +675,152 @@ def _nmpc_assembly_goldens():
                    "Mayer 2 x0^2 + x1^2 + 0.1 t x0"}
 
 
+def _mhe_assembly_goldens():
+    """The horizon loop of ``MHE.setup`` (hilo_mpc/modules/estimator/mhe.py, ``for ii in range(self._horizon)`` ...
+    ``time += dt_ii``) executed from its source lines on the reaction model of the MHE tests
+    (ca' = f (1 - ca) - k ca, cb' = k ca - f cb, y = cb), Radau-3, with the arrival and stage cost functions taken from
+    the executed ``MHEQuadraticCost``: continuity with the additive state noise, arrival cost on interval 0 only, stage
+    cost from interval 1 on, one parameter variable for the whole horizon."""
+    mpath = os.path.join(REF, 'hilo_mpc', 'util', 'modeling.py')
+    upath = os.path.join(REF, 'hilo_mpc', 'util', 'util.py')
+    epath = os.path.join(REF, 'hilo_mpc', 'modules', 'estimator', 'mhe.py')
+    ca = _stub_casadi_module()
+
+    class _DM(np.ndarray):
+        def __new__(cls, a=()):
+            return np.asarray(a, dtype=float).view(cls)
+    ca.DM = _DM
+    ca.SX = _Vec
+    ca.MX = _Vec
+    ca.Function = _SymFunction
+    ca.vertcat = lambda *a: _Vec([e for v in a for e in np.asarray(v, dtype=object).reshape(-1)])
+    ca.mtimes = lambda a, b: np.dot(a, b)
+    ca.collocation_points = _CaStub.collocation_points
+    ca.sum1 = lambda a: np.sum(np.asarray(a, dtype=object).reshape(-1))
+
+    def substitute(expr, old, new):
+        names = [sym.name() for sym in np.asarray(old, dtype=object).reshape(-1)]
+        vals = [_SX._f(v) for v in np.asarray(new, dtype=object).reshape(-1)]
+
+        def rebound(e):
+            return _rebind(e, names, vals)
+        if isinstance(expr, np.ndarray):
+            return _Vec([rebound(e) for e in expr.reshape(-1)])
+        return rebound(expr)
+    ca.substitute = substitute
+    ns = {'np': np, 'ca': ca, 'sys': sys, 'Symbolic': object, 'warnings': __import__('warnings')}
+    for name in ('check_and_wrap_to_list', 'check_if_has_duplicates', 'check_if_list_of_type', 'check_if_list_of_none',
+                 'check_if_square', 'who_am_i'):
+        exec(_function_source(upath, name)[0], ns)
+    for name in ('GenericCost', 'MHEQuadraticCost'):
+        exec(_class_source(mpath, name)[0], ns)
+    body = []
+    for name, deco in (('_construct_polynomial_basis', '@staticmethod'), ('_collocation', '@classmethod')):
+        fsrc, _ = _function_source(mpath, name, cls='RungeKutta')
+        body.append(textwrap.indent(deco + '\n' + fsrc.replace(deco + '\n', ''), '    '))
+    exec('class RungeKutta:\n' + '\n'.join(body), ns)
+    N, deg, nx = 4, 3, 2
+
+    class _Names(_Vec):
+        pass
+
+    def named(names):
+        v = _Vec([_SX.sym(n) for n in names]).view(_Names)
+        v._names = list(names)
+        return v
+
+    class _Model:
+        def __init__(self):
+            self.x, self.p, self.u, self.y = named(['ca', 'cb']), named(['k']), named(['f']), named(['y'])
+            self._x, self._p, self._u, self._y = self.x, self.p, self.u, self.y
+            self.dynamical_state_names, self.parameter_names = self.x._names, self.p._names
+            self.input_names, self.measurement_names = self.u._names, self.y._names
+            self.n_x, self.n_p, self.n_u, self.n_y = 2, 1, 1, 1
+            self.meas = _Vec([self.x[1]])
+    mdl = _Model()
+    arr = ns['MHEQuadraticCost'](mdl)
+    arr.add_states(weights=[10., 10.], guess=[.5, .2])
+    arr.add_parameters(weights=[1.], guess=[1.])
+    arr._setup(x_scale=[1., 1.], w_scale=[1., 1.], p_scale=[1.], u_scale=[1.])
+    stg = ns['MHEQuadraticCost'](mdl)
+    stg.add_measurements(weights=[100.])
+    stg.add_state_noise(weights=[20., 20.])
+    stg._setup(x_scale=[1., 1.], w_scale=[1., 1.], p_scale=[1.], u_scale=[1.])
+
+    def syms_of(lst):
+        return _Vec([sym for r in lst for sym in np.asarray(r['placeholder'], dtype=object).reshape(-1)])
+    xarr_ph = _Vec([sym for r in arr._iter_ref_list if r['type'] == 'states' for sym in r['placeholder']])
+    parr_ph = _Vec([sym for r in arr._iter_ref_list if r['type'] == 'parameters' for sym in r['placeholder']])
+    arrival_fun = _SymFunction('arr', [mdl.x, mdl.p, xarr_ph, parr_ph], [_Vec([arr.cost])])
+    stage_fun = _SymFunction('stg', [stg._w, mdl.x, syms_of(stg._tv_ref_list)], [_Vec([stg.cost])])
+    # per-interval collocation of the model (executed reference routine)
+    t, dt = _Vec.sym('t'), _SX.sym('dt_0')
+    xx, uu, pp = _Vec.sym('x', nx), _Vec.sym('u', 1), _Vec.sym('p', 1)
+    pr = dict(ode=_Vec([uu[0] * (1. - xx[0]) - pp[0] * xx[0], pp[0] * xx[0] - uu[0] * xx[1]]), alg=_Vec([]),
+              quad=_Vec([0. * xx[0]]), meas=None, t=t, x=xx, z=_Vec.sym('z', 0), u=uu, p=pp, dt=dt)
+    ns['RungeKutta']._collocation(pr, degree=deg, collocation_points='radau')
+    ipsyms = _Vec([e for v in pr['collocation_points_ode'] for e in v])
+    stage = _SymFunction('stage', [t, _Vec([dt]), ipsyms, xx, uu, pp], [pr['collocation_equations'], pr['ode']])
+
+    def int_dynamics_fun(time, dt_ii, ip_ii, x_ii, u_ii, zp_ii, p_, e_soft, y_ii):
+        return stage(time, _Vec([dt_ii]), ip_ii, x_ii, u_ii, p_)
+    lines = open(epath).read().split('\n')
+    start = next(i for i, ln in enumerate(lines) if ln.strip() == 'for ii in range(self._horizon):'
+                 and 'x_ii = x[ii, 0]' in lines[i + 1])
+    end = next(i for i in range(start, len(lines)) if lines[i].strip() == 'time += dt_ii')
+    loop = textwrap.dedent('\n'.join(lines[start:end + 1]))
+
+    class _Flag:
+        is_set = False
+
+    class _Self:
+        _horizon = N
+        _state_noise_flag = True
+        _nlp_options = {'integration_method': 'collocation'}
+        _arrival_term_flag = _stage_term_flag = True
+        stage_constraint = _Flag()
+
+        def _arrival_term_fun(self, x_ii, p_, xa, pa):
+            return arrival_fun(x_ii, p_, xa, pa)
+
+        def _stage_term_fun(self, w_ii, x_ii, y_ii):
+            return stage_fun(w_ii, x_ii, y_ii)
+    xs, ws = np.empty((N + 1, 1), dtype=object), np.empty((N, 1), dtype=object)
+    ips, zps = np.empty((N, 1), dtype=object), np.empty((N, 1), dtype=object)
+    for k in range(N + 1):
+        xs[k, 0] = _Vec.sym(f'X{k}', nx)
+    for k in range(N):
+        ws[k, 0], ips[k, 0], zps[k, 0] = _Vec.sym(f'W{k}', nx), _Vec.sym(f'C{k}', deg * nx), _Vec([])
+    um = np.empty((1, N), dtype=object)
+    ym = np.empty((1, N), dtype=object)
+    for k in range(N):
+        um[0, k], ym[0, k] = _SX.sym(f'UM{k}'), _SX.sym(f'YM{k}')
+
+    class _Mdl2:
+        n_x = nx
+    dtv, time_now = _Vec.sym('PDT', N), _Vec.sym('PTIME')
+    env = {'np': np, 'ca': ca, 'self': _Self(), 'x': xs, 'w': ws, 'ip': ips, 'zp': zps, 'u_meas': um.view(_Vec),
+           'y_meas': ym.view(_Vec), 'p': _Vec.sym('P', 1), 'model': _Mdl2(), '_dt': dtv, 'x_arrival': _Vec.sym('XA', nx),
+           'p_arrival': _Vec.sym('PA', 1), 'time': time_now - ca.sum1(dtv), 'g': [], 'g_lb': [], 'g_ub': [], 'J': 0,
+           'int_dynamics_fun': int_dynamics_fun, 'e_soft_stage': _Vec([]), 'gk_col_lb': [np.zeros(deg * nx)],
+           'gk_col_ub': [np.zeros(deg * nx)]}
+    exec(loop, env)
+    gvec = [e for blk in env['g'] for e in np.asarray(blk, dtype=object).reshape(-1)]
+    names = ['P_0'] + [f'X{k}_{i}' for k in range(N + 1) for i in range(nx)] + [f'W{k}_{i}' for k in range(N) for i in range(nx)] + \
+        [f'C{k}_{i}' for k in range(N) for i in range(deg * nx)] + [f'UM{k}' for k in range(N)] + [f'YM{k}' for k in range(N)] + \
+        ['XA_0', 'XA_1', 'PA_0', 'PTIME_0']
+    rng = np.random.RandomState(44)
+    pts = []
+    for _ in range(3):
+        ev = {n: float(rng.normal()) for n in names}
+        for k in range(N):
+            ev[f'PDT_{k}'] = .25          # the independent restatement has one dt
+        pts.append({'env': dict(ev), 'g': [float(_SX._f(e)(dict(ev))) for e in gvec],
+                    'J': float(_SX._f(np.asarray(env['J'], dtype=object).reshape(-1)[0])(dict(ev)))})
+    return {'source': f'hilo_mpc/modules/estimator/mhe.py:{start + 1}-{end + 1}', 'N': N, 'degree': deg, 'dt': .25,
+            'points': pts}
+
+
 def _class_source(path, name):
     src = open(path).read()
     tree = ast.parse(src)
@@ -838,6 +1001,9 @@ def main():
 
     # ---- the horizon loop of NMPC._setup (mpc.py)
     out['nmpc_assembly'] = _nmpc_assembly_goldens()
+
+    # ---- the horizon loop of MHE.setup (mhe.py)
+    out['mhe_assembly'] = _mhe_assembly_goldens()
 
     with open(OUT, 'w') as f:
         json.dump(out, f)
