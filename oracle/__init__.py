@@ -22,7 +22,8 @@ Parity status:
   values (``mpc.py:293-333``), the equation-string parser (``util/parsing.py``), the export of trained networks
   (``util/machine_learning.py:521-578``), the QP matrices of ``LMPC.setup`` (``mpc.py:2179-2266``) against
   ``oracle/lmpc.py`` and the product's condensed form, the horizon loops of ``NMPC._setup`` and ``MHE.setup`` (objective and
-  constraint vector of the whole NLP) against ``FlatNlp`` / ``oracle/independent.py::ReactionMheNlp``.
+  constraint vector of the whole NLP) against ``FlatNlp`` / ``oracle/independent.py::ReactionMheNlp``, one predict + update
+  step of the UKF (``kf.py:486-604``) against ``ukf_predict`` / ``ukf_update`` and the kernel body.
 * NMPC / LMPC / MHE solves: the reference's tests hold NO numeric assertion for these and IPOPT / qpOASES cannot be run
   here (``casadi`` is not installed) -> "parity unpinned" at the IPOPT/qpOASES boundary only.  The
   oracle restates the transcription exactly and is validated by its own KKT residual, by SciPy's independent

@@ -4,7 +4,8 @@
 ParticleFilter.estimate (pf.py:405-421), the horizon of time-varying parameter values (mpc.py:293-333), the
 equation-string parser (util/parsing.py), the export of trained networks (util/machine_learning.py:521-578) and one
 interval of the collocation / explicit Runge-Kutta transcription (modeling.py:1129-1281), the quadratic cost classes
-(modeling.py:38-818), the QP matrices of LMPC.setup (mpc.py:2179-2266) and the horizon loops of NMPC._setup and MHE.setup."""
+(modeling.py:38-818), the QP matrices of LMPC.setup (mpc.py:2179-2266), the horizon loops of NMPC._setup and MHE.setup and one UKF step
+(kf.py:486-604)."""
 import json
 import os
 
@@ -393,3 +394,62 @@ def test_mhe_horizon_assembly_equals_the_reference():
                 v[nlp.ic(k, i)] = [e[f'C{k}_{2 * i}'], e[f'C{k}_{2 * i + 1}']]
         np.testing.assert_allclose(nlp.constraints(v), pt['g'], rtol=1e-12, atol=1e-13)
         np.testing.assert_allclose(nlp.objective(v), pt['J'], rtol=1e-12)
+
+
+@pytest.mark.parametrize('case', range(len(GOLD['ukf_step']['cases'])))
+def test_unscented_kalman_filter_step_equals_the_reference(case):
+    """``UnscentedKalmanFilter._setup_parameters / _setup_predict / _setup_update`` (kf.py:486-604) executed from source on
+    numeric matrices with CasADi's shape semantics: weights, sigma points from the columns of the UPPER Cholesky factor,
+    weighted mean / covariance, and the update that re-uses the propagated points - one predict + update step of a
+    3-state bioreactor (explicit-Euler map, two measurements) for three (alpha, beta, kappa) settings.  The oracle's
+    restatement and the kernel body (compiled for the host) must reproduce it."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), 'hostsim'))
+    from est_runner import HostEst
+    from hilo_mpc_b200 import Model
+    from hilo_mpc_b200.estgen import build_est_module
+    from oracle import estimators as est
+    G = GOLD['ukf_step']
+    c, par, dt = G['cases'][case], G['parameters'], G['dt']
+    kw = dict(alpha=c['alpha'], beta=c['beta'], kappa=c['kappa'])
+
+    def f(xc, uc, pc):
+        T, cB, cS = xc
+        r = (par['mu_0'] + par['mu_1'] * T) * cS * cB / (par['K'] + cS)
+        return np.array([T + dt * par['alpha_'] * (par['T_amb'] - T), cB + dt * (r - uc[0] * cB),
+                         cS + dt * (-r / par['Y'] - uc[0] * cS)])
+    hfun = lambda xc, uc, pc: xc[:2]
+    x, P, Q, R, u, y = (np.array(c[k]) for k in ('x', 'P', 'Q', 'R', 'u', 'y'))
+    _, gamma, w = est.ukf_weights(3, **kw)
+    np.testing.assert_allclose(w, c['weights'], rtol=1e-14)
+    np.testing.assert_allclose(gamma, c['gamma'], rtol=1e-14)
+    # alpha = 1e-3 makes the weights +-1e6: the weighted sums cancel six digits, and the reference's running sums, the
+    # oracle's matrix products and the kernel's loops round differently - tolerances scale with |w_0|
+    scale = max(1., abs(w[0, 0]))
+    rt_mean, rt_cov = 1e-11 * scale, max(1e-7, 1e-9 * scale)
+    xp, Pp, X = est.ukf_predict(f, x, P, u, None, Q, discrete=True, **kw)
+    np.testing.assert_allclose(xp, c['x_pred'], rtol=rt_mean)
+    np.testing.assert_allclose(Pp, c['P_pred'], rtol=rt_cov, atol=rt_cov * np.abs(c['P_pred']).max())
+    np.testing.assert_allclose(X, c['X_prop'], rtol=1e-12)
+    xu, Pu, yp = est.ukf_update(hfun, xp, Pp, X, y, u, None, R, **kw)
+    np.testing.assert_allclose(xu, c['x_up'], rtol=max(1e-10, rt_mean))
+    np.testing.assert_allclose(Pu, c['P_up'], rtol=rt_cov, atol=rt_cov * np.abs(c['P_up']).max())
+    np.testing.assert_allclose(yp, c['y_pred'], rtol=rt_mean)
+    # the kernel body on the host
+    m = Model(discrete=True, name='bioreactor_euler')
+    s = m.set_dynamical_states(['T', 'cB', 'cS'])
+    d = m.set_inputs(['D'])
+    m.set_measurements(['yT', 'yB'])
+    r = (par['mu_0'] + par['mu_1'] * s[0]) * s[2] * s[1] / (par['K'] + s[2])
+    m.set_dynamical_equations([s[0] + dt * par['alpha_'] * (par['T_amb'] - s[0]), s[1] + dt * (r - d[0] * s[1]),
+                               s[2] + dt * (-r / par['Y'] - d[0] * s[2])])
+    m.set_measurement_equations([s[0], s[1]])
+    m.setup(dt=dt)
+    h = HostEst(build_est_module(m, hostsim=True))
+    out = h.call('ukf', x, P=P, y=y, u=u, Q=Q, R=R, dt=dt, **kw)
+    assert out['status'][0] == 0
+    np.testing.assert_allclose(out['x'][0], c['x_up'], rtol=max(1e-10, rt_mean))
+    np.testing.assert_allclose(out['P'][0], c['P_up'], rtol=rt_cov, atol=rt_cov * np.abs(c['P_up']).max())
+    np.testing.assert_allclose(out['X'][0].T, c['X_prop'], rtol=1e-12)
+    np.testing.assert_allclose(out['y_pred'][0], c['y_pred'], rtol=rt_mean)

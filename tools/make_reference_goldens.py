@@ -19,6 +19,7 @@ the reference tree, executes it unmodified in a namespace with a *stub* ``ca`` (
 * the horizon loop of ``NMPC._setup`` (mpc.py: ``for ii in range(self._prediction_horizon)`` ... ``time += dt_ii``) around
   the executed ``RungeKutta._collocation``: objective and constraint vector of the whole NLP; the loop of ``MHE.setup``
   (mhe.py) the same way on the reaction model of the MHE tests.
+* ``UnscentedKalmanFilter._setup_parameters / _setup_predict / _setup_update`` (kf.py:486-604) on numeric matrices.
 * ``NMPC._get_tvp_parameters_values`` (mpc.py:293-333): the horizon of stored time-varying parameter values iteration by
   iteration, including what it does once the horizon runs past the end of the data.
 
@@ -821,6 +822,107 @@ def _mhe_assembly_goldens():
             'points': pts}
 
 
+def _ukf_goldens():
+    """``UnscentedKalmanFilter._setup_parameters / _setup_predict / _setup_update`` (hilo_mpc/modules/estimator/kf.py:486-604)
+    executed from their source text.  The routines are straight-line matrix code on their "symbols", so the stub hands
+    them NUMERIC matrices with CasADi's shape semantics (always 2-D, ``X[:, k]`` a column) under the symbols' names and
+    records what they pass to ``ca.Function`` as outputs: the numbers one predict + update step produces.  ``ca.chol`` is
+    the upper factor (R^T R = A), ``ca.solve`` a dense solve.  Model: the 3-state bioreactor of tests/test_KFs.py:695-712
+    as an explicit-Euler discrete map, two measurements."""
+    path = os.path.join(REF, 'hilo_mpc', 'modules', 'estimator', 'kf.py')
+    import warnings
+
+    class _Mx(np.matrix):
+        def name(self):
+            return 'P'
+
+        def numel(self):
+            return self.size
+
+    values = {}
+
+    class _Sym:
+        @staticmethod
+        def sym(name, *shape):
+            return _Mx(np.array(values[name], dtype=float))
+
+        def __new__(cls, v=0):
+            return _Zero()                  # ca.MX(0): the start value of the running sums
+
+    class _Zero:
+        def __add__(self, o):
+            return _Mx(np.array(o, dtype=float))
+        __radd__ = __iadd__ = __add__
+    ca = type('ca', (), {})()
+    ca.SX = ca.MX = _Sym
+    ca.DM = float
+    ca.vertcat = lambda *a: _Mx(np.vstack([np.asarray(v).reshape(-1, 1) for v in a if np.size(v)] or [np.zeros((0, 1))]))
+    ca.horzcat = lambda *a: _Mx(np.hstack([np.asarray(v) for v in a]))
+    ca.chol = lambda a: _Mx(np.linalg.cholesky(np.asarray(a)).T)
+    ca.solve = lambda A, B: _Mx(np.linalg.solve(np.asarray(A), np.asarray(B)))
+    captured = {}
+
+    class _Function:
+        def __init__(self, name, ins, outs, *names):
+            captured[name] = [np.asarray(o).copy() for o in outs]
+    ca.Function = _Function
+    import typing
+    ns = {'np': np, 'ca': ca, 'warnings': warnings, 'Optional': typing.Optional, 'Union': typing.Union}
+    body = []
+    for name in ('_setup_parameters', '_setup_predict', '_setup_update'):
+        fsrc, span = _function_source(path, name, cls='UnscentedKalmanFilter')
+        body.append(textwrap.indent(fsrc, '    '))
+    exec('class UKF:\n' + '\n'.join(body), ns)
+    par = dict(alpha_=.1, T_amb=25., mu_0=.2, mu_1=.01, K=.5, Y=.6)
+    dt = .1
+
+    def f(xc, uc):
+        T, cB, cS = xc
+        r = (par['mu_0'] + par['mu_1'] * T) * cS * cB / (par['K'] + cS)
+        return np.array([T + dt * par['alpha_'] * (par['T_amb'] - T), cB + dt * (r - uc[0] * cB), cS + dt * (-r / par['Y'] - uc[0] * cS)])
+
+    class _Model:
+        n_x, n_u, n_p, n_y = 3, 1, 0, 2
+        dynamical_state_names = ['T', 'cB', 'cS']
+
+        def __call__(self, x0=None, p=None, which=None):
+            X = np.asarray(x0)
+            uc = np.asarray(p).reshape(-1)
+            if which == 'meas_function':
+                return {'yf': _Mx(X[:2, :])}
+            return {'xf': _Mx(np.stack([f(X[:, k], uc) for k in range(X.shape[1])], axis=1))}
+
+    class _Sol:
+        def setup(self, *a, **k):
+            pass
+    cases = []
+    rng = np.random.RandomState(55)
+    for alpha, beta, kappa in ((.5, 2., 0.), (1e-3, 2., 0.), (1., 0., 1.)):
+        obj = ns['UKF']()
+        obj._model, obj._solution = _Model(), _Sol()
+        obj._alpha, obj._beta, obj._kappa = alpha, beta, kappa
+        A = rng.normal(size=(3, 3))
+        x = np.array([30., 1.2, 4.]) + rng.normal(size=3) * .1
+        P = A @ A.T * .01 + np.eye(3) * .02
+        Q, R = np.diag(rng.uniform(1e-4, 1e-3, 3)), np.diag(rng.uniform(1e-3, 1e-2, 2))
+        u, y = np.array([.05 + .01 * rng.normal()]), np.array([30.2, 1.25]) + rng.normal(size=2) * .05
+        values.update({'a': np.eye(3), 'x': x.reshape(-1, 1), 'u': u.reshape(-1, 1), 'p': np.zeros((0, 1)), 'P': P, 'Q': Q})
+        obj._setup_parameters()
+        obj._sqrt = lambda M: ca.chol(M)          # the Function('sqrt', [a], [ca.chol(a)]) built from the placeholder
+        obj._setup_predict()
+        pred = captured['prediction_step'][0]
+        x_pred, P_pred, Xp = pred[:, :1], pred[:, 1:4], pred[:, 4:]
+        values.update({'x': x_pred, 'P': P_pred, 'X': Xp, 'y': y.reshape(-1, 1), 'R': R})
+        obj._setup_update()
+        up, y_pred = captured['update_step']
+        cases.append({'alpha': alpha, 'beta': beta, 'kappa': kappa, 'x': x.tolist(), 'P': P.tolist(), 'Q': Q.tolist(),
+                      'R': R.tolist(), 'u': u.tolist(), 'y': y.tolist(), 'x_pred': x_pred.reshape(-1).tolist(),
+                      'P_pred': P_pred.tolist(), 'X_prop': Xp.tolist(), 'x_up': up[:, 0].tolist(), 'P_up': up[:, 1:].tolist(),
+                      'y_pred': np.asarray(y_pred).reshape(-1).tolist(), 'weights': obj._weights.tolist(),
+                      'gamma': float(obj._gamma)})
+    return {'source': 'hilo_mpc/modules/estimator/kf.py:486-604', 'dt': dt, 'parameters': par, 'cases': cases}
+
+
 def _class_source(path, name):
     src = open(path).read()
     tree = ast.parse(src)
@@ -1004,6 +1106,9 @@ def main():
 
     # ---- the horizon loop of MHE.setup (mhe.py)
     out['mhe_assembly'] = _mhe_assembly_goldens()
+
+    # ---- one predict + update step of the unscented Kalman filter (kf.py)
+    out['ukf_step'] = _ukf_goldens()
 
     with open(OUT, 'w') as f:
         json.dump(out, f)
